@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE — generates ``tests/golden/*.pt`` by running the REAL reference modules.
+
+Run in the dev container only (needs ``/root/reference``):
+
+    python -m oracle.make_golden
+
+For every case the weights (``init_*_params``), the synthetic batch and the initial noise are regenerated from
+seeds by ``oracle/lamslide_oracle.py`` (seeded CPU generators), loaded into the reference's own ``nn.Module``s
+with ``load_state_dict(strict=True)`` (which also pins the state-dict key names/shapes of SURVEY.md §8(b)), and
+the reference's ``sample()`` path (``oracle/ref_loader.reference_sample``: reference Encoder / Decoder /
+LatentSIV3 / Transport / Sampler + the torchdiffeq Euler shim) produces the expected tensors.  Only seeds,
+checksums and expected outputs are stored, so the fixtures stay small; the checksums make a silent RNG
+difference on another box a loud failure instead of a parity mismatch.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from lam_slide_b200.configs import get_config  # noqa: E402
+from oracle import lamslide_oracle as O  # noqa: E402
+from oracle.ref_loader import RefFirstStage, load_reference, reference_sample  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name, config, backbone overrides, B, T, num_steps, seeds(fs, bb, batch, noise)
+CASES = [
+    dict(case="peptide_small", cfg="peptide", overrides=dict(depth=2), B=2, T=24, num_steps=10, seeds=(101, 102, 103, 104)),
+    dict(case="peptide_full", cfg="peptide", overrides={}, B=1, T=1000, num_steps=10, seeds=(111, 112, 113, 114)),
+    dict(case="md17_small", cfg="md17", overrides=dict(depth=2), B=1, T=8, num_steps=5, seeds=(201, 202, 203, 204)),
+    dict(case="md17_full", cfg="md17", overrides={}, B=1, T=30, num_steps=10, seeds=(211, 212, 213, 214)),
+    dict(case="nba_full", cfg="nba", overrides={}, B=3, T=20, num_steps=10, seeds=(301, 302, 303, 304)),
+    dict(case="pedestrian_full", cfg="pedestrian", overrides={}, B=6, T=20, num_steps=10, seeds=(401, 402, 403, 404)),
+    dict(case="peptide_linear_velocity", cfg="peptide", overrides=dict(depth=1), B=1, T=16, num_steps=6,
+         seeds=(121, 122, 123, 124), path_type="Linear", prediction="velocity"),
+]
+
+
+def case_inputs(c: dict):
+    """Everything a test needs to re-create the inputs of a golden case (shared with tests/)."""
+    cfg = get_config(c["cfg"], **c["overrides"])
+    if "path_type" in c:
+        cfg["path_type"], cfg["prediction"] = c["path_type"], c["prediction"]
+    s_fs, s_bb, s_batch, s_noise = c["seeds"]
+    fs_sd = O.init_first_stage_params(cfg["first_stage"], s_fs)
+    bb_sd = O.init_backbone_params(cfg["backbone"], s_bb)
+    batch = O.synthetic_batch(cfg, c["B"], s_batch, T=c["T"])
+    g = torch.Generator().manual_seed(s_noise)
+    L = cfg["first_stage"]["encoder"]["num_latents"]
+    noise = torch.randn(c["B"], c["T"], L, cfg["backbone"]["in_dim"], generator=g)
+    y = None
+    if cfg["n_classes"]:
+        table = torch.randn(cfg["n_classes"], 256, generator=g)  # CondWrapper.vec_in_embedding (nba.py:254-263)
+        y = table[batch["cond_scene"]]
+    return cfg, fs_sd, bb_sd, batch, noise, y
+
+
+def main() -> None:
+    ref = load_reference()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    for c in CASES:
+        cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)
+        bb = cfg["backbone"]
+        fs = RefFirstStage(cfg["first_stage"]).eval()
+        fs.load_state_dict(fs_sd, strict=True)
+        net = ref.LatentSIV3(depth=bb["depth"], in_dim=bb["in_dim"], hidden_size=bb["hidden_size"],
+                             num_heads=bb["num_heads"], vec_in_dim=bb["vec_in_dim"], mlp_ratio=bb["mlp_ratio"],
+                             normalize=bb["normalize"], theta=bb["theta"]).eval()
+        net.load_state_dict(bb_sd, strict=True)
+        rec: dict = {}
+        out = reference_sample(fs, net, {k: v.clone() for k, v in batch.items()}, cond_idx=cfg["cond_idx"],
+                               path_type=cfg["path_type"], prediction=cfg["prediction"], num_steps=c["num_steps"],
+                               noise=noise, y=y, mask_cond_mean=cfg["mask_cond_mean"], record=rec)
+        # single backbone evaluation at the first grid point (the per-op parity anchor)
+        t0, _ = O.sample_interval(cfg["path_type"], cfg["prediction"])
+        tt = torch.full((c["B"],), t0)
+        kw = dict(x_cond=rec["x_cond"], x_cond_mask=rec["x_cond_mask"])
+        if y is not None:
+            kw["y"] = y
+        with torch.no_grad():
+            net_out = net(x=noise, t=tt, **kw)
+        big = c["T"] > 100
+        sl = slice(None, None, 20) if big else slice(None)
+        heavy = rec["latents"][:, sl].numel() > 100_000  # MD17: L=192 ⇒ keep first/last velocity only
+        vsel = [0, c["num_steps"] - 2] if heavy else list(range(c["num_steps"] - 1))
+        fixture = dict(
+            case={k: v for k, v in c.items()},
+            checksums=dict(fs=O.state_checksum(fs_sd), bb=O.state_checksum(bb_sd),
+                           batch=O.state_checksum({k: v.float() for k, v in batch.items()}),
+                           noise=float(noise.double().sum())),
+            latents=rec["latents"][:, sl].clone(),
+            x_cond=None if heavy else rec["x_cond"][:, sl].clone(),
+            net_out_t0=net_out[:, sl].clone(),
+            velocities=rec["velocities"][vsel][:, :, sl].clone(),
+            velocity_steps=vsel,
+            final_latents=rec["states"][-1].clone() if not big else rec["states"][-1][:, sl].clone(),
+            outputs={k: v[:, sl].clone() for k, v in out.items()},
+            frame_slice=(sl.start, sl.stop, sl.step),
+            torch_version=torch.__version__,
+        )
+        path = os.path.join(GOLDEN_DIR, c["case"] + ".pt")
+        torch.save(fixture, path)
+        print(f"{c['case']:28s} -> {os.path.getsize(path) / 1024:8.1f} KiB   vel max {float(rec['velocities'].abs().max()):.3f}")
+
+
+if __name__ == "__main__":
+    main()

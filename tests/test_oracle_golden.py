@@ -1,0 +1,86 @@
+"""CPU: the oracle restatement reproduces the golden vectors generated from the real reference modules
+(oracle/make_golden.py).  fp32 vs fp32, so the tolerance is rounding only."""
+import pytest
+import torch
+
+from oracle import lamslide_oracle as O
+from tests.helpers import CASE_BY_NAME, case_inputs, check_inputs_match_fixture, frame_slice, load_golden, max_rel
+
+FAST = ["peptide_small", "md17_small", "nba_full", "pedestrian_full", "peptide_linear_velocity", "md17_full", "peptide_full"]
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_oracle_matches_reference_golden(name):
+    torch.set_num_threads(8)
+    fx = load_golden(name)
+    c = CASE_BY_NAME[name]
+    cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)
+    check_inputs_match_fixture(fx, fs_sd, bb_sd, batch, noise)
+    rec = {}
+    with torch.no_grad():
+        out = O.sample(fs_sd, bb_sd, cfg, batch, noise, num_steps=c["num_steps"], y=y, record=rec)
+    sl = frame_slice(fx)
+    assert max_rel(rec["latents"][:, sl], fx["latents"]) < 1e-5
+    if fx["x_cond"] is not None:
+        assert max_rel(rec["x_cond"][:, sl], fx["x_cond"]) < 1e-5
+    vel = rec["velocities"][fx["velocity_steps"]][:, :, sl]
+    assert max_rel(vel, fx["velocities"]) < 2e-4  # (π/2)/cos(πt/2) amplifies fp32 rounding ≈ 30×
+    assert max_rel(rec["states"][-1][:, sl], fx["final_latents"]) < 1e-4
+    for k, v in fx["outputs"].items():
+        assert max_rel(out[k][:, sl], v) < 1e-4
+
+
+def test_backbone_single_eval_matches_golden():
+    fx = load_golden("nba_full")
+    c = CASE_BY_NAME["nba_full"]
+    cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)
+    with torch.no_grad():
+        flat = {k: v.flatten(0, 1) for k, v in batch.items() if k != "cond_scene"}
+        lat = O.first_stage_encode(fs_sd, cfg["first_stage"], flat).unflatten(0, (c["B"], c["T"]))
+        x_cond, m = O.setup_conditioning(lat, cfg["cond_idx"], True)
+        t0, _ = O.sample_interval(cfg["path_type"], cfg["prediction"])
+        out = O.backbone_forward(bb_sd, cfg["backbone"], noise, torch.full((c["B"],), t0), x_cond, m, y)
+    assert max_rel(out, fx["net_out_t0"]) < 1e-5
+
+
+def test_euler_grid_and_eval_count():
+    """num_steps=n makes n-1 model calls on linspace(t0,t1,n) (integrators.py:98)."""
+    calls = []
+
+    def fn(x, t):
+        calls.append(float(t[0]))
+        return torch.zeros_like(x)
+
+    O.ode_sample(fn, torch.zeros(2, 3, 1, 4), path_type="GVP", prediction="data", num_steps=10)
+    assert len(calls) == 9
+    assert abs(calls[0] - 0.001) < 1e-7 and abs(calls[-1] - 0.8881111) < 1e-5
+    calls.clear()
+    O.ode_sample(fn, torch.zeros(2, 3, 1, 4), path_type="Linear", prediction="velocity", num_steps=10)
+    assert len(calls) == 9 and calls[0] == 0.0 and abs(calls[-1] - 8 / 9) < 1e-6
+
+
+def test_gvp_data_drift_closed_form():
+    """v = (π/2)(m − sin(a)x)/cos(a), a = πt/2."""
+    import math
+    g = torch.Generator().manual_seed(0)
+    x, m = torch.randn(4, 5, 2, 8, generator=g, dtype=torch.float64), torch.randn(4, 5, 2, 8, generator=g, dtype=torch.float64)
+    t = torch.tensor([0.001, 0.3, 0.7, 0.8881], dtype=torch.float64)
+    a = (math.pi * t / 2).reshape(-1, 1, 1, 1)
+    closed = (math.pi / 2) * (m - torch.sin(a) * x) / torch.cos(a)
+    assert max_rel(O.drift("GVP", "data", x, t, m), closed) < 1e-12
+
+
+def test_masked_padding_is_exact():
+    """Encoder output with zero-padded entities + key mask == un-padded call."""
+    from lam_slide_b200.configs import get_config
+    cfg = get_config("pedestrian")
+    sd = O.init_first_stage_params(cfg["first_stage"], 7)
+    g = torch.Generator().manual_seed(1)
+    pos = torch.randn(5, 4, 2, generator=g)
+    ent = torch.stack([torch.randperm(10, generator=g)[:4] for _ in range(5)])
+    small = dict(pos=pos, entities=ent, attention_mask=torch.ones(5, 4, dtype=torch.bool))
+    pad = dict(pos=torch.cat([pos, torch.zeros(5, 6, 2)], 1), entities=torch.cat([ent, torch.zeros(5, 6, dtype=torch.int64)], 1),
+               attention_mask=torch.cat([torch.ones(5, 4, dtype=torch.bool), torch.zeros(5, 6, dtype=torch.bool)], 1))
+    a = O.first_stage_encode(sd, cfg["first_stage"], small)
+    b = O.first_stage_encode(sd, cfg["first_stage"], pad)
+    assert max_rel(a, b) < 1e-6

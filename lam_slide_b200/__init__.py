@@ -1,0 +1,13 @@
+"""lam_slide_b200 — B200-native (sm_100a) implementation of LaM-SLidE's sampling hot path.
+
+Public surface (mirrors the reference's interfaces for this path; see DESIGN.md / INTEGRATION.md):
+    LatentSIV3            second-stage latent transformer          (latent_si_v31.py)
+    FirstStage            BackboneBase + Encoder/Decoder           (lightning_base.py, encoder.py, decoder.py)
+    CreateTransport, Sampler                                       (src/modules/transport)
+    SecondStageSampler    encode -> conditioning -> Euler ODE -> decode  (SecondStageCondLightningBase.sample)
+"""
+from .backbone import LatentSIV3  # noqa: F401
+from .configs import CONFIGS, get_config  # noqa: F401
+from .first_stage import FirstStage  # noqa: F401
+from .model import SecondStageSampler  # noqa: F401
+from .transport import CreateTransport, Sampler, Transport  # noqa: F401

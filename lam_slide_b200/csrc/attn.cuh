@@ -1,0 +1,276 @@
+// Attention kernels of the second-stage transformer (mmdit.py:42-55: softmax(q k^T / sqrt(hd)) v, no mask).
+// q and k arrive already RMS-normalised + rotated, and q pre-multiplied by hd^-0.5 * log2(e), from the linear1 GEMM
+// epilogue, so both kernels work in the exp2 domain.
+//
+//   attn_flash_kernel : flash-style streaming softmax over long sequences (temporal axis, S = T up to 1000; spatial axis
+//                       when L is large, e.g. MD17 L = 192).  128 queries per CTA (8 warps x 16 rows), 64-key K/V tiles
+//                       double-buffered in shared memory with cp.async, QK^T and PV on warp-level bf16 MMA
+//                       (m16n8k16, fp32 accumulate), softmax statistics in fp32 registers.  The kernel is bound by
+//                       MUFU.EX2 (S*S exps per head), not by the tensor pipe: hd = 16/24/32 gives only ~100 tensor
+//                       FLOPs per exp.
+//   attn_small_kernel : S <= 32 (4AA / pedestrian L = 2, NBA L = 8): one thread per (token, head).
+//
+// Sequence addressing (token-major qkv [tokens, 3H], (K=3, heads, hd) feature order):
+//   sequence z -> base token = (z / inner) * outer_stride + (z % inner) * inner_stride,  token(s) = base + s * seq_stride
+//   temporal: inner = L, outer_stride = T*L, inner_stride = 1, seq_stride = L;  spatial: inner = 1, outer_stride = L, seq_stride = 1
+#pragma once
+#include "ptx.cuh"
+
+namespace lam {
+
+struct SeqMap {
+  int S, inner, outer_stride, inner_stride, seq_stride;
+  __device__ __forceinline__ long long base(int z) const {
+    return (long long)(z / inner) * outer_stride + (long long)(z % inner) * inner_stride;
+  }
+};
+
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, SeqMap sm, int n_qtiles) {
+  constexpr int HDP = (HD == 24) ? 32 : HD;  // contraction dim of QK^T padded to a multiple of 16
+  constexpr int KSTEPS = HDP / 16;
+  constexpr int PITCH = HDP + 8;  // bf16 elements; 80 B / 48 B row pitch: conflict-free fragment loads and ldmatrix
+  constexpr int KT = 64;          // keys per tile
+  constexpr int QT = 128;         // queries per CTA
+  constexpr int CH = HD / 8;      // 16-byte chunks per row that carry data
+  constexpr int CHP = HDP / 8;    // chunks per K row incl. zero padding
+
+  __shared__ __align__(16) __nv_bfloat16 Ks[2][KT][PITCH];
+  __shared__ __align__(16) __nv_bfloat16 Vs[2][KT][PITCH];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int z = blockIdx.x / n_qtiles;
+  const int qt = blockIdx.x % n_qtiles;
+  const int hh = blockIdx.y;
+  const int S = sm.S;
+  const long long base = sm.base(z);
+  const size_t ldq = (size_t)3 * H;
+  const __nv_bfloat16* qptr = qkv + hh * HD;
+  const __nv_bfloat16* kptr = qkv + H + hh * HD;
+  const __nv_bfloat16* vptr = qkv + 2 * H + hh * HD;
+
+  auto load_tile = [&](int kt, int buf) {
+    for (int idx = tid; idx < KT * CHP; idx += 256) {
+      int r = idx / CHP, c = idx % CHP;
+      int s = kt * KT + r;
+      bool ok = (s < S) && (c < CH);
+      size_t tok = (size_t)(base + (long long)(ok ? s : 0) * sm.seq_stride);
+      cp_async16(&Ks[buf][r][c * 8], kptr + tok * ldq + (c < CH ? c : 0) * 8, ok);
+    }
+    for (int idx = tid; idx < KT * CH; idx += 256) {
+      int r = idx / CH, c = idx % CH;
+      int s = kt * KT + r;
+      bool ok = s < S;
+      size_t tok = (size_t)(base + (long long)(ok ? s : 0) * sm.seq_stride);
+      cp_async16(&Vs[buf][r][c * 8], vptr + tok * ldq + c * 8, ok);
+    }
+    cp_async_commit();
+  };
+
+  const int nkt = (S + KT - 1) / KT;
+  load_tile(0, 0);
+
+  // Q fragments straight from global memory (read once)
+  const int q0 = qt * QT + warp * 16 + g;  // rows q0 and q0 + 8
+  uint32_t aq[KSTEPS][4];
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int row = q0 + (i & 1) * 8;
+      int d = ks * 16 + (i >> 1) * 8 + t * 2;
+      uint32_t v = 0;
+      if (row < S && d < HD) {
+        size_t tok = (size_t)(base + (long long)row * sm.seq_stride);
+        v = *reinterpret_cast<const uint32_t*>(qptr + tok * ldq + d);
+      }
+      aq[ks][i] = v;
+    }
+  }
+
+  float m_i[2] = {-INFINITY, -INFINITY};
+  float l_i[2] = {0.f, 0.f};
+  float o[HD / 8][4];
+#pragma unroll
+  for (int d = 0; d < HD / 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    cp_async_wait<0>();
+    __syncthreads();  // tile kt visible to all warps; every warp is done with tile kt-1 (buffer buf^1)
+    if (kt + 1 < nkt) load_tile(kt + 1, buf ^ 1);
+
+    float s[KT / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < KT / 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[buf][nt * 8 + g][ks * 16 + t * 2]);
+        uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[buf][nt * 8 + g][ks * 16 + 8 + t * 2]);
+        mma_bf16_16816(s[nt], aq[ks], b0, b1);
+      }
+    }
+    if (kt == nkt - 1) {
+#pragma unroll
+      for (int nt = 0; nt < KT / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int key = kt * KT + nt * 8 + t * 2 + (e & 1);
+          if (key >= S) s[nt][e] = -INFINITY;
+        }
+      }
+    }
+    // online softmax (rows g: e = 0,1; rows g+8: e = 2,3)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < KT / 8; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mnew[r] = fmaxf(m_i[r], mx[r]);
+      corr[r] = fast_exp2(m_i[r] - mnew[r]);
+      m_i[r] = mnew[r];
+      l_i[r] *= corr[r];
+    }
+#pragma unroll
+    for (int d = 0; d < HD / 8; ++d) {
+      o[d][0] *= corr[0], o[d][1] *= corr[0];
+      o[d][2] *= corr[1], o[d][3] *= corr[1];
+    }
+#pragma unroll
+    for (int nt = 0; nt < KT / 8; ++nt) {
+      s[nt][0] = fast_exp2(s[nt][0] - mnew[0]);
+      s[nt][1] = fast_exp2(s[nt][1] - mnew[0]);
+      s[nt][2] = fast_exp2(s[nt][2] - mnew[1]);
+      s[nt][3] = fast_exp2(s[nt][3] - mnew[1]);
+      l_i[0] += s[nt][0] + s[nt][1];
+      l_i[1] += s[nt][2] + s[nt][3];
+    }
+    // O += P V
+#pragma unroll
+    for (int j = 0; j < KT / 16; ++j) {
+      uint32_t ap[4];
+      ap[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      ap[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      ap[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      ap[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+      for (int d = 0; d < HD / 8; ++d) {
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, smem_u32(&Vs[buf][j * 16 + (lane & 15)][d * 8]));
+        mma_bf16_16816(o[d], ap, b0, b1);
+      }
+    }
+  }
+
+  // finalize: full row sums across the quad, normalise, store bf16
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
+    l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
+  }
+  const float inv0 = 1.f / l_i[0], inv1 = 1.f / l_i[1];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    int row = q0 + r * 8;
+    if (row < S) {
+      size_t tok = (size_t)(base + (long long)row * sm.seq_stride);
+      __nv_bfloat16* op = out + tok * ldo + hh * HD + t * 2;
+      float inv = r ? inv1 : inv0;
+#pragma unroll
+      for (int d = 0; d < HD / 8; ++d)
+        *reinterpret_cast<uint32_t*>(op + d * 8) = pack_bf16x2(o[d][2 * r] * inv, o[d][2 * r + 1] * inv);
+    }
+  }
+}
+
+// One thread per (token, head); S <= 32 keys, contiguous or strided.  Online softmax in the exp2 domain.
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_small_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, int heads, SeqMap sm,
+                  long long n_items) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_items) return;
+  const int hh = (int)(idx % heads);
+  long long rest = idx / heads;
+  const int s_q = (int)(rest % sm.S);
+  const int z = (int)(rest / sm.S);
+  const long long base = sm.base(z);
+  const size_t ldq = (size_t)3 * H;
+  const size_t tok_q = (size_t)(base + (long long)s_q * sm.seq_stride);
+
+  float q[HD], acc[HD];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + tok_q * ldq + hh * HD);
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      uint4 v = __ldg(qp + c);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h2[i]);
+        q[c * 8 + 2 * i] = f.x, q[c * 8 + 2 * i + 1] = f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int s = 0; s < sm.S; ++s) {
+    const size_t tok = (size_t)(base + (long long)s * sm.seq_stride);
+    const uint4* kp = reinterpret_cast<const uint4*>(qkv + tok * ldq + H + hh * HD);
+    const uint4* vp = reinterpret_cast<const uint4*>(qkv + tok * ldq + 2 * H + hh * HD);
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      uint4 v = __ldg(kp + c);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h2[i]);
+        dot = fmaf(q[c * 8 + 2 * i], f.x, dot);
+        dot = fmaf(q[c * 8 + 2 * i + 1], f.y, dot);
+      }
+    }
+    const float mn = fmaxf(m, dot);
+    const float corr = fast_exp2(m - mn);
+    const float p = fast_exp2(dot - mn);
+    m = mn;
+    l = l * corr + p;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      uint4 v = __ldg(vp + c);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h2[i]);
+        acc[c * 8 + 2 * i] = fmaf(p, f.x, acc[c * 8 + 2 * i] * corr);
+        acc[c * 8 + 2 * i + 1] = fmaf(p, f.y, acc[c * 8 + 2 * i + 1] * corr);
+      }
+    }
+  }
+  const float inv = 1.f / l;
+  uint4* op = reinterpret_cast<uint4*>(out + tok_q * ldo + hh * HD);
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    uint4 v;
+    v.x = pack_bf16x2(acc[c * 8 + 0] * inv, acc[c * 8 + 1] * inv);
+    v.y = pack_bf16x2(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
+    v.z = pack_bf16x2(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
+    v.w = pack_bf16x2(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
+    op[c] = v;
+  }
+}
+
+}  // namespace lam

@@ -1,0 +1,235 @@
+// Vectorised / warp-shuffle kernels around the GEMMs of the second stage: input embedding, the per-sample vector path
+// (timestep embedding -> time_in [+ vec_in] -> all adaLN modulations), LayerNorm+modulate, drift + Euler update,
+// conditioning, RoPE tables.  All statistics and the ODE state stay in fp32.
+#pragma once
+#include "ptx.cuh"
+
+namespace lam {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+// ---- RoPE tables (mmdit.py:75-82): angle = p * theta^(-2i/hd) in fp64, cos/sin stored fp32 [S, hd/2]
+__global__ void rope_table_kernel(float* __restrict__ cs, float* __restrict__ sn, int S, int half, double theta) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * half) return;
+  int p = idx / half, i = idx % half;
+  double omega = 1.0 / pow(theta, (double)(2 * i) / (double)(2 * half));
+  double a = (double)p * omega;
+  cs[idx] = (float)cos(a);
+  sn[idx] = (float)sin(a);
+}
+
+// ---- timestep_embedding (mmdit.py:93-113): e = cat[cos(1000 t f), sin(1000 t f)], f_i = exp(-ln(1e4) i / 128); [B, 256]
+__global__ void timestep_embed_kernel(const float* __restrict__ t, float* __restrict__ e, int B) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 128) return;
+  int b = idx / 128, i = idx % 128;
+  float f = expf(-9.210340371976184f * (float)i / 128.0f);
+  float arg = (1000.0f * t[b]) * f;
+  e[b * 256 + i] = cosf(arg);
+  e[b * 256 + 128 + i] = sinf(arg);
+}
+
+// ---- small dense layer on per-sample vectors: out[b, n] = post( sum_k pre(in[b, k]) * W[n, k] + bias[n] ) (+ add[b, n])
+// One warp per output column, 8 samples per block staged in shared memory.  pre/post: 0 = identity, 1 = SiLU.
+__global__ void __launch_bounds__(256)
+vec_linear_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ W, const float* __restrict__ bias,
+                  const float* __restrict__ add, float* __restrict__ out, int ldo, int B, int N, int K, int pre, int post) {
+  extern __shared__ float xs[];  // [8][K]
+  const int b0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 8 * K; i += 256) {
+    int bb = i / K, k = i % K;
+    float v = (b0 + bb < B) ? in[(size_t)(b0 + bb) * ldi + k] : 0.f;
+    xs[i] = pre == 1 ? silu_f(v) : v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float w = __ldg(W + (size_t)n * K + k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, xs[i * K + k], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane < 8 && b0 + lane < B) {
+    float v = acc[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) v = (lane == i) ? acc[i] : v;
+    v += bias ? bias[n] : 0.f;
+    if (post == 1) v = silu_f(v);
+    if (add) v += add[(size_t)(b0 + lane) * ldo + n];
+    out[(size_t)(b0 + lane) * ldo + n] = v;
+  }
+}
+
+// ---- input embedding (latent_si_v31.py:172-174): h = x Wx^T + x_cond Wc^T + (bx + bc) + E_mask[m]
+// Wt is the pre-transposed, concatenated weight [2D, H] (k-major so a warp reads consecutive output columns).
+// 32 tokens per block; each thread owns output columns tid and tid + 256.
+template <int NCOL>
+__global__ void __launch_bounds__(256)
+embed_in_kernel(const float* __restrict__ x, const float* __restrict__ xc, const long long* __restrict__ mask,
+                const float* __restrict__ Wt, const float* __restrict__ bias, const float* __restrict__ emask,
+                float* __restrict__ h, int n_tok, int D, int H) {
+  extern __shared__ float xs[];  // [2D][36]
+  const int tok0 = blockIdx.x * 32;
+  const int K2 = 2 * D;
+  for (int i = threadIdx.x; i < 32 * K2; i += 256) {
+    int tt = i / K2, k = i % K2;
+    int tok = tok0 + tt;
+    float v = 0.f;
+    if (tok < n_tok) v = k < D ? x[(size_t)tok * D + k] : xc[(size_t)tok * D + (k - D)];
+    xs[k * 36 + tt] = v;
+  }
+  __syncthreads();
+  float acc[NCOL][32];
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[c][i] = 0.f;
+  int col[NCOL];
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c) col[c] = threadIdx.x + c * 256;
+  for (int k = 0; k < K2; ++k) {
+    float w[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) w[c] = col[c] < H ? __ldg(Wt + (size_t)k * H + col[c]) : 0.f;
+    const float4* xr = reinterpret_cast<const float4*>(xs + k * 36);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = xr[i];
+#pragma unroll
+      for (int c = 0; c < NCOL; ++c) {
+        acc[c][4 * i + 0] = fmaf(w[c], v.x, acc[c][4 * i + 0]);
+        acc[c][4 * i + 1] = fmaf(w[c], v.y, acc[c][4 * i + 1]);
+        acc[c][4 * i + 2] = fmaf(w[c], v.z, acc[c][4 * i + 2]);
+        acc[c][4 * i + 3] = fmaf(w[c], v.w, acc[c][4 * i + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c) {
+    if (col[c] >= H) continue;
+    const float bj = bias[col[c]];
+    const float e0 = emask[col[c]], e1 = emask[H + col[c]];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      int tok = tok0 + i;
+      if (tok < n_tok) h[(size_t)tok * H + col[c]] = acc[c][i] + bj + (mask[tok] ? e1 : e0);
+    }
+  }
+}
+
+// ---- in-place LayerNorm without affine over rows of width H (F.layer_norm at latent_si_v31.py:174, eps 1e-5); warp per row
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(float* __restrict__ h, int rows, int H, float eps) {
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* p = h + (size_t)row * H;
+  float s = 0.f;
+  for (int j = lane; j < H; j += 32) s += p[j];
+  float mean = warp_sum(s) / H;
+  float v = 0.f;
+  for (int j = lane; j < H; j += 32) {
+    float d = p[j] - mean;
+    v = fmaf(d, d, v);
+  }
+  float rstd = rsqrtf(warp_sum(v) / H + eps);
+  for (int j = lane; j < H; j += 32) p[j] = (p[j] - mean) * rstd;
+}
+
+// ---- LayerNorm (no affine, eps 1e-6) + adaLN modulate (mmdit.py:21-22) -> bf16 A operand of the next GEMM
+//   u[row, :] = LN(h[row, :]) * (1 + scale[b, :]) + shift[b, :],  b = row / rows_per_sample;  warp per row, H = 128 * HV
+template <int HV>
+__global__ void __launch_bounds__(256)
+ln_modulate_kernel(const float* __restrict__ h, __nv_bfloat16* __restrict__ u, const float* __restrict__ shift,
+                   const float* __restrict__ scale, int mod_stride, int rows, int rows_per_sample) {
+  constexpr int H = HV * 128;
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* p = reinterpret_cast<const float4*>(h + (size_t)row * H);
+  float4 v[HV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < HV; ++i) {
+    v[i] = p[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < HV; ++i) {
+    v[i].x -= mean, v[i].y -= mean, v[i].z -= mean, v[i].w -= mean;
+    q = fmaf(v[i].x, v[i].x, q), q = fmaf(v[i].y, v[i].y, q), q = fmaf(v[i].z, v[i].z, q), q = fmaf(v[i].w, v[i].w, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + 1e-6f);
+  const int b = row / rows_per_sample;
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
+  uint2* up = reinterpret_cast<uint2*>(u + (size_t)row * H);
+#pragma unroll
+  for (int i = 0; i < HV; ++i) {
+    float4 a = __ldg(sc + lane + 32 * i), c = __ldg(sh + lane + 32 * i);
+    float y0 = fmaf(v[i].x * rstd, 1.0f + a.x, c.x);
+    float y1 = fmaf(v[i].y * rstd, 1.0f + a.y, c.y);
+    float y2 = fmaf(v[i].z * rstd, 1.0f + a.z, c.z);
+    float y3 = fmaf(v[i].w * rstd, 1.0f + a.w, c.w);
+    up[lane + 32 * i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
+// ---- probability-flow drift + explicit Euler (transport.py:158-202, integrators.py:119 / torchdiffeq fixed grid)
+// Every drift of the reference is linear in (net output m, state x) with time-only coefficients, computed on the host
+// in fp64:  v = cm * m + cx * x;   x <- x + dt * v.   Optionally records v and the new state.
+__global__ void __launch_bounds__(256)
+drift_euler_kernel(const float4* __restrict__ m, float4* __restrict__ x, float4* __restrict__ v_out, float4* __restrict__ state_out,
+                   float cm, float cx, float dt, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 mv = m[i], xv = x[i], v;
+  v.x = fmaf(cm, mv.x, cx * xv.x), v.y = fmaf(cm, mv.y, cx * xv.y);
+  v.z = fmaf(cm, mv.z, cx * xv.z), v.w = fmaf(cm, mv.w, cx * xv.w);
+  xv.x = fmaf(dt, v.x, xv.x), xv.y = fmaf(dt, v.y, xv.y), xv.z = fmaf(dt, v.z, xv.z), xv.w = fmaf(dt, v.w, xv.w);
+  x[i] = xv;
+  if (v_out) v_out[i] = v;
+  if (state_out) state_out[i] = xv;
+}
+
+// ---- setup_conditioning (lightning_base.py:240-263): mask[:, c0:c1] = 1; x_cond = where(mask, latents, mean_{t in cond} latents | 0)
+__global__ void __launch_bounds__(256)
+conditioning_kernel(const float* __restrict__ lat, float* __restrict__ x_cond, long long* __restrict__ mask, int B, int T, int L,
+                    int D, int c0, int c1, int use_mean) {
+  // one thread per (b, l, d); loops over T
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)B * L * D;
+  if (idx >= tot) return;
+  int d = (int)(idx % D);
+  int l = (int)((idx / D) % L);
+  int b = (int)(idx / ((long long)D * L));
+  const size_t s_t = (size_t)L * D;
+  const float* p = lat + (size_t)b * T * s_t + (size_t)l * D + d;
+  float fill = 0.f;
+  if (use_mean) {
+    float s = 0.f;
+    for (int t = c0; t < c1; ++t) s += p[(size_t)t * s_t];
+    fill = s / (float)(c1 - c0);
+  }
+  float* o = x_cond + (size_t)b * T * s_t + (size_t)l * D + d;
+  for (int t = 0; t < T; ++t) {
+    bool c = t >= c0 && t < c1;
+    o[(size_t)t * s_t] = c ? p[(size_t)t * s_t] : fill;
+    if (d == 0) mask[((size_t)b * T + t) * L + l] = c ? 1 : 0;
+  }
+}
+
+}  // namespace lam

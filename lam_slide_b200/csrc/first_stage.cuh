@@ -1,0 +1,232 @@
+// fp32 kernels of the UPT-style first stage (encoder.py, decoder.py, torch_modules.py): small per-entity MLPs,
+// LayerNorms, entity-ID embedding gathers and the (masked) entity cross-attention / latent self-attention.
+// The first stage is ~0.3 % of the trajectory FLOPs; it is kept in fp32 on the FMA pipe so that the
+// latents that condition the ODE carry no bf16 rounding.  Rows = frames x tokens-per-frame.
+#pragma once
+#include "elementwise.cuh"
+
+namespace lam {
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// ---- Y[r, n] = epi( sum_k X[r, k] W[n, k] + bias[n] )   64x64 tile, 16-deep k slices, 4x4 outputs per thread.
+//   epi: optional GELU, optional + rowadd[(r % rowadd_period), n], optional + res[r, n]
+struct LinearArgs {
+  const float* X; int ldx;
+  const float* W;      // [N, K] (nn.Linear layout)
+  const float* bias;   // [N] or null
+  float* Y; int ldy;
+  const float* res; int ldr;        // residual or null
+  const float* rowadd; int rowadd_period; int ldra;  // e.g. sin/cos residue-index embedding, or null
+  int rows, N, K;
+  int gelu;
+};
+
+__global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs a) {
+  __shared__ float Xs[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int ty = tid / 16, tx = tid % 16;  // thread computes rows ty*4..+3, cols tx*4..+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < a.K; k0 += 16) {
+    // 64 x 16 tiles of X and W, 4 elements per thread each; k fastest in global => coalesced 64 B runs
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * 256;
+      int rr = e / 16, kk = e % 16;
+      int r = r0 + rr, n = n0 + rr, k = k0 + kk;
+      Xs[kk][rr] = (r < a.rows && k < a.K) ? a.X[(size_t)r * a.ldx + k] : 0.f;
+      Ws[kk][rr] = (n < a.N && k < a.K) ? __ldg(a.W + (size_t)n * a.K + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 xv = *reinterpret_cast<const float4*>(&Xs[kk][ty * 4]);
+      float4 wv = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      float xr[4] = {xv.x, xv.y, xv.z, xv.w}, wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = r0 + ty * 4 + i;
+    if (r >= a.rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= a.N) continue;
+      float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
+      if (a.gelu) v = gelu_exact(v);
+      if (a.rowadd) v += a.rowadd[(size_t)(r % a.rowadd_period) * a.ldra + n];
+      if (a.res) v += a.res[(size_t)r * a.ldr + n];
+      a.Y[(size_t)r * a.ldy + n] = v;
+    }
+  }
+}
+
+// ---- LayerNorm over rows (nn.LayerNorm semantics, eps given, optional affine), out-of-place with pitches; warp per row.
+// x_bcast_period > 0: the input row is x[r % period] (used to normalise the learned latents once per frame without
+// materialising the broadcast — encoder.py:39).
+__global__ void __launch_bounds__(256)
+layernorm_f32_kernel(const float* __restrict__ x, int ldx, int x_bcast_period, float* __restrict__ y, int ldy,
+                     const float* __restrict__ w, const float* __restrict__ b, int rows, int dim, float eps) {
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = x + (size_t)(x_bcast_period > 0 ? row % x_bcast_period : row) * ldx;
+  float s = 0.f;
+  for (int j = lane; j < dim; j += 32) s += p[j];
+  float mean = warp_sum(s) / dim;
+  float v = 0.f;
+  for (int j = lane; j < dim; j += 32) {
+    float d = p[j] - mean;
+    v = fmaf(d, d, v);
+  }
+  float rstd = rsqrtf(warp_sum(v) / dim + eps);
+  float* o = y + (size_t)row * ldy;
+  for (int j = lane; j < dim; j += 32) {
+    float t = (p[j] - mean) * rstd;
+    o[j] = w ? fmaf(t, w[j], b[j]) : t;
+  }
+}
+
+// ---- dst[r, col0 + j] = table[idx[r], j]   (embedding gather into a column block of a wider row-major matrix)
+__global__ void gather_cols_kernel(float* __restrict__ dst, int ldd, int col0, const float* __restrict__ table, int width,
+                                   const long long* __restrict__ idx, long long rows) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width) return;
+  long long r = i / width;
+  int j = (int)(i % width);
+  dst[(size_t)r * ldd + col0 + j] = table[(size_t)idx[r] * width + j];
+}
+// ---- dst[r, col0 + j] = src[r, j]
+__global__ void copy_cols_kernel(float* __restrict__ dst, int ldd, int col0, const float* __restrict__ src, int width, long long rows) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width) return;
+  long long r = i / width;
+  int j = (int)(i % width);
+  dst[(size_t)r * ldd + col0 + j] = src[(size_t)r * width + j];
+}
+// ---- dst[r, :] = src[r % period, :]   (broadcast of the learned latents over frames)
+__global__ void bcast_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int width, int period, long long rows) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width) return;
+  long long r = i / width;
+  int j = (int)(i % width);
+  dst[i] = src[(size_t)(r % period) * width + j];
+}
+// ---- PointEmbed features (embeddings.py:80-88): [sin(pos . basis) (nb), cos(pos . basis) (nb), pos (3)], basis [3, nb]
+__global__ void point_feats_kernel(const float* __restrict__ pos, const float* __restrict__ basis, float* __restrict__ out, int nb,
+                                   long long rows) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int width = 2 * nb + 3;
+  if (i >= rows * width) return;
+  long long r = i / width;
+  int j = (int)(i % width);
+  const float* p = pos + (size_t)r * 3;
+  float v;
+  if (j >= 2 * nb) {
+    v = p[j - 2 * nb];
+  } else {
+    int e = j < nb ? j : j - nb;
+    float proj = p[0] * basis[e] + p[1] * basis[nb + e] + p[2] * basis[2 * nb + e];
+    v = j < nb ? sinf(proj) : cosf(proj);
+  }
+  out[i] = v;
+}
+
+// ---- attention of the Perceiver-style blocks (torch_modules.py:147-186, 221-253), dim_head = 16, fp32.
+// One thread per (frame, head, query).  q/k are RMS-normalised per head (eps 1e-6, learned scale) when qk_norm;
+// keys with mask == 0 are excluded (bool key mask, True = keep).  q_frame_stride may be 0 (queries shared by all frames).
+struct SmallAttnArgs {
+  const float* q; long long q_frame_stride; int ldq;   // q[frame, sq, head*16 + d]
+  const float* k; const float* v; long long kv_frame_stride; int ldkv;  // k/v[frame, sk, head*16 + d] (pointers pre-offset)
+  const float* gq; const float* gk;                    // RMSNorm scales [16] or null
+  const unsigned char* mask;                           // [frames, Sk] or null
+  float* out; int ldo;                                 // out[frame, sq, head*16 + d]
+  int frames, Sq, Sk, heads;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128) small_attn_f32_kernel(SmallAttnArgs a) {
+  constexpr int DH = 16;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)a.frames * a.heads * a.Sq;
+  if (idx >= tot) return;
+  const int sq = (int)(idx % a.Sq);
+  const int hh = (int)((idx / a.Sq) % a.heads);
+  const long long f = idx / ((long long)a.Sq * a.heads);
+  float q[DH], acc[DH];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(a.q + f * a.q_frame_stride + (size_t)sq * a.ldq + hh * DH);
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 t = qp[c];
+      q[4 * c] = t.x, q[4 * c + 1] = t.y, q[4 * c + 2] = t.z, q[4 * c + 3] = t.w;
+      ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+    }
+    if (a.gq) {
+      float r = rsqrtf(ss * (1.0f / DH) + 1e-6f);
+#pragma unroll
+      for (int d = 0; d < DH; ++d) q[d] = q[d] * r * a.gq[d];
+    }
+#pragma unroll
+    for (int d = 0; d < DH; ++d) q[d] *= a.scale;
+  }
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  const float* kb = a.k + f * a.kv_frame_stride + hh * DH;
+  const float* vb = a.v + f * a.kv_frame_stride + hh * DH;
+  for (int s = 0; s < a.Sk; ++s) {
+    if (a.mask && !a.mask[f * a.Sk + s]) continue;
+    const float4* kp = reinterpret_cast<const float4*>(kb + (size_t)s * a.ldkv);
+    float kk[DH];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 t = kp[c];
+      kk[4 * c] = t.x, kk[4 * c + 1] = t.y, kk[4 * c + 2] = t.z, kk[4 * c + 3] = t.w;
+      ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+    }
+    float dot = 0.f;
+    if (a.gk) {
+      float r = rsqrtf(ss * (1.0f / DH) + 1e-6f);
+#pragma unroll
+      for (int d = 0; d < DH; ++d) dot = fmaf(q[d], kk[d] * r * a.gk[d], dot);
+    } else {
+#pragma unroll
+      for (int d = 0; d < DH; ++d) dot = fmaf(q[d], kk[d], dot);
+    }
+    const float mn = fmaxf(m, dot);
+    const float corr = expf(m - mn);
+    const float p = expf(dot - mn);
+    m = mn;
+    l = l * corr + p;
+    const float4* vp = reinterpret_cast<const float4*>(vb + (size_t)s * a.ldkv);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 t = vp[c];
+      acc[4 * c] = fmaf(p, t.x, acc[4 * c] * corr);
+      acc[4 * c + 1] = fmaf(p, t.y, acc[4 * c + 1] * corr);
+      acc[4 * c + 2] = fmaf(p, t.z, acc[4 * c + 2] * corr);
+      acc[4 * c + 3] = fmaf(p, t.w, acc[4 * c + 3] * corr);
+    }
+  }
+  const float inv = 1.0f / l;
+  float4* op = reinterpret_cast<float4*>(a.out + ((size_t)f * a.Sq + sq) * a.ldo + hh * DH);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) op[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+}
+
+}  // namespace lam

@@ -1,0 +1,1156 @@
+// liblamslide.so — host runtime + C ABI (include/lamslide.h) of the B200-native LaM-SLidE sampling hot path.
+// One translation unit: weight packing, TMA descriptors, kernel orchestration for LatentSIV3.forward, the SiT Euler
+// ODE loop, setup_conditioning and the first-stage encode / decode.  No CPU fallback: every entry point launches the
+// sm_100a kernels in gemm_tc.cuh / attn.cuh / elementwise.cuh / first_stage.cuh or fails with an error code.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/lamslide.h"
+#include "gemm_tc.cuh"
+#include "attn.cuh"
+#include "elementwise.cuh"
+#include "first_stage.cuh"
+
+using namespace lam;
+
+// ================================================================================================ error handling
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                          \
+  do {                                                                                                          \
+    cudaError_t _e = (expr);                                                                                    \
+    if (_e != cudaSuccess) return fail(LAMSLIDE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                                     \
+  } while (0)
+#define LAUNCH_CHECK()                                                                                          \
+  do {                                                                                                          \
+    ++g_launches;                                                                                               \
+    cudaError_t _e = cudaGetLastError();                                                                        \
+    if (_e != cudaSuccess) return fail(LAMSLIDE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                                     \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ================================================================================================ state dict / device arena
+struct StateDict {
+  std::unordered_map<std::string, const lamslide_tensor*> m;
+  StateDict(const lamslide_tensor* t, int n) {
+    for (int i = 0; i < n; ++i) m[t[i].name] = &t[i];
+  }
+  // returns the tensor or nullptr (+ error text) — shape is checked when dims are given (0-terminated list)
+  const lamslide_tensor* get(const std::string& name, std::initializer_list<int64_t> shape) const {
+    auto it = m.find(name);
+    if (it == m.end()) {
+      fail(LAMSLIDE_ERR_MISSING, "state dict key '%s' is missing", name.c_str());
+      return nullptr;
+    }
+    const lamslide_tensor* t = it->second;
+    int64_t want = 1, have = 1;
+    for (auto s : shape) want *= s;
+    for (int i = 0; i < t->ndim; ++i) have *= t->shape[i];
+    if (want != have) {
+      fail(LAMSLIDE_ERR_MISSING, "state dict key '%s' has %lld elements, expected %lld", name.c_str(), (long long)have,
+           (long long)want);
+      return nullptr;
+    }
+    return t;
+  }
+};
+
+struct Arena {
+  std::vector<void*> blocks;
+  ~Arena() {
+    for (void* p : blocks) cudaFree(p);
+  }
+  int upload(const void* host, size_t bytes, void** out) {
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, align_up(bytes, 256)));
+    blocks.push_back(d);
+    CUDA_TRY(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+    *out = d;
+    return 0;
+  }
+  int upload_f32(const float* host, size_t n, float** out) { return upload(host, n * sizeof(float), (void**)out); }
+  int upload_bf16(const float* host, size_t n, __nv_bfloat16** out) {
+    std::vector<__nv_bfloat16> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = __float2bfloat16_rn(host[i]);
+    return upload(tmp.data(), n * sizeof(__nv_bfloat16), (void**)out);
+  }
+};
+
+// ================================================================================================ TMA descriptors
+static PFN_cuTensorMapEncodeTiled_v12000 get_tmap_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// row-major [rows, cols] bf16, tile box_rows x 64 columns, 128-byte swizzle (matches umma_desc_sw128)
+static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  auto enc = get_tmap_encoder();
+  if (!enc) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if (cols % 64 != 0) return fail(LAMSLIDE_ERR_INVALID, "GEMM K = %llu must be a multiple of 64", (unsigned long long)cols);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// ================================================================================================ GEMM launch
+template <int BN>
+struct StagesFor {
+  static constexpr int value = BN >= 192 ? 2 : (BN >= 96 ? 3 : 4);
+};
+
+template <int BN, class Epi>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int rows, int N, int K, const typename Epi::Params& ep,
+                       cudaStream_t st) {
+  constexpr int STAGES = StagesFor<BN>::value;
+  using SM = GemmSmem<BN, STAGES>;
+  auto kern = gemm_tc_kernel<BN, STAGES, Epi>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    configured = true;
+  }
+  dim3 grid(N / BN, cdiv(rows, kBlockM));
+  kern<<<grid, kGemmThreads, SM::kTotal, st>>>(ta, tb, K / kBlockK, ep);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ================================================================================================ second stage handle
+struct BlockWeights {
+  __nv_bfloat16* w1 = nullptr;  // [3H+M, H]
+  __nv_bfloat16* w2 = nullptr;  // [H, H+M]
+  float *b1 = nullptr, *b2 = nullptr, *gq = nullptr, *gk = nullptr;
+  CUtensorMap tm_w1, tm_w2;
+};
+
+struct lamslide_backbone {
+  lamslide_backbone_config cfg;
+  int device = 0;
+  int H = 0, M = 0, D = 0, hd = 0, heads = 0, depth = 0;
+  int bn1 = 0, bn2 = 0, bn_out = 0;
+  int mod_width = 0;  // depth * 6H + 2H
+  Arena arena;
+  float *wt_in = nullptr, *b_in = nullptr, *emask = nullptr;
+  float *time_w1 = nullptr, *time_b1 = nullptr, *time_w2 = nullptr, *time_b2 = nullptr;
+  float *vec_w1 = nullptr, *vec_b1 = nullptr, *vec_w2 = nullptr, *vec_b2 = nullptr;
+  float *mod_w = nullptr, *mod_b = nullptr;
+  std::vector<BlockWeights> blocks;  // 2 * depth: spatial, temporal, spatial, ...
+  __nv_bfloat16* w_out = nullptr;
+  float* b_out = nullptr;
+  CUtensorMap tm_wout;
+};
+
+struct BackboneWorkspace {
+  float* h;
+  __nv_bfloat16* u;
+  __nv_bfloat16* qkv;
+  __nv_bfloat16* act;
+  float* m_out;
+  float *e, *hid, *vec, *hid2, *mod, *tvec;
+  float *cos_s, *sin_s, *cos_t, *sin_t;
+  size_t bytes;
+};
+
+static BackboneWorkspace plan_workspace(const lamslide_backbone* bb, void* base, int B, int T, int L) {
+  BackboneWorkspace w;
+  size_t off = 0;
+  const size_t n = (size_t)B * T * L;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((uint8_t*)base + off) : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  const int H = bb->H, M = bb->M, D = bb->D, half = bb->hd / 2;
+  w.h = (float*)take(n * H * 4);
+  w.u = (__nv_bfloat16*)take(n * H * 2);
+  w.qkv = (__nv_bfloat16*)take(n * 3 * H * 2);
+  w.act = (__nv_bfloat16*)take(n * (size_t)(H + M) * 2);
+  w.m_out = (float*)take(n * D * 4);
+  w.e = (float*)take((size_t)B * 256 * 4);
+  w.hid = (float*)take((size_t)B * H * 4);
+  w.vec = (float*)take((size_t)B * H * 4);
+  w.hid2 = (float*)take((size_t)B * H * 4);
+  w.mod = (float*)take((size_t)B * bb->mod_width * 4);
+  w.tvec = (float*)take((size_t)B * 4);
+  w.cos_s = (float*)take((size_t)L * half * 4);
+  w.sin_s = (float*)take((size_t)L * half * 4);
+  w.cos_t = (float*)take((size_t)T * half * 4);
+  w.sin_t = (float*)take((size_t)T * half * 4);
+  w.bytes = off;
+  return w;
+}
+
+static int plain_bn_for(int N) {
+  for (int bn : {256, 192, 128, 96, 64, 48, 32, 16})
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+static int pick_bn(std::initializer_list<int> cands, int a, int b, int c) {
+  for (int bn : cands)
+    if (a % bn == 0 && (b == 0 || b % bn == 0) && (c == 0 || bn % c == 0)) return bn;
+  return 0;
+}
+
+extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, const lamslide_tensor* tensors, int32_t n_tensors,
+                                        lamslide_backbone** out) {
+  if (!cfg || !tensors || !out) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const int H = cfg->hidden_size, D = cfg->in_dim, heads = cfg->num_heads, M = cfg->mlp_hidden, depth = cfg->depth;
+  if (heads <= 0 || H % heads != 0)  // latent_si_v31.py:92-95
+    return fail(LAMSLIDE_ERR_INVALID, "Hidden size %d must be divisible by num_heads %d", H, heads);
+  const int hd = H / heads;
+  if (hd != 16 && hd != 24 && hd != 32) return fail(LAMSLIDE_ERR_INVALID, "head_dim %d unsupported (16, 24, 32)", hd);
+  if (H % 128 != 0 || H > 512) return fail(LAMSLIDE_ERR_INVALID, "hidden_size %d unsupported (multiple of 128, <= 512)", H);
+  if (M % 64 != 0 || M <= 0) return fail(LAMSLIDE_ERR_INVALID, "mlp hidden %d must be a positive multiple of 64", M);
+  if (D % 16 != 0 || D > 256 || D <= 0) return fail(LAMSLIDE_ERR_INVALID, "in_dim %d unsupported (multiple of 16, <= 256)", D);
+  if (depth <= 0) return fail(LAMSLIDE_ERR_INVALID, "depth must be positive");
+  const int bn1 = hd == 24 ? pick_bn({192, 96}, H, M, hd) : pick_bn({128, 64}, H, M, hd);
+  const int bn2 = pick_bn({192, 128, 96, 64}, H, 0, 0);
+  const int bn_out = plain_bn_for(D);
+  if (!bn1 || !bn2 || !bn_out) return fail(LAMSLIDE_ERR_INVALID, "no GEMM tiling for hidden_size %d / mlp %d / head_dim %d", H, M, hd);
+
+  auto* bb = new lamslide_backbone();
+  std::unique_ptr<lamslide_backbone> guard(bb);
+  bb->cfg = *cfg;
+  bb->H = H, bb->M = M, bb->D = D, bb->hd = hd, bb->heads = heads, bb->depth = depth;
+  bb->bn1 = bn1, bb->bn2 = bn2, bb->bn_out = bn_out;
+  bb->mod_width = depth * 6 * H + 2 * H;
+  CUDA_TRY(cudaGetDevice(&bb->device));
+  StateDict sd(tensors, n_tensors);
+  Arena& A = bb->arena;
+
+#define GET(var, name, ...)                         \
+  const lamslide_tensor* var = sd.get(name, {__VA_ARGS__}); \
+  if (!var) return LAMSLIDE_ERR_MISSING;
+
+  {  // input embedding: Wt[k, j] with k over [x (D) | x_cond (D)], bias = bx + bc
+    GET(wx, "x_in.weight", H, D);
+    GET(bx, "x_in.bias", H);
+    GET(wc, "cond_to_emb.weight", H, D);
+    GET(bc, "cond_to_emb.bias", H);
+    GET(em, "mask_to_emb.weight", 2, H);
+    std::vector<float> wt((size_t)2 * D * H), bsum(H);
+    for (int j = 0; j < H; ++j) {
+      for (int k = 0; k < D; ++k) {
+        wt[(size_t)k * H + j] = wx->data[(size_t)j * D + k];
+        wt[(size_t)(D + k) * H + j] = wc->data[(size_t)j * D + k];
+      }
+      bsum[j] = bx->data[j] + bc->data[j];
+    }
+    TRY(A.upload_f32(wt.data(), wt.size(), &bb->wt_in));
+    TRY(A.upload_f32(bsum.data(), H, &bb->b_in));
+    TRY(A.upload_f32(em->data, 2 * H, &bb->emask));
+  }
+  {
+    GET(w1, "time_in.in_layer.weight", H, 256);
+    GET(b1, "time_in.in_layer.bias", H);
+    GET(w2, "time_in.out_layer.weight", H, H);
+    GET(b2, "time_in.out_layer.bias", H);
+    TRY(A.upload_f32(w1->data, (size_t)H * 256, &bb->time_w1));
+    TRY(A.upload_f32(b1->data, H, &bb->time_b1));
+    TRY(A.upload_f32(w2->data, (size_t)H * H, &bb->time_w2));
+    TRY(A.upload_f32(b2->data, H, &bb->time_b2));
+  }
+  if (cfg->vec_in_dim > 0) {
+    const int V = cfg->vec_in_dim;
+    GET(w1, "vec_in.in_layer.weight", H, V);
+    GET(b1, "vec_in.in_layer.bias", H);
+    GET(w2, "vec_in.out_layer.weight", H, H);
+    GET(b2, "vec_in.out_layer.bias", H);
+    TRY(A.upload_f32(w1->data, (size_t)H * V, &bb->vec_w1));
+    TRY(A.upload_f32(b1->data, H, &bb->vec_b1));
+    TRY(A.upload_f32(w2->data, (size_t)H * H, &bb->vec_w2));
+    TRY(A.upload_f32(b2->data, H, &bb->vec_b2));
+  }
+  {  // every modulation.lin of every layer + the final adaLN in ONE [depth*6H + 2H, H] matrix: one launch per ODE step
+    std::vector<float> mw((size_t)bb->mod_width * H), mb(bb->mod_width);
+    for (int i = 0; i < depth; ++i) {
+      std::string p = "blocks." + std::to_string(i) + ".modulation.lin.";
+      GET(w, p + "weight", 6 * H, H);
+      GET(b, p + "bias", 6 * H);
+      memcpy(&mw[(size_t)i * 6 * H * H], w->data, (size_t)6 * H * H * 4);
+      memcpy(&mb[(size_t)i * 6 * H], b->data, (size_t)6 * H * 4);
+    }
+    GET(w, "adaLN_modulation.1.weight", 2 * H, H);
+    GET(b, "adaLN_modulation.1.bias", 2 * H);
+    memcpy(&mw[(size_t)depth * 6 * H * H], w->data, (size_t)2 * H * H * 4);
+    memcpy(&mb[(size_t)depth * 6 * H], b->data, (size_t)2 * H * 4);
+    TRY(A.upload_f32(mw.data(), mw.size(), &bb->mod_w));
+    TRY(A.upload_f32(mb.data(), mb.size(), &bb->mod_b));
+  }
+  bb->blocks.resize(2 * depth);
+  for (int i = 0; i < depth; ++i) {
+    for (int s = 0; s < 2; ++s) {
+      std::string p = "blocks." + std::to_string(i) + (s == 0 ? ".spatial_block." : ".temporal_block.");
+      BlockWeights& bw = bb->blocks[2 * i + s];
+      GET(w1, p + "linear1.weight", 3 * H + M, H);
+      GET(b1, p + "linear1.bias", 3 * H + M);
+      GET(w2, p + "linear2.weight", H, H + M);
+      GET(b2, p + "linear2.bias", H);
+      GET(gq, p + "norm.query_norm.scale", hd);
+      GET(gk, p + "norm.key_norm.scale", hd);
+      TRY(A.upload_bf16(w1->data, (size_t)(3 * H + M) * H, &bw.w1));
+      TRY(A.upload_bf16(w2->data, (size_t)H * (H + M), &bw.w2));
+      TRY(A.upload_f32(b1->data, 3 * H + M, &bw.b1));
+      TRY(A.upload_f32(b2->data, H, &bw.b2));
+      TRY(A.upload_f32(gq->data, hd, &bw.gq));
+      TRY(A.upload_f32(gk->data, hd, &bw.gk));
+      TRY(make_tmap(&bw.tm_w1, bw.w1, 3 * H + M, H, bn1));
+      TRY(make_tmap(&bw.tm_w2, bw.w2, H, H + M, bn2));
+    }
+  }
+  {
+    GET(w, "linear.weight", D, H);
+    GET(b, "linear.bias", D);
+    TRY(A.upload_bf16(w->data, (size_t)D * H, &bb->w_out));
+    TRY(A.upload_f32(b->data, D, &bb->b_out));
+    TRY(make_tmap(&bb->tm_wout, bb->w_out, D, H, bn_out));
+  }
+#undef GET
+  *out = guard.release();
+  return 0;
+}
+
+extern "C" void lamslide_backbone_destroy(lamslide_backbone* h) { delete h; }
+
+extern "C" size_t lamslide_backbone_workspace_bytes(const lamslide_backbone* h, int32_t B, int32_t T, int32_t L) {
+  if (!h || B <= 0 || T <= 0 || L <= 0) return 0;
+  return plan_workspace(h, nullptr, B, T, L).bytes;
+}
+
+// ---- vector path helpers
+static int vec_linear(const float* in, int ldi, const float* W, const float* bias, const float* add, float* out, int ldo, int B,
+                      int N, int K, int pre, int post, cudaStream_t st) {
+  dim3 grid(cdiv(N, 8), cdiv(B, 8));
+  vec_linear_kernel<<<grid, 256, (size_t)8 * K * sizeof(float), st>>>(in, ldi, W, bias, add, out, ldo, B, N, K, pre, post);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <int HD>
+static int launch_linear1(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, int rows,
+                          const typename EpiLinear1<HD>::Params& ep, cudaStream_t st) {
+  const int N = 3 * bb->H + bb->M, K = bb->H;
+  if constexpr (HD == 24) {
+    if (bb->bn1 == 192) return launch_gemm<192, EpiLinear1<24>>(ta, bw.tm_w1, rows, N, K, ep, st);
+    return launch_gemm<96, EpiLinear1<24>>(ta, bw.tm_w1, rows, N, K, ep, st);
+  } else {
+    if (bb->bn1 == 128) return launch_gemm<128, EpiLinear1<HD>>(ta, bw.tm_w1, rows, N, K, ep, st);
+    return launch_gemm<64, EpiLinear1<HD>>(ta, bw.tm_w1, rows, N, K, ep, st);
+  }
+}
+
+static int launch_linear2(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, int rows,
+                          const EpiLinear2::Params& ep, cudaStream_t st) {
+  const int N = bb->H, K = bb->H + bb->M;
+  switch (bb->bn2) {
+    case 192: return launch_gemm<192, EpiLinear2>(ta, bw.tm_w2, rows, N, K, ep, st);
+    case 128: return launch_gemm<128, EpiLinear2>(ta, bw.tm_w2, rows, N, K, ep, st);
+    case 96: return launch_gemm<96, EpiLinear2>(ta, bw.tm_w2, rows, N, K, ep, st);
+    default: return launch_gemm<64, EpiLinear2>(ta, bw.tm_w2, rows, N, K, ep, st);
+  }
+}
+
+static int launch_plain(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int rows, int N, int K, const EpiPlain::Params& ep,
+                        cudaStream_t st) {
+  switch (bn) {
+    case 16: return launch_gemm<16, EpiPlain>(ta, tb, rows, N, K, ep, st);
+    case 32: return launch_gemm<32, EpiPlain>(ta, tb, rows, N, K, ep, st);
+    case 48: return launch_gemm<48, EpiPlain>(ta, tb, rows, N, K, ep, st);
+    case 64: return launch_gemm<64, EpiPlain>(ta, tb, rows, N, K, ep, st);
+    case 96: return launch_gemm<96, EpiPlain>(ta, tb, rows, N, K, ep, st);
+    case 128: return launch_gemm<128, EpiPlain>(ta, tb, rows, N, K, ep, st);
+    case 192: return launch_gemm<192, EpiPlain>(ta, tb, rows, N, K, ep, st);
+    case 256: return launch_gemm<256, EpiPlain>(ta, tb, rows, N, K, ep, st);
+    default: return fail(LAMSLIDE_ERR_INVALID, "unsupported GEMM tile width %d", bn);
+  }
+}
+
+template <int HD>
+static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H, int ldo, int heads, const SeqMap& sm, int n_seq,
+                            bool force_flash, cudaStream_t st) {
+  if (sm.S <= 32 && !force_flash) {
+    long long items = (long long)n_seq * sm.S * heads;
+    attn_small_kernel<HD><<<cdiv(items, 256), 256, 0, st>>>(qkv, out, H, ldo, heads, sm, items);
+  } else {
+    int nqt = cdiv(sm.S, 128);
+    dim3 grid((unsigned)(n_seq * nqt), heads);
+    attn_flash_kernel<HD><<<grid, 256, 0, st>>>(qkv, out, H, ldo, sm, nqt);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int attention_dispatch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H, int ldo, int heads, int hd, const SeqMap& sm,
+                              int n_seq, bool force_flash, cudaStream_t st) {
+  switch (hd) {
+    case 16: return launch_attention<16>(qkv, out, H, ldo, heads, sm, n_seq, force_flash, st);
+    case 24: return launch_attention<24>(qkv, out, H, ldo, heads, sm, n_seq, force_flash, st);
+    case 32: return launch_attention<32>(qkv, out, H, ldo, heads, sm, n_seq, force_flash, st);
+    default: return fail(LAMSLIDE_ERR_INVALID, "head_dim %d unsupported", hd);
+  }
+}
+
+static int ln_modulate(const lamslide_backbone* bb, const float* h, __nv_bfloat16* u, const float* shift, const float* scale, int rows,
+                       int rows_per_sample, cudaStream_t st) {
+  dim3 grid(cdiv(rows, 8));
+  switch (bb->H / 128) {
+    case 1: ln_modulate_kernel<1><<<grid, 256, 0, st>>>(h, u, shift, scale, bb->mod_width, rows, rows_per_sample); break;
+    case 2: ln_modulate_kernel<2><<<grid, 256, 0, st>>>(h, u, shift, scale, bb->mod_width, rows, rows_per_sample); break;
+    case 3: ln_modulate_kernel<3><<<grid, 256, 0, st>>>(h, u, shift, scale, bb->mod_width, rows, rows_per_sample); break;
+    case 4: ln_modulate_kernel<4><<<grid, 256, 0, st>>>(h, u, shift, scale, bb->mod_width, rows, rows_per_sample); break;
+    default: return fail(LAMSLIDE_ERR_INVALID, "hidden_size %d unsupported", bb->H);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
+struct ForwardCtx {
+  BackboneWorkspace ws;
+  CUtensorMap tm_u, tm_act;
+  bool tables_ready = false;
+};
+
+static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, int L, void* workspace, size_t workspace_bytes,
+                           cudaStream_t st) {
+  if (B <= 0 || T <= 0 || L <= 0) return fail(LAMSLIDE_ERR_INVALID, "B, T, L must be positive");
+  fc.ws = plan_workspace(bb, workspace, B, T, L);
+  if (!workspace || workspace_bytes < fc.ws.bytes)
+    return fail(LAMSLIDE_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, fc.ws.bytes);
+  if (((uintptr_t)workspace & 1023) != 0) return fail(LAMSLIDE_ERR_INVALID, "workspace must be 1024-byte aligned");
+  const long long n = (long long)B * T * L;
+  if (n > 0x7fffffffLL / 4) return fail(LAMSLIDE_ERR_INVALID, "too many tokens (%lld)", n);
+  TRY(make_tmap(&fc.tm_u, fc.ws.u, (uint64_t)n, bb->H, kBlockM));
+  TRY(make_tmap(&fc.tm_act, fc.ws.act, (uint64_t)n, bb->H + bb->M, kBlockM));
+  const int half = bb->hd / 2;
+  rope_table_kernel<<<cdiv(L * half, 256), 256, 0, st>>>(fc.ws.cos_s, fc.ws.sin_s, L, half, (double)bb->cfg.theta);
+  LAUNCH_CHECK();
+  rope_table_kernel<<<cdiv(T * half, 256), 256, 0, st>>>(fc.ws.cos_t, fc.ws.sin_t, T, half, (double)bb->cfg.theta);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// LatentSIV3.forward on prepared workspace; result (net output) in ws.m_out, or `out` when given.
+static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, const float* t, const float* x_cond,
+                       const int64_t* mask, const float* y, float* out, int B, int T, int L, cudaStream_t st) {
+  const int H = bb->H, M = bb->M, D = bb->D, hd = bb->hd, heads = bb->heads;
+  const int n = B * T * L;
+  BackboneWorkspace& w = fc.ws;
+  if (y && bb->cfg.vec_in_dim <= 0) return fail(LAMSLIDE_ERR_INVALID, "y given but the model has no vec_in");
+
+  // 1. h = x_in(x) + cond_to_emb(x_cond) + mask_to_emb(mask) [+ layer_norm]
+  {
+    size_t smem = (size_t)2 * D * 36 * sizeof(float);
+    if (H <= 256) {
+      embed_in_kernel<1><<<cdiv(n, 32), 256, smem, st>>>(x, x_cond, (const long long*)mask, bb->wt_in, bb->b_in, bb->emask, w.h, n, D, H);
+    } else {
+      embed_in_kernel<2><<<cdiv(n, 32), 256, smem, st>>>(x, x_cond, (const long long*)mask, bb->wt_in, bb->b_in, bb->emask, w.h, n, D, H);
+    }
+    LAUNCH_CHECK();
+    if (bb->cfg.normalize) {
+      layernorm_rows_kernel<<<cdiv(n, 8), 256, 0, st>>>(w.h, n, H, 1e-5f);
+      LAUNCH_CHECK();
+    }
+  }
+  // 2. vec = time_in(timestep_embedding(t)) [+ vec_in(y)];  all modulations of all layers in one matrix product
+  {
+    timestep_embed_kernel<<<cdiv(B * 128, 256), 256, 0, st>>>(t, w.e, B);
+    LAUNCH_CHECK();
+    TRY(vec_linear(w.e, 256, bb->time_w1, bb->time_b1, nullptr, w.hid, H, B, H, 256, 0, 1, st));
+    TRY(vec_linear(w.hid, H, bb->time_w2, bb->time_b2, nullptr, w.vec, H, B, H, H, 0, 0, st));
+    if (y) {
+      TRY(vec_linear(y, bb->cfg.vec_in_dim, bb->vec_w1, bb->vec_b1, nullptr, w.hid2, H, B, H, bb->cfg.vec_in_dim, 0, 1, st));
+      TRY(vec_linear(w.hid2, H, bb->vec_w2, bb->vec_b2, w.vec, w.vec, H, B, H, H, 0, 0, st));
+    }
+    TRY(vec_linear(w.vec, H, bb->mod_w, bb->mod_b, nullptr, w.mod, bb->mod_width, B, bb->mod_width, H, 1, 0, st));
+  }
+  // 3. layers
+  const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)hd));
+  for (int i = 0; i < bb->depth; ++i) {
+    for (int s = 0; s < 2; ++s) {
+      const BlockWeights& bw = bb->blocks[2 * i + s];
+      const float* modl = w.mod + (size_t)i * 6 * H + (size_t)s * 3 * H;  // shift | scale | gate
+      TRY(ln_modulate(bb, w.h, w.u, modl, modl + H, n, T * L, st));
+      SeqMap sm;
+      int n_seq;
+      const float *cs, *sn;
+      int pos_div, pos_mod;
+      if (s == 0) {  // spatial: sequences (b, t) over l
+        sm = SeqMap{L, 1, L, 0, 1};
+        n_seq = B * T;
+        cs = w.cos_s, sn = w.sin_s, pos_div = 1, pos_mod = L;
+      } else {  // temporal: sequences (b, l) over t
+        sm = SeqMap{T, L, T * L, 1, L};
+        n_seq = B * L;
+        cs = w.cos_t, sn = w.sin_t, pos_div = L, pos_mod = T;
+      }
+#define L1_PARAMS(HD_)                                                                                               \
+  typename EpiLinear1<HD_>::Params ep{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul}; \
+  TRY(launch_linear1<HD_>(bb, fc.tm_u, bw, n, ep, st));
+      if (hd == 16) {
+        L1_PARAMS(16)
+      } else if (hd == 24) {
+        L1_PARAMS(24)
+      } else {
+        L1_PARAMS(32)
+      }
+#undef L1_PARAMS
+      TRY(attention_dispatch(w.qkv, w.act, H, H + M, heads, hd, sm, n_seq, false, st));
+      EpiLinear2::Params e2{w.h, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, n};
+      TRY(launch_linear2(bb, fc.tm_act, bw, n, e2, st));
+    }
+  }
+  // 4. final adaLN + linear
+  {
+    const float* ada = w.mod + (size_t)bb->depth * 6 * H;  // shift | scale
+    TRY(ln_modulate(bb, w.h, w.u, ada, ada + H, n, T * L, st));
+    EpiPlain::Params ep{out ? out : w.m_out, bb->b_out, D, n};
+    TRY(launch_plain(bb->bn_out, fc.tm_u, bb->tm_wout, n, D, H, ep, st));
+  }
+  return 0;
+}
+
+static int check_device(const lamslide_backbone* h) {
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != h->device) return fail(LAMSLIDE_ERR_INVALID, "handle was created on device %d, current device is %d", h->device, dev);
+  return 0;
+}
+
+extern "C" int lamslide_backbone_forward(lamslide_backbone* h, const float* x, const float* t, const float* x_cond,
+                                         const int64_t* x_cond_mask, const float* y, float* out, int32_t B, int32_t T, int32_t L,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !x || !t || !x_cond || !x_cond_mask || !out) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  TRY(check_device(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  ForwardCtx fc;
+  TRY(forward_prepare(h, fc, B, T, L, workspace, workspace_bytes, st));
+  return forward_run(h, fc, x, t, x_cond, x_cond_mask, y, out, B, T, L, st);
+}
+
+__global__ void fill_kernel(float* p, float v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void copy_f4_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) dst[i] = src[i];
+}
+
+// torch.linspace(start, end, steps) in fp32 (symmetric evaluation, as ATen's CPU/CUDA kernels do)
+static float linspace_f32(float start, float end, int steps, int i) {
+  float step = (end - start) / (float)(steps - 1);
+  int halfway = steps / 2;
+  return i < halfway ? start + step * (float)i : end - step * (float)(steps - i - 1);
+}
+
+// v = cm * m + cx * x for every (path, prediction) of Transport.get_drift (transport.py:158-202; path.py ICPlan / GVPCPlan)
+static int drift_coefficients(int path_type, int prediction, double t, double* cm, double* cx) {
+  if (prediction == 0) {
+    *cm = 1.0, *cx = 0.0;
+    return 0;
+  }
+  const double PI = 3.14159265358979323846;
+  double alpha, sigma, d_sigma, ratio;
+  if (path_type == 1) {  // GVP
+    alpha = std::sin(t * PI / 2), sigma = std::cos(t * PI / 2), d_sigma = -PI / 2 * std::sin(t * PI / 2);
+    ratio = PI / (2 * std::tan(t * PI / 2));
+  } else if (path_type == 0) {  // Linear
+    alpha = t, sigma = 1 - t, d_sigma = -1, ratio = 1 / t;
+  } else {
+    return fail(LAMSLIDE_ERR_INVALID, "path_type %d unsupported (0 Linear, 1 GVP)", path_type);
+  }
+  const double drift_var = ratio * sigma * sigma - sigma * d_sigma;  // -drift_mean = ratio * x
+  switch (prediction) {
+    case 1:  // data: score = -(x - alpha m) / sigma^2
+      *cm = drift_var * alpha / (sigma * sigma);
+      *cx = ratio - drift_var / (sigma * sigma);
+      return 0;
+    case 2:  // noise: score = -m / sigma
+      *cm = -drift_var / sigma;
+      *cx = ratio;
+      return 0;
+    case 3:  // score
+      *cm = drift_var;
+      *cx = ratio;
+      return 0;
+    default: return fail(LAMSLIDE_ERR_INVALID, "prediction %d unsupported", prediction);
+  }
+}
+
+extern "C" int lamslide_ode_sample(lamslide_backbone* h, float* x, const float* x_cond, const int64_t* x_cond_mask, const float* y,
+                                   int32_t path_type, int32_t prediction, int32_t num_steps, float* states_out,
+                                   float* velocities_out, int32_t B, int32_t T, int32_t L, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  if (!h || !x || !x_cond || !x_cond_mask) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  if (num_steps < 2) return fail(LAMSLIDE_ERR_INVALID, "num_steps must be >= 2");
+  TRY(check_device(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  ForwardCtx fc;
+  TRY(forward_prepare(h, fc, B, T, L, workspace, workspace_bytes, st));
+  // Transport.check_interval (transport.py:69-101) for the ODE sampler
+  float t0 = 0.f, t1 = 1.f;
+  if (prediction != 0) t0 = 1e-3f, t1 = 1.f - 1e-3f;
+  const long long nel = (long long)B * T * L * h->D;
+  const long long n4 = nel / 4;  // D % 16 == 0
+  if (states_out) {
+    copy_f4_kernel<<<cdiv(n4, 256), 256, 0, st>>>((const float4*)x, (float4*)states_out, n4);
+    LAUNCH_CHECK();
+  }
+  for (int i = 0; i < num_steps - 1; ++i) {
+    const float ti = linspace_f32(t0, t1, num_steps, i);
+    const float tn = linspace_f32(t0, t1, num_steps, i + 1);
+    fill_kernel<<<cdiv(B, 256), 256, 0, st>>>(fc.ws.tvec, ti, B);
+    LAUNCH_CHECK();
+    TRY(forward_run(h, fc, x, fc.ws.tvec, x_cond, x_cond_mask, y, nullptr, B, T, L, st));
+    double cm, cx;
+    TRY(drift_coefficients(path_type, prediction, (double)ti, &cm, &cx));
+    drift_euler_kernel<<<cdiv(n4, 256), 256, 0, st>>>(
+        (const float4*)fc.ws.m_out, (float4*)x, velocities_out ? (float4*)(velocities_out + (size_t)i * nel) : nullptr,
+        states_out ? (float4*)(states_out + (size_t)(i + 1) * nel) : nullptr, (float)cm, (float)cx, tn - ti, n4);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int lamslide_euler_step(float* x, const float* net_out, int32_t path_type, int32_t prediction, float t, float t_next,
+                                   float* velocity_out, int64_t numel, void* stream) {
+  if (!x || !net_out) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  if (numel % 4 != 0) return fail(LAMSLIDE_ERR_INVALID, "numel must be a multiple of 4");
+  double cm, cx;
+  TRY(drift_coefficients(path_type, prediction, (double)t, &cm, &cx));
+  drift_euler_kernel<<<cdiv(numel / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)net_out, (float4*)x, (float4*)velocity_out, nullptr,
+                                                                            (float)cm, (float)cx, t_next - t, numel / 4);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lamslide_setup_conditioning(const float* latents, float* x_cond, int64_t* x_cond_mask, int32_t B, int32_t T, int32_t L,
+                                           int32_t D, int32_t cond_begin, int32_t cond_end, int32_t mask_cond_mean, void* stream) {
+  if (!latents || !x_cond || !x_cond_mask) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  if (cond_begin < 0 || cond_end > T || cond_begin >= cond_end) return fail(LAMSLIDE_ERR_INVALID, "bad cond_idx [%d, %d)", cond_begin, cond_end);
+  long long tot = (long long)B * L * D;
+  conditioning_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(latents, x_cond, (long long*)x_cond_mask, B, T, L, D,
+                                                                        cond_begin, cond_end, mask_cond_mean);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ================================================================================================ first stage
+struct LNW {
+  float *w = nullptr, *b = nullptr;
+};
+struct LinW {
+  float *w = nullptr, *b = nullptr;
+  int out = 0, in = 0;
+};
+struct AttnBlockW {  // CrossAttentionBlock / SelfAttentionBlock (torch_modules.py:189-273)
+  bool cross = false;
+  int dim = 0, ctx_dim = 0, heads = 0, dh = 0;
+  LNW norm, norm_ctx, ff_norm;
+  LinW to_q, to_kv, to_qkv, to_out, ff0, ff1;
+  float *gq = nullptr, *gk = nullptr;
+};
+
+struct lamslide_first_stage {
+  lamslide_first_stage_config cfg;
+  std::vector<std::string> out_names;
+  int device = 0;
+  Arena arena;
+  int feat_dim = 0;
+  float* ent_table = nullptr;                           // [num_entities, entity_dim], max_norm pre-applied
+  float *tab0 = nullptr, *tab1 = nullptr;               // embedding_res / embed_atom / embed_team ; embed_group
+  int tab0_dim = 0, tab1_dim = 0;
+  float* sincos = nullptr;                              // [max_res, dim_input]
+  float* point_basis = nullptr;                         // [3, nb]
+  int point_nb = 0;
+  LinW point_mlp, merge0, merge2, enc_mlp0, enc_mlp2, quant, post_quant, query_mlp, extender;
+  float* latents = nullptr;                             // [L, D]
+  std::vector<AttnBlockW> enc_cross, enc_self, dec_self, dec_cross;
+  AttnBlockW out_block;
+  std::vector<LinW> head0, head2;
+};
+
+struct FsLoader {
+  StateDict sd;
+  Arena& A;
+  FsLoader(const lamslide_tensor* t, int n, Arena& a) : sd(t, n), A(a) {}
+  int lin(const std::string& p, int out, int in, bool bias, LinW* L) {
+    const lamslide_tensor* w = sd.get(p + ".weight", {out, in});
+    if (!w) return LAMSLIDE_ERR_MISSING;
+    TRY(A.upload_f32(w->data, (size_t)out * in, &L->w));
+    if (bias) {
+      const lamslide_tensor* b = sd.get(p + ".bias", {out});
+      if (!b) return LAMSLIDE_ERR_MISSING;
+      TRY(A.upload_f32(b->data, out, &L->b));
+    }
+    L->out = out, L->in = in;
+    return 0;
+  }
+  int ln(const std::string& p, int dim, LNW* n) {
+    const lamslide_tensor* w = sd.get(p + ".weight", {dim});
+    const lamslide_tensor* b = sd.get(p + ".bias", {dim});
+    if (!w || !b) return LAMSLIDE_ERR_MISSING;
+    TRY(A.upload_f32(w->data, dim, &n->w));
+    TRY(A.upload_f32(b->data, dim, &n->b));
+    return 0;
+  }
+  int vec(const std::string& name, int n, float** out) {
+    const lamslide_tensor* t = sd.get(name, {n});
+    if (!t) return LAMSLIDE_ERR_MISSING;
+    return A.upload_f32(t->data, n, out);
+  }
+  // nn.Embedding(max_norm=1): rows with norm > 1 are rescaled to 1/(norm + 1e-7) on lookup (idempotent => apply once)
+  int table(const std::string& name, int rows, int dim, bool max_norm, float** out) {
+    const lamslide_tensor* t = sd.get(name, {rows, dim});
+    if (!t) return LAMSLIDE_ERR_MISSING;
+    std::vector<float> tmp(t->data, t->data + (size_t)rows * dim);
+    if (max_norm) {
+      for (int r = 0; r < rows; ++r) {
+        float ss = 0.f;  // fp32 like torch's embedding_renorm_
+        for (int j = 0; j < dim; ++j) ss += tmp[(size_t)r * dim + j] * tmp[(size_t)r * dim + j];
+        float nrm = std::sqrt(ss);
+        if (nrm > 1.0f) {
+          float sc = 1.0f / (nrm + 1e-7f);
+          for (int j = 0; j < dim; ++j) tmp[(size_t)r * dim + j] *= sc;
+        }
+      }
+    }
+    return A.upload_f32(tmp.data(), tmp.size(), out);
+  }
+  int attn_block(const std::string& p, bool cross, int dim, int ctx_dim, int heads, int dh, bool qk_norm, AttnBlockW* b) {
+    b->cross = cross, b->dim = dim, b->ctx_dim = ctx_dim, b->heads = heads, b->dh = dh;
+    const int inner = heads * dh;
+    TRY(ln(p + "attn.norm", dim, &b->norm));
+    if (cross) {
+      TRY(ln(p + "attn.norm_context", ctx_dim, &b->norm_ctx));
+      TRY(lin(p + "attn.fn.to_q", inner, dim, false, &b->to_q));
+      TRY(lin(p + "attn.fn.to_kv", 2 * inner, ctx_dim, false, &b->to_kv));
+    } else {
+      TRY(lin(p + "attn.fn.to_qkv", 3 * inner, dim, false, &b->to_qkv));
+    }
+    TRY(lin(p + "attn.fn.to_out", dim, inner, true, &b->to_out));
+    if (qk_norm) {
+      TRY(vec(p + "attn.fn.norm.query_norm.scale", dh, &b->gq));
+      TRY(vec(p + "attn.fn.norm.key_norm.scale", dh, &b->gk));
+    }
+    TRY(ln(p + "ff.norm", dim, &b->ff_norm));
+    TRY(lin(p + "ff.fn.net.0.0", dim, dim, true, &b->ff0));
+    TRY(lin(p + "ff.fn.net.1", dim, dim, true, &b->ff1));
+    return 0;
+  }
+};
+
+extern "C" int lamslide_first_stage_create(const lamslide_first_stage_config* cfg, const lamslide_tensor* tensors, int32_t n_tensors,
+                                           lamslide_first_stage** out) {
+  if (!cfg || !tensors || !out) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->enc_dim_head_cross != 16 || cfg->enc_dim_head_latent != 16 || cfg->dec_dim_head_cross != 16 || cfg->dec_dim_head_latent != 16)
+    return fail(LAMSLIDE_ERR_INVALID, "first-stage attention supports dim_head = 16 only (all shipped configs)");
+  if (cfg->n_outputs < 1 || cfg->n_outputs > LAMSLIDE_MAX_OUTPUTS) return fail(LAMSLIDE_ERR_INVALID, "bad n_outputs");
+  if (cfg->dim_latent % 4 || cfg->dim_input % 4 || cfg->entity_dim % 4 || cfg->dec_dim_query % 4)
+    return fail(LAMSLIDE_ERR_INVALID, "first-stage widths must be multiples of 4");
+  auto* fs = new lamslide_first_stage();
+  std::unique_ptr<lamslide_first_stage> guard(fs);
+  fs->cfg = *cfg;
+  CUDA_TRY(cudaGetDevice(&fs->device));
+  for (int i = 0; i < cfg->n_outputs; ++i) fs->out_names.push_back(cfg->output_names[i]);
+  FsLoader ld(tensors, n_tensors, fs->arena);
+  const int Din = cfg->dim_input, D = cfg->dim_latent, E = cfg->entity_dim, C = Din + E, dq = cfg->dec_dim_query;
+  const bool qkn = cfg->qk_norm != 0;
+  TRY(ld.table("encoder.entity_embedding.embedding.weight", cfg->num_entities, E, true, &fs->ent_table));
+  switch (cfg->kind) {
+    case LAMSLIDE_FS_PEPTIDE: {
+      TRY(ld.table("embedding_res.weight", 20, 64, true, &fs->tab0));
+      fs->tab0_dim = 64;
+      fs->feat_dim = 64 + 42;
+      const lamslide_tensor* sc = ld.sd.get("embed_res_pos.embeddings", {cfg->max_res, Din});
+      if (!sc) return LAMSLIDE_ERR_MISSING;
+      TRY(fs->arena.upload_f32(sc->data, (size_t)cfg->max_res * Din, &fs->sincos));
+      break;
+    }
+    case LAMSLIDE_FS_MD17: {
+      TRY(ld.table("embed_atom.weight", cfg->n_atom_types, 64, true, &fs->tab0));
+      fs->tab0_dim = 64;
+      fs->point_nb = 63;
+      const lamslide_tensor* pb = ld.sd.get("embed_pos.basis", {3, 63});
+      if (!pb) return LAMSLIDE_ERR_MISSING;
+      TRY(fs->arena.upload_f32(pb->data, 3 * 63, &fs->point_basis));
+      TRY(ld.lin("embed_pos.mlp", 128, 129, true, &fs->point_mlp));
+      fs->feat_dim = 64 + 128;
+      break;
+    }
+    case LAMSLIDE_FS_NBA:
+      TRY(ld.table("embed_team.weight", 3, 32, false, &fs->tab0));
+      TRY(ld.table("embed_group.weight", 2, 32, false, &fs->tab1));
+      fs->tab0_dim = fs->tab1_dim = 32;
+      fs->feat_dim = 2 + 32 + 32;
+      break;
+    case LAMSLIDE_FS_PEDESTRIAN: fs->feat_dim = 2; break;
+    default: return fail(LAMSLIDE_ERR_INVALID, "unknown first-stage kind %d", cfg->kind);
+  }
+  TRY(ld.lin("net_merge.0", Din, fs->feat_dim, true, &fs->merge0));
+  TRY(ld.lin("net_merge.2", Din, Din, true, &fs->merge2));
+  TRY(ld.lin("encoder.mlp.0", D, C, true, &fs->enc_mlp0));
+  TRY(ld.lin("encoder.mlp.2", C, D, true, &fs->enc_mlp2));
+  {
+    const lamslide_tensor* lt = ld.sd.get("encoder.latents", {cfg->enc_num_latents, D});
+    if (!lt) return LAMSLIDE_ERR_MISSING;
+    TRY(fs->arena.upload_f32(lt->data, (size_t)cfg->enc_num_latents * D, &fs->latents));
+  }
+  fs->enc_cross.resize(cfg->enc_blocks_cross);
+  for (int i = 0; i < cfg->enc_blocks_cross; ++i)
+    TRY(ld.attn_block("encoder.cross_attn_blocks." + std::to_string(i) + ".", true, D, C, cfg->enc_heads_cross, 16, qkn, &fs->enc_cross[i]));
+  fs->enc_self.resize(cfg->enc_blocks_attn);
+  for (int i = 0; i < cfg->enc_blocks_attn; ++i)
+    TRY(ld.attn_block("encoder.blocks_attn." + std::to_string(i) + ".", false, D, D, cfg->enc_heads_latent, 16, qkn, &fs->enc_self[i]));
+  TRY(ld.lin("quant.0", D, D, true, &fs->quant));
+  TRY(ld.lin("post_quant.1", D, D, true, &fs->post_quant));
+  TRY(ld.lin("decoder.query_mlp.1", dq, E, true, &fs->query_mlp));
+  fs->dec_self.resize(cfg->dec_blocks_attn);
+  for (int i = 0; i < cfg->dec_blocks_attn; ++i)
+    TRY(ld.attn_block("decoder.self_attn_blocks." + std::to_string(i) + ".", false, D, D, cfg->dec_heads_latent, 16, qkn, &fs->dec_self[i]));
+  fs->dec_cross.resize(cfg->dec_blocks_cross);
+  for (int i = 0; i < cfg->dec_blocks_cross; ++i)
+    TRY(ld.attn_block("decoder.cross_attn_blocks." + std::to_string(i) + ".", true, D, dq, cfg->dec_heads_cross, 16, qkn, &fs->dec_cross[i]));
+  TRY(ld.attn_block("decoder.output_block.", true, dq, D, cfg->dec_heads_cross, 16, qkn, &fs->out_block));
+  fs->head0.resize(cfg->n_outputs);
+  fs->head2.resize(cfg->n_outputs);
+  for (int i = 0; i < cfg->n_outputs; ++i) {
+    std::string p = "decoder.output_layers." + fs->out_names[i];
+    TRY(ld.lin(p + ".0", dq, dq, true, &fs->head0[i]));
+    TRY(ld.lin(p + ".2", cfg->output_dims[i], dq, true, &fs->head2[i]));
+  }
+  if (cfg->dec_query_splitter) {
+    // Conv1d(D -> D*n, k=1) then "B (D N) L -> B (L N) D": permute output channels (d*n + j) -> (j*D + d) at pack time so the
+    // GEMM output [F*L, n*D] IS the [F, L*n, D] key/value token matrix (decoder.py:385-389).
+    const int n = cfg->dec_num_split;
+    const lamslide_tensor* w = ld.sd.get("decoder.extender.1.weight", {(int64_t)D * n, D});
+    const lamslide_tensor* b = ld.sd.get("decoder.extender.1.bias", {(int64_t)D * n});
+    if (!w || !b) return LAMSLIDE_ERR_MISSING;
+    std::vector<float> wp((size_t)D * n * D), bp((size_t)D * n);
+    for (int d = 0; d < D; ++d)
+      for (int j = 0; j < n; ++j) {
+        memcpy(&wp[((size_t)j * D + d) * D], &w->data[((size_t)d * n + j) * D], (size_t)D * 4);
+        bp[(size_t)j * D + d] = b->data[(size_t)d * n + j];
+      }
+    TRY(fs->arena.upload_f32(wp.data(), wp.size(), &fs->extender.w));
+    TRY(fs->arena.upload_f32(bp.data(), bp.size(), &fs->extender.b));
+    fs->extender.out = D * n, fs->extender.in = D;
+  }
+  *out = guard.release();
+  return 0;
+}
+
+extern "C" void lamslide_first_stage_destroy(lamslide_first_stage* h) { delete h; }
+
+// ---- bump allocator over the caller's workspace (dry run when base == nullptr)
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base((uint8_t*)b) {}
+  float* f(size_t n) {
+    float* p = base ? (float*)(base + off) : nullptr;
+    off += align_up(n * 4, 256);
+    return p;
+  }
+};
+
+static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, long long rows, bool gelu, const float* res, int ldr,
+                     const float* rowadd, int period, int ldra, cudaStream_t st) {
+  LinearArgs a;
+  a.X = X, a.ldx = ldx, a.W = L.w, a.bias = L.b, a.Y = Y, a.ldy = ldy, a.res = res, a.ldr = ldr;
+  a.rowadd = rowadd, a.rowadd_period = period > 0 ? period : 1, a.ldra = ldra;
+  a.rows = (int)rows, a.N = L.out, a.K = L.in, a.gelu = gelu ? 1 : 0;
+  dim3 grid(cdiv(L.out, 64), cdiv(rows, 64));
+  linear_f32_kernel<<<grid, 256, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+static int fs_layernorm(const float* x, int ldx, int period, float* y, int ldy, const LNW* n, long long rows, int dim, float eps,
+                        cudaStream_t st) {
+  layernorm_f32_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, ldx, period, y, ldy, n ? n->w : nullptr, n ? n->b : nullptr, (int)rows, dim, eps);
+  LAUNCH_CHECK();
+  return 0;
+}
+static int fs_attn(const SmallAttnArgs& a, cudaStream_t st) {
+  long long tot = (long long)a.frames * a.heads * a.Sq;
+  small_attn_f32_kernel<<<cdiv(tot, 128), 128, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+struct BlockScratch {
+  float *xn, *cn, *q, *kv, *att, *f1;
+};
+static BlockScratch block_scratch(Bump& bp, long long rows_x, int dim, long long rows_ctx, int ctx_dim, int inner) {
+  BlockScratch s;
+  s.xn = bp.f((size_t)rows_x * dim);
+  s.cn = bp.f((size_t)rows_ctx * ctx_dim);
+  s.q = bp.f((size_t)rows_x * inner);
+  s.kv = bp.f((size_t)std::max(rows_ctx * 2, rows_x * 3) * inner);
+  s.att = bp.f((size_t)rows_x * inner);
+  s.f1 = bp.f((size_t)rows_x * dim);
+  return s;
+}
+
+// x [F*Sx, dim] (updated in place)  <-  CrossAttentionBlock(x, context = ctx [F*Sc, ctx_dim], mask)
+static int run_cross_block(const AttnBlockW& b, float* x, int F, int Sx, const float* ctx, int Sc, const uint8_t* mask,
+                           const BlockScratch& s, cudaStream_t st) {
+  const long long rx = (long long)F * Sx, rc = (long long)F * Sc;
+  const int inner = b.heads * b.dh;
+  TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.norm, rx, b.dim, 1e-5f, st));
+  TRY(fs_layernorm(ctx, b.ctx_dim, 0, s.cn, b.ctx_dim, &b.norm_ctx, rc, b.ctx_dim, 1e-5f, st));
+  TRY(fs_linear(b.to_q, s.xn, b.dim, s.q, inner, rx, false, nullptr, 0, nullptr, 0, 0, st));
+  TRY(fs_linear(b.to_kv, s.cn, b.ctx_dim, s.kv, 2 * inner, rc, false, nullptr, 0, nullptr, 0, 0, st));
+  SmallAttnArgs a;
+  a.q = s.q, a.q_frame_stride = (long long)Sx * inner, a.ldq = inner;
+  a.k = s.kv, a.v = s.kv + inner, a.kv_frame_stride = (long long)Sc * 2 * inner, a.ldkv = 2 * inner;  // k first, then v
+  a.gq = b.gq, a.gk = b.gk, a.mask = mask, a.out = s.att, a.ldo = inner;
+  a.frames = F, a.Sq = Sx, a.Sk = Sc, a.heads = b.heads, a.scale = 1.0f / std::sqrt((float)b.dh);
+  TRY(fs_attn(a, st));
+  TRY(fs_linear(b.to_out, s.att, inner, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st));
+  TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.ff_norm, rx, b.dim, 1e-5f, st));
+  TRY(fs_linear(b.ff0, s.xn, b.dim, s.f1, b.dim, rx, true, nullptr, 0, nullptr, 0, 0, st));
+  TRY(fs_linear(b.ff1, s.f1, b.dim, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st));
+  return 0;
+}
+
+static int run_self_block(const AttnBlockW& b, float* x, int F, int S, const BlockScratch& s, cudaStream_t st) {
+  const long long rx = (long long)F * S;
+  const int inner = b.heads * b.dh;
+  TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.norm, rx, b.dim, 1e-5f, st));
+  TRY(fs_linear(b.to_qkv, s.xn, b.dim, s.kv, 3 * inner, rx, false, nullptr, 0, nullptr, 0, 0, st));
+  SmallAttnArgs a;
+  a.q = s.kv, a.q_frame_stride = (long long)S * 3 * inner, a.ldq = 3 * inner;
+  a.k = s.kv + inner, a.v = s.kv + 2 * inner, a.kv_frame_stride = (long long)S * 3 * inner, a.ldkv = 3 * inner;
+  a.gq = b.gq, a.gk = b.gk, a.mask = nullptr, a.out = s.att, a.ldo = inner;
+  a.frames = F, a.Sq = S, a.Sk = S, a.heads = b.heads, a.scale = 1.0f / std::sqrt((float)b.dh);
+  TRY(fs_attn(a, st));
+  TRY(fs_linear(b.to_out, s.att, inner, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st));
+  TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.ff_norm, rx, b.dim, 1e-5f, st));
+  TRY(fs_linear(b.ff0, s.xn, b.dim, s.f1, b.dim, rx, true, nullptr, 0, nullptr, 0, 0, st));
+  TRY(fs_linear(b.ff1, s.f1, b.dim, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st));
+  return 0;
+}
+
+static int encode_impl(lamslide_first_stage* fs, const lamslide_frame_inputs* in, float* latents_out, int F, int N, void* workspace,
+                       size_t* bytes, cudaStream_t st) {
+  const lamslide_first_stage_config& c = fs->cfg;
+  const int Din = c.dim_input, D = c.dim_latent, E = c.entity_dim, C = Din + E, L = c.enc_num_latents;
+  const long long R = (long long)F * N, FL = (long long)F * L;
+  Bump bp(workspace);
+  float* feat = bp.f((size_t)R * fs->feat_dim);
+  float* pfeat = c.kind == LAMSLIDE_FS_MD17 ? bp.f((size_t)R * 129) : nullptr;
+  float* hid1 = bp.f((size_t)R * Din);
+  float* ctx_in = bp.f((size_t)R * C);
+  float* hid2 = bp.f((size_t)R * D);
+  float* ctx = bp.f((size_t)R * C);
+  float* z = bp.f((size_t)FL * D);
+  int inner = std::max(c.enc_heads_cross, c.enc_heads_latent) * 16;
+  BlockScratch s = block_scratch(bp, FL, D, R, C, inner);
+  if (bytes) {
+    *bytes = bp.off;
+    return 0;
+  }
+  const int TB = 256;
+  // 1. Backbone.prepare_inputs features
+  const float* feat_in = feat;
+  switch (c.kind) {
+    case LAMSLIDE_FS_PEPTIDE:
+      if (!in->index0) return fail(LAMSLIDE_ERR_INVALID, "peptide encode needs aatype (index0)");
+      if (N > c.max_res) return fail(LAMSLIDE_ERR_INVALID, "N = %d exceeds max_res = %d", N, c.max_res);
+      gather_cols_kernel<<<cdiv(R * 64, TB), TB, 0, st>>>(feat, fs->feat_dim, 0, fs->tab0, 64, (const long long*)in->index0, R);
+      LAUNCH_CHECK();
+      copy_cols_kernel<<<cdiv(R * 42, TB), TB, 0, st>>>(feat, fs->feat_dim, 64, in->pos, 42, R);
+      LAUNCH_CHECK();
+      break;
+    case LAMSLIDE_FS_MD17:
+      if (!in->index0) return fail(LAMSLIDE_ERR_INVALID, "md17 encode needs atom (index0)");
+      gather_cols_kernel<<<cdiv(R * 64, TB), TB, 0, st>>>(feat, fs->feat_dim, 0, fs->tab0, 64, (const long long*)in->index0, R);
+      LAUNCH_CHECK();
+      point_feats_kernel<<<cdiv(R * 129, TB), TB, 0, st>>>(in->pos, fs->point_basis, pfeat, fs->point_nb, R);
+      LAUNCH_CHECK();
+      TRY(fs_linear(fs->point_mlp, pfeat, 129, feat + 64, fs->feat_dim, R, false, nullptr, 0, nullptr, 0, 0, st));
+      break;
+    case LAMSLIDE_FS_NBA:
+      if (!in->index0 || !in->index1) return fail(LAMSLIDE_ERR_INVALID, "nba encode needs team (index0) and group (index1)");
+      copy_cols_kernel<<<cdiv(R * 2, TB), TB, 0, st>>>(feat, fs->feat_dim, 0, in->pos, 2, R);
+      LAUNCH_CHECK();
+      gather_cols_kernel<<<cdiv(R * 32, TB), TB, 0, st>>>(feat, fs->feat_dim, 2, fs->tab0, 32, (const long long*)in->index0, R);
+      LAUNCH_CHECK();
+      gather_cols_kernel<<<cdiv(R * 32, TB), TB, 0, st>>>(feat, fs->feat_dim, 34, fs->tab1, 32, (const long long*)in->index1, R);
+      LAUNCH_CHECK();
+      break;
+    default: feat_in = in->pos; break;
+  }
+  // net_merge (+ residue-index sin/cos embedding for peptides) written straight into the context matrix [x | E_ent]
+  TRY(fs_linear(fs->merge0, feat_in, fs->feat_dim, hid1, Din, R, true, nullptr, 0, nullptr, 0, 0, st));
+  TRY(fs_linear(fs->merge2, hid1, Din, ctx_in, C, R, false, nullptr, 0, fs->sincos, N, Din, st));
+  gather_cols_kernel<<<cdiv(R * E, TB), TB, 0, st>>>(ctx_in, C, Din, fs->ent_table, E, (const long long*)in->entities, R);
+  LAUNCH_CHECK();
+  // EncoderBase.prepare_inputs MLP (encoder.py:35-41)
+  TRY(fs_linear(fs->enc_mlp0, ctx_in, C, hid2, D, R, true, nullptr, 0, nullptr, 0, 0, st));
+  TRY(fs_linear(fs->enc_mlp2, hid2, D, ctx, C, R, false, nullptr, 0, nullptr, 0, 0, st));
+  bcast_rows_kernel<<<cdiv(FL * D, TB), TB, 0, st>>>(z, fs->latents, D, L, FL);
+  LAUNCH_CHECK();
+  for (auto& b : fs->enc_cross) TRY(run_cross_block(b, z, F, L, ctx, N, in->mask, s, st));
+  for (auto& b : fs->enc_self) TRY(run_self_block(b, z, F, L, s, st));
+  // quant: Linear -> LayerNorm(no affine) (lightning_base.py:24-27)
+  TRY(fs_linear(fs->quant, z, D, s.xn, D, FL, false, nullptr, 0, nullptr, 0, 0, st));
+  TRY(fs_layernorm(s.xn, D, 0, latents_out, D, nullptr, FL, D, 1e-5f, st));
+  return 0;
+}
+
+static int decode_impl(lamslide_first_stage* fs, const float* latents, const int64_t* entities, float* const* outs, int F, int N,
+                       void* workspace, size_t* bytes, cudaStream_t st) {
+  const lamslide_first_stage_config& c = fs->cfg;
+  const int D = c.dim_latent, E = c.entity_dim, L = c.enc_num_latents, dq = c.dec_dim_query;
+  const int Lk = c.dec_query_splitter ? L * c.dec_num_split : L;
+  const long long R = (long long)F * N, FL = (long long)F * L, FLk = (long long)F * Lk;
+  Bump bp(workspace);
+  float* zl = bp.f((size_t)FL * D);
+  float* z = bp.f((size_t)FL * D);
+  float* ent = bp.f((size_t)R * E);
+  float* Q = bp.f((size_t)R * dq);
+  float* zk = c.dec_query_splitter ? bp.f((size_t)FLk * D) : nullptr;
+  float* t1 = bp.f((size_t)R * dq);
+  BlockScratch s_self = block_scratch(bp, FL, D, FL, D, c.dec_heads_latent * 16);
+  BlockScratch s_cross = block_scratch(bp, FL, D, R, dq, c.dec_heads_cross * 16);
+  BlockScratch s_out = block_scratch(bp, R, dq, FLk, D, c.dec_heads_cross * 16);
+  if (bytes) {
+    *bytes = bp.off;
+    return 0;
+  }
+  const int TB = 256;
+  // post_quant: LayerNorm(no affine) -> Linear (lightning_base.py:28-31)
+  TRY(fs_layernorm(latents, D, 0, zl, D, nullptr, FL, D, 1e-5f, st));
+  TRY(fs_linear(fs->post_quant, zl, D, z, D, FL, false, nullptr, 0, nullptr, 0, 0, st));
+  // queries = query_mlp(entity_embedding(entities)) (decoder.py:83-86; Dropout inactive in eval)
+  gather_cols_kernel<<<cdiv(R * E, TB), TB, 0, st>>>(ent, E, 0, fs->ent_table, E, (const long long*)entities, R);
+  LAUNCH_CHECK();
+  TRY(fs_linear(fs->query_mlp, ent, E, Q, dq, R, false, nullptr, 0, nullptr, 0, 0, st));
+  for (auto& b : fs->dec_self) TRY(run_self_block(b, z, F, L, s_self, st));
+  for (auto& b : fs->dec_cross) TRY(run_cross_block(b, z, F, L, Q, N, nullptr, s_cross, st));
+  const float* kvsrc = z;
+  if (c.dec_query_splitter) {
+    TRY(fs_linear(fs->extender, z, D, zk, D * c.dec_num_split, FL, false, nullptr, 0, nullptr, 0, 0, st));
+    kvsrc = zk;
+  }
+  TRY(run_cross_block(fs->out_block, Q, F, N, kvsrc, Lk, nullptr, s_out, st));
+  for (int i = 0; i < c.n_outputs; ++i) {
+    if (!outs[i]) continue;
+    TRY(fs_linear(fs->head0[i], Q, dq, t1, dq, R, true, nullptr, 0, nullptr, 0, 0, st));
+    TRY(fs_linear(fs->head2[i], t1, dq, outs[i], c.output_dims[i], R, false, nullptr, 0, nullptr, 0, 0, st));
+  }
+  return 0;
+}
+
+extern "C" size_t lamslide_first_stage_workspace_bytes(const lamslide_first_stage* h, int32_t frames, int32_t N) {
+  if (!h || frames <= 0 || N <= 0) return 0;
+  size_t a = 0, b = 0;
+  encode_impl(const_cast<lamslide_first_stage*>(h), nullptr, nullptr, frames, N, nullptr, &a, nullptr);
+  decode_impl(const_cast<lamslide_first_stage*>(h), nullptr, nullptr, nullptr, frames, N, nullptr, &b, nullptr);
+  return std::max(a, b);
+}
+
+static int fs_check(lamslide_first_stage* h, int frames, int N, void* ws, size_t ws_bytes) {
+  if (!h) return fail(LAMSLIDE_ERR_INVALID, "null handle");
+  if (frames <= 0 || N <= 0) return fail(LAMSLIDE_ERR_INVALID, "frames and N must be positive");
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev != h->device) return fail(LAMSLIDE_ERR_INVALID, "handle was created on device %d, current device is %d", h->device, dev);
+  size_t need = lamslide_first_stage_workspace_bytes(h, frames, N);
+  if (!ws || ws_bytes < need) return fail(LAMSLIDE_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, need);
+  if (((uintptr_t)ws & 255) != 0) return fail(LAMSLIDE_ERR_INVALID, "workspace must be 256-byte aligned");
+  return 0;
+}
+
+extern "C" int lamslide_encode(lamslide_first_stage* h, const lamslide_frame_inputs* in, float* latents_out, int32_t frames, int32_t N,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!in || !in->pos || !in->entities || !latents_out) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  TRY(fs_check(h, frames, N, workspace, workspace_bytes));
+  return encode_impl(h, in, latents_out, frames, N, workspace, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int lamslide_decode(lamslide_first_stage* h, const float* latents, const int64_t* entities, float* const* outs,
+                               int32_t frames, int32_t N, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!latents || !entities || !outs) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  TRY(fs_check(h, frames, N, workspace, workspace_bytes));
+  return decode_impl(h, latents, entities, outs, frames, N, workspace, nullptr, (cudaStream_t)stream);
+}
+
+// ================================================================================================ misc + test hooks
+extern "C" int lamslide_abi_version(void) { return LAMSLIDE_ABI_VERSION; }
+extern "C" const char* lamslide_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t lamslide_launch_count(int32_t reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+extern "C" int lamslide_debug_gemm(const void* a_bf16, const void* b_bf16, const float* bias, float* c, int32_t M, int32_t N, int32_t K,
+                                   int32_t block_n, void* stream) {
+  if (!a_bf16 || !b_bf16 || !c) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  int bn = block_n > 0 ? block_n : plain_bn_for(N);
+  if (bn <= 0 || N % bn != 0) return fail(LAMSLIDE_ERR_INVALID, "N = %d is not a multiple of the tile width %d", N, bn);
+  CUtensorMap ta, tb;
+  TRY(make_tmap(&ta, a_bf16, M, K, kBlockM));
+  TRY(make_tmap(&tb, b_bf16, N, K, bn));
+  EpiPlain::Params ep{c, bias, N, M};
+  return launch_plain(bn, ta, tb, M, N, K, ep, (cudaStream_t)stream);
+}
+
+extern "C" int lamslide_debug_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t L, int32_t H, int32_t heads,
+                                        int32_t ldo, int32_t temporal, int32_t force_flash, void* stream) {
+  if (!qkv_bf16 || !out_bf16 || heads <= 0 || H % heads) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  SeqMap sm = temporal ? SeqMap{T, L, T * L, 1, L} : SeqMap{L, 1, L, 0, 1};
+  int n_seq = temporal ? B * L : B * T;
+  return attention_dispatch((const __nv_bfloat16*)qkv_bf16, (__nv_bfloat16*)out_bf16, H, ldo, heads, H / heads, sm, n_seq,
+                            force_flash != 0, (cudaStream_t)stream);
+}

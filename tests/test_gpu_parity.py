@@ -1,0 +1,149 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors that were
+generated from the real reference modules.  Tolerances are the ones BASELINE.json's north_star states:
+    per-step velocity max relative error  <= 1e-2   (bf16 tensor-core operands, fp32 state)
+    final-frame coordinate RMSD           <= 1e-3 of the data scale (synthetic data scale = 1)
+The first stage runs in fp32 and is held to 1e-4."""
+import pytest
+import torch
+
+from oracle import lamslide_oracle as O
+from tests.helpers import CASE_BY_NAME, case_inputs, check_inputs_match_fixture, frame_slice, load_golden, max_rel, rmsd
+
+pytestmark = pytest.mark.gpu
+
+VEL_TOL = 1e-2
+RMSD_TOL = 1e-3
+FS_TOL = 1e-4
+
+
+def _cuda_batch(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+def _build(cfg, fs_sd, bb_sd):
+    import lam_slide_b200 as P
+    m = P.SecondStageSampler(cfg).cuda()
+    m.first_stage_model.backbone.load_state_dict(fs_sd, strict=True)
+    m.backbone.load_state_dict(bb_sd, strict=True)
+    return m
+
+
+@pytest.mark.parametrize("name", ["peptide", "md17", "nba", "pedestrian"])
+def test_first_stage_encode_decode_vs_oracle(name):
+    from lam_slide_b200.configs import get_config
+    cfg = get_config(name)
+    fs_sd = O.init_first_stage_params(cfg["first_stage"], 21)
+    bb_sd = O.init_backbone_params(dict(cfg["backbone"], depth=1), 22)
+    cfg["backbone"]["depth"] = 1
+    m = _build(cfg, fs_sd, bb_sd)
+    B, T = 3, 5
+    batch = O.synthetic_batch(cfg, B, 23, T=T)
+    flat = {k: v.flatten(0, 1) for k, v in batch.items() if k != "cond_scene"}
+    with torch.no_grad():
+        lat_ref = O.first_stage_encode(fs_sd, cfg["first_stage"], flat)
+        out_ref = O.first_stage_decode(fs_sd, cfg["first_stage"], lat_ref, flat["entities"])
+    fs = m.first_stage_model.backbone
+    lat = fs.encode(_cuda_batch(flat))
+    assert max_rel(lat.cpu(), lat_ref) < FS_TOL
+    out = fs.decode(lat_ref.cuda(), flat["entities"].cuda())
+    for k, v in out_ref.items():
+        assert max_rel(out[k].cpu(), v) < FS_TOL, k
+
+
+def test_setup_conditioning_vs_oracle():
+    import lam_slide_b200 as P
+    m = P.SecondStageSampler.from_name("nba").cuda()
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(3, 20, 8, 32, generator=g)
+    xc_ref, mk_ref = O.setup_conditioning(lat, (0, 8), True)
+    xc, mk = m.setup_conditioning(lat.cuda())
+    assert torch.equal(mk.cpu(), mk_ref)
+    assert max_rel(xc.cpu(), xc_ref) < 1e-6
+
+
+@pytest.mark.parametrize("name,depth,B,T", [("peptide", 2, 2, 24), ("md17", 1, 1, 6), ("nba", 2, 3, 20), ("pedestrian", 2, 5, 20),
+                                            ("peptide", 1, 1, 200)])
+def test_backbone_forward_vs_oracle(name, depth, B, T):
+    """One LatentSIV3.forward: bf16 operands vs the fp32 oracle."""
+    import lam_slide_b200 as P
+    from lam_slide_b200.configs import get_config
+    cfg = get_config(name, depth=depth)
+    bb = cfg["backbone"]
+    bb_sd = O.init_backbone_params(bb, 31)
+    net = P.LatentSIV3(depth=depth, in_dim=bb["in_dim"], hidden_size=bb["hidden_size"], num_heads=bb["num_heads"],
+                       vec_in_dim=bb["vec_in_dim"], mlp_ratio=bb["mlp_ratio"], normalize=bb["normalize"]).cuda()
+    net.load_state_dict(bb_sd, strict=True)
+    L = cfg["first_stage"]["encoder"]["num_latents"]
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(B, T, L, bb["in_dim"], generator=g)
+    xc = torch.randn(B, T, L, bb["in_dim"], generator=g)
+    mk = (torch.rand(B, T, L, generator=g) < 0.3).long()
+    t = torch.rand(B, generator=g)
+    y = torch.randn(B, bb["vec_in_dim"], generator=g) if bb["vec_in_dim"] else None
+    with torch.no_grad():
+        ref = O.backbone_forward(bb_sd, bb, x, t, xc, mk, y)
+    out = net(x.cuda(), t.cuda(), xc.cuda(), mk.cuda(), None if y is None else y.cuda())
+    assert torch.isfinite(out).all()
+    assert max_rel(out.cpu(), ref) < VEL_TOL
+
+
+@pytest.mark.parametrize("name", ["peptide_small", "md17_small", "nba_full", "pedestrian_full", "peptide_linear_velocity",
+                                  "md17_full", "peptide_full"])
+def test_sample_vs_reference_golden(name):
+    """Full sample(): encode -> conditioning -> Euler ODE -> decode vs the golden vectors of the REAL reference."""
+    fx = load_golden(name)
+    c = CASE_BY_NAME[name]
+    cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)
+    check_inputs_match_fixture(fx, fs_sd, bb_sd, batch, noise)
+    m = _build(cfg, fs_sd, bb_sd)
+    sl = frame_slice(fx)
+    B, T = c["B"], c["T"]
+    cb = _cuda_batch(batch)
+    latents = m.encode(cb)
+    assert max_rel(latents.cpu()[:, sl], fx["latents"]) < FS_TOL
+    x_cond, x_mask = m.setup_conditioning(latents)
+    if fx["x_cond"] is not None:
+        assert max_rel(x_cond.cpu()[:, sl], fx["x_cond"]) < FS_TOL
+    # single network evaluation at t0
+    t0, _ = O.sample_interval(cfg["path_type"], cfg["prediction"])
+    yy = None if y is None else y.cuda()
+    out0 = m.backbone(noise.cuda(), torch.full((B,), t0).cuda(), x_cond, x_mask, yy)
+    assert max_rel(out0.cpu()[:, sl], fx["net_out_t0"]) < VEL_TOL
+    # fused ODE with velocity recording
+    states, vel = m.backbone.ode_sample(noise.cuda(), x_cond, x_mask, yy, path_type=cfg["path_type"], prediction=cfg["prediction"],
+                                        num_steps=c["num_steps"], return_velocities=True)
+    vel = vel.cpu()[fx["velocity_steps"]][:, :, sl]
+    for i in range(vel.shape[0]):
+        assert max_rel(vel[i], fx["velocities"][i]) < VEL_TOL, f"velocity step {fx['velocity_steps'][i]}"
+    assert max_rel(states[-1].cpu()[:, sl], fx["final_latents"]) < VEL_TOL
+    out = m.first_stage_model.decode(states[-1].flatten(0, 1), cb["entities"].flatten(0, 1))
+    main = cfg["main_output"]
+    got = out[main].unflatten(0, (B, T)).cpu()[:, sl]
+    # final-frame coordinate RMSD (data scale 1 for the synthetic N(0,1) coordinates)
+    assert rmsd(got[:, -1], fx["outputs"][main][:, -1]) < RMSD_TOL
+    assert rmsd(got, fx["outputs"][main]) < RMSD_TOL
+
+
+def test_public_sample_api_host_batch():
+    """model.sample(batch) with a HOST batch (the call a user of the reference makes): H2D inside, dict out."""
+    c = CASE_BY_NAME["nba_full"]
+    fx = load_golden("nba_full")
+    cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)
+    m = _build(cfg, fs_sd, bb_sd)
+    g = torch.Generator().manual_seed(c["seeds"][3])
+    _ = torch.randn(c["B"], c["T"], 8, 32, generator=g)
+    table = torch.randn(cfg["n_classes"], 256, generator=g)
+    m.vec_in_embedding.weight.data.copy_(table)
+    out = m.sample({k: v.clone() for k, v in batch.items()}, noise=noise)
+    assert out["pos"].shape == (c["B"], c["T"], cfg["N"], 2)
+    assert rmsd(out["pos"].cpu(), fx["outputs"]["pos"]) < RMSD_TOL
+
+
+def test_errors_are_loud():
+    import lam_slide_b200 as P
+    with pytest.raises(ValueError):
+        P.LatentSIV3(depth=1, in_dim=32, hidden_size=100, num_heads=16)
+    net = P.LatentSIV3(depth=1, in_dim=32, hidden_size=128, num_heads=4)
+    x = torch.randn(1, 4, 2, 32)
+    with pytest.raises(Exception):  # CPU tensors: no fallback
+        net(x, torch.zeros(1), x, torch.zeros(1, 4, 2, dtype=torch.long))

@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the sampling hot path (BASELINE.json: "4AA-shaped trajectory samples/sec (flow ODE)").
+
+    python bench.py --gpus N --steps K --warmup W            # native arm (this repo's CUDA path)
+    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host CPU (oracle port)
+
+One "step" = one full ``sample()`` pass (first-stage encode -> setup_conditioning -> SiT Euler ODE, num_steps=10 => 9
+evaluations of the latent transformer -> first-stage decode [-> NCCL all-gather of the decoded coordinates when N > 1])
+over one batch of synthetic 4AA-shaped trajectories (T=1000 frames, 4 residues, L=2 latents, D=96).
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the meaning of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "trajectory_samples_per_sec"
+UNIT = "trajectories/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="peptide", choices=["peptide", "md17", "nba", "pedestrian"])
+    ap.add_argument("--batch-per-gpu", type=int, default=None)
+    ap.add_argument("--num-steps", type=int, default=10, help="ODE grid points (num_steps-1 network evaluations)")
+    ap.add_argument("--T", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+DEFAULT_BATCH = {"peptide": 64, "md17": 256, "nba": 1024, "pedestrian": 1024}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(cfg, num_steps: int, B: int, reps: int, warmup: int):
+    """The oracle port of the reference's algorithm (fp32 torch CPU ops) on the host cores — a REPORTED baseline."""
+    from oracle import lamslide_oracle as O  # the one place bench.py may use oracle/: as the CPU arm
+    torch.set_num_threads(os.cpu_count())
+    O.USE_SDPA = True  # same attention library call as the reference (mmdit.py:51)
+    fs_sd = O.init_first_stage_params(cfg["first_stage"], 1)
+    bb_sd = O.init_backbone_params(cfg["backbone"], 2)
+    batch = O.synthetic_batch(cfg, B, 3)
+    L = cfg["first_stage"]["encoder"]["num_latents"]
+    g = torch.Generator().manual_seed(4)
+    noise = torch.randn(B, cfg["T"], L, cfg["backbone"]["in_dim"], generator=g)
+    y = torch.randn(B, 256, generator=g) if cfg["n_classes"] else None
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + reps):
+            t0 = time.perf_counter()
+            O.sample(fs_sd, bb_sd, cfg, batch, noise, num_steps=num_steps, y=y)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's own CPU path (oracle port; the Python reference cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.ref_batch
+    times, cores = cpu_baseline(cfg, args.num_steps, B, args.steps, args.warmup)
+    total = sum(times)
+    value = B * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{cfg['name']} sample(): T={cfg['T']}, num_steps={args.num_steps}, batch={B} (bounded CPU sample)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} x sample() of {B} trajectory(ies), fp32 torch CPU ops, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    import lam_slide_b200 as P
+    from lam_slide_b200 import _lib
+    from lam_slide_b200.configs import flops_per_eval, flops_per_trajectory
+    from lam_slide_b200.synthetic import randomize_zero_init, synthetic_batch
+
+    cfg = P.get_config(args.config)
+    if args.T:
+        cfg["T"] = args.T
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch_per_gpu or DEFAULT_BATCH[args.config]
+    T, N = cfg["T"], cfg["N"]
+    L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+
+    # model: random-init weights of the named architecture (same seed on every rank = replicated weights)
+    torch.manual_seed(0)
+    model = P.SecondStageSampler(cfg, sampling_kwargs={"sampling_method": "euler", "num_steps": args.num_steps})
+    randomize_zero_init(model, seed=1)
+    model = model.to(dev)
+
+    # synthetic inputs: per-rank shard of the global batch (seed derived from the global sample index range)
+    host_batch = synthetic_batch(cfg, B, seed=1004 + rank, pin=True)
+    dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    noise = torch.randn(B, T, L, D, device=dev, generator=g)
+    main_key = cfg["main_output"]
+    gather_buf = None
+
+    def step_device():
+        out = model.sample(dict(dev_batch), noise=noise)[main_key]
+        if dist_on:
+            nonlocal gather_buf
+            if gather_buf is None:
+                gather_buf = torch.empty((world,) + tuple(out.shape), device=dev, dtype=out.dtype)
+            dist.all_gather_into_tensor(gather_buf, out.contiguous())
+        return out
+
+    host_out = None
+
+    def step_e2e():
+        nonlocal host_out
+        out = model.sample(dict(host_batch), noise=None)[main_key]  # H2D of the batch inside; noise drawn on device like the reference
+        if host_out is None:
+            host_out = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host_out.copy_(out, non_blocking=True)
+        return out
+
+    def timed(fn, steps):
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist_on:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _lib.launch_count(reset=True)
+    ms = timed(step_device, args.steps)
+    launches = _lib.launch_count()
+    clock_info = clocks.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # end-to-end through the public API with HOST (pinned) buffers
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
+    d2h = host_out.numel() * host_out.element_size()
+
+    # per-kernel-class timing (CUDA events on the launching stream) on extra steps after the timed region
+    peaks, peaks_src = load_peaks()
+    roofline, shares = None, None
+    if not args.no_profile:
+        _lib.profile_begin()
+        pr_steps = 2
+        for _ in range(pr_steps):
+            model.sample(dict(dev_batch), noise=noise)
+        prof = _lib.profile_end()
+        tot = sum(v["ms"] for v in prof.values())
+        shares = {k: round(v["ms"] / tot, 4) for k, v in prof.items() if v["ms"] > 0}
+        bb = cfg["backbone"]
+        H, M, depth = bb["hidden_size"], int(bb["mlp_ratio"] * bb["hidden_size"]), bb["depth"]
+        n_tok = B * T * L
+        evals = args.num_steps - 1
+        flops = {  # algorithmic FLOPs per launch (SURVEY.md §8(d) terms), per kernel class
+            "gemm_linear1": 2.0 * n_tok * H * (3 * H + M),
+            "gemm_linear2": 2.0 * n_tok * (H + M) * H,
+            "attn_temporal": 4.0 * bb["num_heads"] * (H // bb["num_heads"]) * B * L * T * T,
+        }
+        dom = max(flops, key=lambda k: prof[k]["ms"])
+        n_launch = prof[dom]["launch_groups"]
+        ms_per_launch = prof[dom]["ms"] / n_launch
+        achieved = flops[dom] / (ms_per_launch * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": f"{peaks_src} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "ms_per_launch": ms_per_launch, "launches_per_step": n_launch / pr_steps,
+                    "share_of_step": shares.get(dom)}
+        ftraj = flops_per_trajectory(cfg, args.num_steps)
+        whole = {"achieved_tflops_per_gpu": ftraj * value / world / 1e12,
+                 "frac_of_burst_peak": ftraj * value / world / 1e12 / peaks["bf16_tflops"],
+                 "frac_of_sustained_peak": ftraj * value / world / 1e12 / peaks["bf16_tflops_sustained"]}
+    else:
+        whole = None
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        times, cores = cpu_baseline(cfg, args.num_steps, 1, reps=3, warmup=1)
+        cpu = {"value": len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"3 x sample() of 1 trajectory (T={T}, num_steps={args.num_steps}), oracle port of the reference, fp32 torch CPU ops"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.config} sample(): encode + Euler ODE (num_steps={args.num_steps} => {args.num_steps - 1} evals) + decode"
+                                   + (" + all_gather" if dist_on else ""),
+                       "batch_per_gpu": B, "global_batch": B * world, "T": T, "entities": N, "latents": L, "latent_dim": D,
+                       "parallelism": f"batch-sharded x{world}", "weights": "random-init (seeded), zero-init layers re-drawn N(0,0.02)",
+                       "l2": "working set (activations ~GBs per step) is far larger than the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clock_info,
+            "roofline": roofline,
+            "whole_step": whole,
+            "kernel_time_shares": shares,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

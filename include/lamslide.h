@@ -147,6 +147,12 @@ const char* lamslide_last_error(void);
 /* number of kernels this library launched on the calling thread since the last reset (bench.py's gpu_launches). */
 int64_t lamslide_launch_count(int32_t reset);
 
+/* Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline and time shares).
+ * begin() arms it for the calling thread; end() synchronises the device and writes a JSON object
+ * {"gemm_linear1": {"ms": .., "launch_groups": ..}, ...} into json_out.  Not for use under CUDA-graph capture. */
+int lamslide_profile_begin(void);
+int lamslide_profile_end(char* json_out, size_t json_bytes);
+
 /* test hooks (tests/ only): the tcgen05 GEMM in isolation, C[M,N] = A[M,K] B[N,K]^T (+ bias); A, B device bf16, C device fp32. */
 int lamslide_debug_gemm(const void* a_bf16, const void* b_bf16, const float* bias, float* c, int32_t M, int32_t N, int32_t K,
                         int32_t block_n, void* stream);

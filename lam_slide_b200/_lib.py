@@ -21,6 +21,7 @@ SYMBOLS = [
     "lamslide_backbone_forward", "lamslide_ode_sample", "lamslide_euler_step", "lamslide_setup_conditioning",
     "lamslide_first_stage_create", "lamslide_first_stage_destroy", "lamslide_first_stage_workspace_bytes",
     "lamslide_encode", "lamslide_decode", "lamslide_debug_gemm", "lamslide_debug_attention",
+    "lamslide_profile_begin", "lamslide_profile_end",
 ]
 
 
@@ -96,6 +97,7 @@ def load() -> C.CDLL:
     lib.lamslide_decode.argtypes = [vp, vp, vp, C.POINTER(vp), i32, i32, vp, sz, vp]
     lib.lamslide_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.lamslide_debug_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.lamslide_profile_end.argtypes = [C.c_char_p, sz]
     if lib.lamslide_abi_version() != 1:
         raise LamSlideError("liblamslide.so ABI version mismatch")
     _lib = lib
@@ -136,6 +138,17 @@ def pack_state_dict(sd: Dict[str, torch.Tensor]) -> Tuple[C.Array, List[torch.Te
         items.append(d)
     arr = (TensorDesc * len(items))(*items)
     return arr, keep
+
+
+def profile_begin() -> None:
+    check(load().lamslide_profile_begin())
+
+
+def profile_end() -> dict:
+    import json
+    buf = C.create_string_buffer(8192)
+    check(load().lamslide_profile_end(buf, 8192))
+    return json.loads(buf.value.decode())
 
 
 def ptr(t) -> int:

@@ -149,7 +149,11 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(float* __restrict__
 
 // ---- LayerNorm (no affine, eps 1e-6) + adaLN modulate (mmdit.py:21-22) -> bf16 A operand of the next GEMM
 //   u[row, :] = LN(h[row, :]) * (1 + scale[b, :]) + shift[b, :],  b = row / rows_per_sample;  warp per row, H = 128 * HV
-template <int HV>
+// SPLIT3 (final head only): the row is written as [hi | lo | hi] (3H bf16), hi = bf16(u), lo = bf16(u - hi); together with
+// a [W_hi | W_hi | W_lo] weight the ordinary bf16 GEMM then evaluates u_hi W_hi + u_lo W_hi + u_hi W_lo, i.e. the head
+// projection at ~16 mantissa bits.  The head is 0.4 % of the FLOPs but its operand rounding would otherwise dominate the
+// error of the predicted latent (and hence the decoded coordinates).
+template <int HV, bool SPLIT3 = false>
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ h, __nv_bfloat16* __restrict__ u, const float* __restrict__ shift,
                    const float* __restrict__ scale, int mod_stride, int rows, int rows_per_sample) {
@@ -176,7 +180,7 @@ ln_modulate_kernel(const float* __restrict__ h, __nv_bfloat16* __restrict__ u, c
   const int b = row / rows_per_sample;
   const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
   const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
-  uint2* up = reinterpret_cast<uint2*>(u + (size_t)row * H);
+  uint2* up = reinterpret_cast<uint2*>(u + (size_t)row * H * (SPLIT3 ? 3 : 1));
 #pragma unroll
   for (int i = 0; i < HV; ++i) {
     float4 a = __ldg(sc + lane + 32 * i), c = __ldg(sh + lane + 32 * i);
@@ -184,7 +188,14 @@ ln_modulate_kernel(const float* __restrict__ h, __nv_bfloat16* __restrict__ u, c
     float y1 = fmaf(v[i].y * rstd, 1.0f + a.y, c.y);
     float y2 = fmaf(v[i].z * rstd, 1.0f + a.z, c.z);
     float y3 = fmaf(v[i].w * rstd, 1.0f + a.w, c.w);
-    up[lane + 32 * i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    uint2 hi = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    up[lane + 32 * i] = hi;
+    if constexpr (SPLIT3) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
+      float2 f01 = __bfloat1622float2(h2[0]), f23 = __bfloat1622float2(h2[1]);
+      up[H / 4 + lane + 32 * i] = make_uint2(pack_bf16x2(y0 - f01.x, y1 - f01.y), pack_bf16x2(y2 - f23.x, y3 - f23.y));
+      up[2 * (H / 4) + lane + 32 * i] = hi;
+    }
   }
 }
 

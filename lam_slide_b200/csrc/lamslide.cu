@@ -57,6 +57,36 @@ static int fail(int code, const char* fmt, ...) {
     if (_r != 0) return _r;  \
   } while (0)
 
+// ================================================================================================ per-kernel-class timing
+// Optional CUDA-event timing of kernel classes on the launching stream (bench.py's roofline / time shares).  Off by default.
+enum ProfCat { PC_EMBED = 0, PC_VEC, PC_LNMOD, PC_LINEAR1, PC_ATTN_SPATIAL, PC_ATTN_TEMPORAL, PC_LINEAR2, PC_HEAD, PC_EULER,
+               PC_ENCODE, PC_DECODE, PC_COND, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"embed_in", "vec_path", "ln_modulate", "gemm_linear1", "attn_spatial", "attn_temporal",
+                                           "gemm_linear2", "gemm_head", "drift_euler", "fs_encode", "fs_decode", "conditioning"};
+struct ProfRec {
+  int cat;
+  cudaEvent_t a, b;
+};
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfRec r;
+  ProfScope(int cat, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (!on) return;
+    r.cat = cat;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, st);
+    g_prof.push_back(r);
+  }
+};
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -347,9 +377,20 @@ extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, con
   {
     GET(w, "linear.weight", D, H);
     GET(b, "linear.bias", D);
-    TRY(A.upload_bf16(w->data, (size_t)D * H, &bb->w_out));
+    // split head weight [W_hi | W_hi | W_lo] (see ln_modulate_kernel<.., SPLIT3>)
+    std::vector<__nv_bfloat16> w3((size_t)D * 3 * H);
+    for (int r = 0; r < D; ++r)
+      for (int k = 0; k < H; ++k) {
+        float v = w->data[(size_t)r * H + k];
+        __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        w3[(size_t)r * 3 * H + k] = hi;
+        w3[(size_t)r * 3 * H + H + k] = hi;
+        w3[(size_t)r * 3 * H + 2 * H + k] = lo;
+      }
+    TRY(A.upload(w3.data(), w3.size() * sizeof(__nv_bfloat16), (void**)&bb->w_out));
     TRY(A.upload_f32(b->data, D, &bb->b_out));
-    TRY(make_tmap(&bb->tm_wout, bb->w_out, D, H, bn_out));
+    TRY(make_tmap(&bb->tm_wout, bb->w_out, D, 3 * H, bn_out));
   }
 #undef GET
   *out = guard.release();
@@ -436,6 +477,20 @@ static int attention_dispatch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int 
   }
 }
 
+static int ln_modulate_split3(const lamslide_backbone* bb, const float* h, __nv_bfloat16* u3, const float* shift, const float* scale,
+                              int rows, int rows_per_sample, cudaStream_t st) {
+  dim3 grid(cdiv(rows, 8));
+  switch (bb->H / 128) {
+    case 1: ln_modulate_kernel<1, true><<<grid, 256, 0, st>>>(h, u3, shift, scale, bb->mod_width, rows, rows_per_sample); break;
+    case 2: ln_modulate_kernel<2, true><<<grid, 256, 0, st>>>(h, u3, shift, scale, bb->mod_width, rows, rows_per_sample); break;
+    case 3: ln_modulate_kernel<3, true><<<grid, 256, 0, st>>>(h, u3, shift, scale, bb->mod_width, rows, rows_per_sample); break;
+    case 4: ln_modulate_kernel<4, true><<<grid, 256, 0, st>>>(h, u3, shift, scale, bb->mod_width, rows, rows_per_sample); break;
+    default: return fail(LAMSLIDE_ERR_INVALID, "hidden_size %d unsupported", bb->H);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
 static int ln_modulate(const lamslide_backbone* bb, const float* h, __nv_bfloat16* u, const float* shift, const float* scale, int rows,
                        int rows_per_sample, cudaStream_t st) {
   dim3 grid(cdiv(rows, 8));
@@ -452,8 +507,7 @@ static int ln_modulate(const lamslide_backbone* bb, const float* h, __nv_bfloat1
 
 struct ForwardCtx {
   BackboneWorkspace ws;
-  CUtensorMap tm_u, tm_act;
-  bool tables_ready = false;
+  CUtensorMap tm_u, tm_act, tm_u3;
 };
 
 static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, int L, void* workspace, size_t workspace_bytes,
@@ -467,6 +521,7 @@ static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, 
   if (n > 0x7fffffffLL / 4) return fail(LAMSLIDE_ERR_INVALID, "too many tokens (%lld)", n);
   TRY(make_tmap(&fc.tm_u, fc.ws.u, (uint64_t)n, bb->H, kBlockM));
   TRY(make_tmap(&fc.tm_act, fc.ws.act, (uint64_t)n, bb->H + bb->M, kBlockM));
+  TRY(make_tmap(&fc.tm_u3, fc.ws.qkv, (uint64_t)n, 3 * bb->H, kBlockM));  // head input [hi | lo | hi] reuses the qkv buffer
   const int half = bb->hd / 2;
   rope_table_kernel<<<cdiv(L * half, 256), 256, 0, st>>>(fc.ws.cos_s, fc.ws.sin_s, L, half, (double)bb->cfg.theta);
   LAUNCH_CHECK();
@@ -485,6 +540,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
 
   // 1. h = x_in(x) + cond_to_emb(x_cond) + mask_to_emb(mask) [+ layer_norm]
   {
+    ProfScope ps(PC_EMBED, st);
     size_t smem = (size_t)2 * D * 36 * sizeof(float);
     if (H <= 256) {
       embed_in_kernel<1><<<cdiv(n, 32), 256, smem, st>>>(x, x_cond, (const long long*)mask, bb->wt_in, bb->b_in, bb->emask, w.h, n, D, H);
@@ -499,6 +555,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   }
   // 2. vec = time_in(timestep_embedding(t)) [+ vec_in(y)];  all modulations of all layers in one matrix product
   {
+    ProfScope ps(PC_VEC, st);
     timestep_embed_kernel<<<cdiv(B * 128, 256), 256, 0, st>>>(t, w.e, B);
     LAUNCH_CHECK();
     TRY(vec_linear(w.e, 256, bb->time_w1, bb->time_b1, nullptr, w.hid, H, B, H, 256, 0, 1, st));
@@ -515,7 +572,10 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
     for (int s = 0; s < 2; ++s) {
       const BlockWeights& bw = bb->blocks[2 * i + s];
       const float* modl = w.mod + (size_t)i * 6 * H + (size_t)s * 3 * H;  // shift | scale | gate
-      TRY(ln_modulate(bb, w.h, w.u, modl, modl + H, n, T * L, st));
+      {
+        ProfScope ps(PC_LNMOD, st);
+        TRY(ln_modulate(bb, w.h, w.u, modl, modl + H, n, T * L, st));
+      }
       SeqMap sm;
       int n_seq;
       const float *cs, *sn;
@@ -530,6 +590,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
         cs = w.cos_t, sn = w.sin_t, pos_div = L, pos_mod = T;
       }
 #define L1_PARAMS(HD_)                                                                                               \
+  ProfScope ps(PC_LINEAR1, st);                                                                                        \
   typename EpiLinear1<HD_>::Params ep{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul}; \
   TRY(launch_linear1<HD_>(bb, fc.tm_u, bw, n, ep, st));
       if (hd == 16) {
@@ -540,17 +601,24 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
         L1_PARAMS(32)
       }
 #undef L1_PARAMS
-      TRY(attention_dispatch(w.qkv, w.act, H, H + M, heads, hd, sm, n_seq, false, st));
-      EpiLinear2::Params e2{w.h, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, n};
-      TRY(launch_linear2(bb, fc.tm_act, bw, n, e2, st));
+      {
+        ProfScope ps(s == 0 ? PC_ATTN_SPATIAL : PC_ATTN_TEMPORAL, st);
+        TRY(attention_dispatch(w.qkv, w.act, H, H + M, heads, hd, sm, n_seq, false, st));
+      }
+      {
+        ProfScope ps(PC_LINEAR2, st);
+        EpiLinear2::Params e2{w.h, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, n};
+        TRY(launch_linear2(bb, fc.tm_act, bw, n, e2, st));
+      }
     }
   }
   // 4. final adaLN + linear
   {
+    ProfScope ps(PC_HEAD, st);
     const float* ada = w.mod + (size_t)bb->depth * 6 * H;  // shift | scale
-    TRY(ln_modulate(bb, w.h, w.u, ada, ada + H, n, T * L, st));
+    TRY(ln_modulate_split3(bb, w.h, w.qkv, ada, ada + H, n, T * L, st));
     EpiPlain::Params ep{out ? out : w.m_out, bb->b_out, D, n};
-    TRY(launch_plain(bb->bn_out, fc.tm_u, bb->tm_wout, n, D, H, ep, st));
+    TRY(launch_plain(bb->bn_out, fc.tm_u3, bb->tm_wout, n, D, 3 * H, ep, st));
   }
   return 0;
 }
@@ -650,6 +718,7 @@ extern "C" int lamslide_ode_sample(lamslide_backbone* h, float* x, const float* 
     TRY(forward_run(h, fc, x, fc.ws.tvec, x_cond, x_cond_mask, y, nullptr, B, T, L, st));
     double cm, cx;
     TRY(drift_coefficients(path_type, prediction, (double)ti, &cm, &cx));
+    ProfScope ps(PC_EULER, st);
     drift_euler_kernel<<<cdiv(n4, 256), 256, 0, st>>>(
         (const float4*)fc.ws.m_out, (float4*)x, velocities_out ? (float4*)(velocities_out + (size_t)i * nel) : nullptr,
         states_out ? (float4*)(states_out + (size_t)(i + 1) * nel) : nullptr, (float)cm, (float)cx, tn - ti, n4);
@@ -673,7 +742,9 @@ extern "C" int lamslide_euler_step(float* x, const float* net_out, int32_t path_
 extern "C" int lamslide_setup_conditioning(const float* latents, float* x_cond, int64_t* x_cond_mask, int32_t B, int32_t T, int32_t L,
                                            int32_t D, int32_t cond_begin, int32_t cond_end, int32_t mask_cond_mean, void* stream) {
   if (!latents || !x_cond || !x_cond_mask) return fail(LAMSLIDE_ERR_INVALID, "null argument");
-  if (cond_begin < 0 || cond_end > T || cond_begin >= cond_end) return fail(LAMSLIDE_ERR_INVALID, "bad cond_idx [%d, %d)", cond_begin, cond_end);
+  if (cond_end > T) cond_end = T;  // python slice semantics of latents[:, c0:c1]
+  if (cond_begin < 0 || cond_begin >= cond_end) return fail(LAMSLIDE_ERR_INVALID, "bad cond_idx [%d, %d)", cond_begin, cond_end);
+  ProfScope ps(PC_COND, (cudaStream_t)stream);
   long long tot = (long long)B * L * D;
   conditioning_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(latents, x_cond, (long long*)x_cond_mask, B, T, L, D,
                                                                         cond_begin, cond_end, mask_cond_mean);
@@ -1115,6 +1186,7 @@ extern "C" int lamslide_encode(lamslide_first_stage* h, const lamslide_frame_inp
                                void* workspace, size_t workspace_bytes, void* stream) {
   if (!in || !in->pos || !in->entities || !latents_out) return fail(LAMSLIDE_ERR_INVALID, "null argument");
   TRY(fs_check(h, frames, N, workspace, workspace_bytes));
+  ProfScope ps(PC_ENCODE, (cudaStream_t)stream);
   return encode_impl(h, in, latents_out, frames, N, workspace, nullptr, (cudaStream_t)stream);
 }
 
@@ -1122,6 +1194,7 @@ extern "C" int lamslide_decode(lamslide_first_stage* h, const float* latents, co
                                int32_t frames, int32_t N, void* workspace, size_t workspace_bytes, void* stream) {
   if (!latents || !entities || !outs) return fail(LAMSLIDE_ERR_INVALID, "null argument");
   TRY(fs_check(h, frames, N, workspace, workspace_bytes));
+  ProfScope ps(PC_DECODE, (cudaStream_t)stream);
   return decode_impl(h, latents, entities, outs, frames, N, workspace, nullptr, (cudaStream_t)stream);
 }
 
@@ -1132,6 +1205,40 @@ extern "C" int64_t lamslide_launch_count(int32_t reset) {
   int64_t v = g_launches;
   if (reset) g_launches = 0;
   return v;
+}
+
+extern "C" int lamslide_profile_begin(void) {
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+
+extern "C" int lamslide_profile_end(char* json_out, size_t json_bytes) {
+  g_prof_on = false;
+  CUDA_TRY(cudaDeviceSynchronize());
+  double ms[PC_COUNT] = {0};
+  long long cnt[PC_COUNT] = {0};
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms[r.cat] += t, cnt[r.cat]++;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  std::string js = "{";
+  for (int i = 0; i < PC_COUNT; ++i) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"launch_groups\": %lld}", i ? ", " : "", kProfNames[i], ms[i], cnt[i]);
+    js += buf;
+  }
+  js += "}";
+  if (!json_out || json_bytes < js.size() + 1) return fail(LAMSLIDE_ERR_INVALID, "profile buffer too small (%zu needed)", js.size() + 1);
+  memcpy(json_out, js.c_str(), js.size() + 1);
+  return 0;
 }
 
 extern "C" int lamslide_debug_gemm(const void* a_bf16, const void* b_bf16, const float* bias, float* c, int32_t M, int32_t N, int32_t K,

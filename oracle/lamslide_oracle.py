@@ -59,10 +59,18 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
     return y if b is None else y + b
 
 
+# When True the attention goes through the same library call the reference uses (F.scaled_dot_product_attention) instead
+# of the explicit softmax below.  Only bench.py's CPU-baseline / --impl reference legs set it, so that the reported CPU
+# number is representative of the reference's own CPU path (the explicit form materialises S x S scores and is ~2x slower).
+USE_SDPA = False
+
+
 def softmax_attention(q: Tensor, k: Tensor, v: Tensor, scale: float, key_mask: Optional[Tensor] = None) -> Tensor:
     """softmax(q kᵀ · scale [+ −inf on masked keys]) v — what F.scaled_dot_product_attention computes at
     mmdit.py:51 (no mask, scale = hd^-0.5) and torch_modules.py:184,251 (bool key mask, True = keep).
     q: [..., Sq, d], k/v: [..., Sk, d], key_mask: broadcastable to [..., 1, Sk]."""
+    if USE_SDPA:
+        return torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=key_mask, scale=scale)
     s = (q @ k.transpose(-1, -2)) * scale
     if key_mask is not None:
         s = s.masked_fill(~key_mask, float("-inf"))

@@ -192,7 +192,7 @@ def main():
         if dist_on:
             nonlocal gather_buf
             if gather_buf is None:
-                gather_buf = torch.empty((world,) + tuple(out.shape), device=dev, dtype=out.dtype)
+                gather_buf = torch.empty((world * out.shape[0],) + tuple(out.shape[1:]), device=dev, dtype=out.dtype)
             dist.all_gather_into_tensor(gather_buf, out.contiguous())
         return out
 

@@ -1,0 +1,66 @@
+"""Multi-GPU sampling: independent trajectories are batch-sharded over the ranks (one process per GPU, weights
+replicated), and the decoded coordinates are gathered with ONE collective at the end.  There is no
+data-path collective: no sample ever needs another sample's data.  The initial noise of global sample ``i`` comes from a
+generator seeded with ``(seed, i)``, so a sharded run reproduces the single-GPU run sample for sample."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_range(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, near-equal chunks: the first ``global_batch % world`` ranks get one extra sample."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch: Dict[str, Tensor], rank: int, world: int) -> Dict[str, Tensor]:
+    B = batch["entities"].shape[0]
+    lo, hi = shard_range(B, rank, world)
+    return {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == B else v) for k, v in batch.items()}
+
+
+def per_sample_noise(seed: int, lo: int, hi: int, shape: Tuple[int, ...], device: torch.device) -> Tensor:
+    """Noise [hi-lo, *shape]; sample i depends on (seed, global index i) only."""
+    out = torch.empty((hi - lo,) + tuple(shape), device=device, dtype=torch.float32)
+    for j, i in enumerate(range(lo, hi)):
+        g = torch.Generator(device=device).manual_seed((seed * 1_000_003 + i) % (2 ** 63 - 1))
+        out[j] = torch.randn(shape, device=device, generator=g)
+    return out
+
+
+def gather_samples(local: Tensor, global_batch: int, group=None) -> Tensor:
+    """All-gather the per-rank outputs [b_r, ...] into [global_batch, ...] (ragged shards are padded to the largest)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_range(global_batch, r, world) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    pad = local
+    if local.shape[0] < mx:
+        pad = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))])
+    buf = local.new_empty((world * mx,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(buf, pad.contiguous(), group=group)
+    if all(hi - lo == mx for lo, hi in sizes):
+        return buf
+    buf = buf.view((world, mx) + tuple(local.shape[1:]))
+    return torch.cat([buf[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)])
+
+
+@torch.no_grad()
+def sample_sharded(model, batch: Dict[str, Tensor], seed: int = 0, gather: bool = True, group=None) -> Tensor:
+    """``model.sample`` on this rank's shard of a replicated host/device batch, then one all-gather of the main output."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B, T = batch["entities"].shape[:2]
+    lo, hi = shard_range(B, rank, world)
+    local = shard_batch(batch, rank, world)
+    cfg = model.cfg
+    L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+    noise = per_sample_noise(seed, lo, hi, (T, L, D), model.device)
+    out = model.sample(dict(local), noise=noise)[cfg["main_output"]]
+    return gather_samples(out, B, group) if gather else out

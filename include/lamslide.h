@@ -157,9 +157,20 @@ int lamslide_profile_end(char* json_out, size_t json_bytes);
 int lamslide_debug_gemm(const void* a_bf16, const void* b_bf16, const float* bias, float* c, int32_t M, int32_t N, int32_t K,
                         int32_t block_n, void* stream);
 /* the attention kernels in isolation on a token-major qkv buffer [tokens, 3H] bf16 -> out [tokens, ldo] bf16.
- * temporal != 0: sequences over T (stride L); else over L.  force_flash: use the flash kernel even for short sequences. */
+ * temporal != 0: sequences over T (stride L); else over L.  mode: 0 = automatic choice, 1 = streaming flash kernel
+ * (running maximum), 2 = whole-sequence kernel (K/V resident in shared memory, no running maximum). */
 int lamslide_debug_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t L, int32_t H, int32_t heads,
-                             int32_t ldo, int32_t temporal, int32_t force_flash, void* stream);
+                             int32_t ldo, int32_t temporal, int32_t mode, void* stream);
+/* linear1 of one ParallelMLPAttentionV2 block with its fused epilogue (mmdit.py:241-247: bias, QK-RMSNorm, RoPE, q pre-scale,
+ * erf-GELU) in isolation: u [rows,H] bf16, w1 [3H+M,H] bf16 -> qkv [rows,3H] bf16, act[:, H:] of [rows,H+M] bf16.
+ * The rope position of a row is (row / pos_div) % pos_mod.  legacy != 0: one-tile-per-CTA kernel; 0: persistent kernel. */
+int lamslide_debug_linear1(const void* u_bf16, const void* w1_bf16, const float* bias, const float* q_scale, const float* k_scale,
+                           void* qkv_bf16, void* act_bf16, int32_t rows, int32_t H, int32_t M, int32_t heads, int32_t pos_div,
+                           int32_t pos_mod, float theta, int32_t legacy, void* stream);
+/* linear2 + gated residual (mmdit.py:248; latent_si_v31.py:54,61) in isolation: h [rows,H] fp32 += gate[row / rows_per_sample]
+ * * (act [rows,H+M] bf16 . w2 [H,H+M]^T + bias).  gate: [n_samples, H] fp32. */
+int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16, const float* bias, const float* gate, float* h, int32_t rows,
+                           int32_t H, int32_t M, int32_t rows_per_sample, int32_t legacy, void* stream);
 
 #ifdef __cplusplus
 }

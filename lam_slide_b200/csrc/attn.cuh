@@ -195,6 +195,178 @@ attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restri
   }
 }
 
+// ---- attn_seq_kernel: whole-sequence K/V resident in shared memory, no running maximum -------------------------------
+// q and k are RMS-normalised (|q|, |k| <= sqrt(hd) * max|scale|), so every logit of the block is bounded by
+//   bound = hd * max|q_scale| * max|k_scale| * hd^-0.5 * log2(e)          (computed on the host at pack time)
+// and softmax can be evaluated as exp2(s) / sum exp2(s) directly in fp32 (shift invariance): no row maximum, no rescale of
+// the accumulator, no cross-lane traffic in the key loop.  The host selects this kernel only when bound <= 64.
+//   grid.x = n_seq * heads (head fastest: the 16 CTAs that share the 128-byte lines of a token row run together);
+//   256 threads = 8 warps x 32 query rows (two m16 tiles share every K / V fragment); all of K and V of the (sequence, head)
+//   is cp.async'ed once into shared memory (row pitch chosen so ldmatrix is conflict-free), then each warp streams over the
+//   keys 16 at a time:  QK^T = m16n8k16 (+ m16n8k8 for the hd = 24 tail), 16 ex2 per thread, P.V = m16n8k16.  No block-level
+//   barrier inside the loop; 2 CTAs per SM overlap one CTA's load phase with the other's math.
+template <int HD>
+struct AttnSeqCfg {
+  static constexpr int PITCH = (HD == 32) ? 40 : 24;  // bf16 elements per K / V row: 48 B (hd 16, 24) or 80 B (hd 32)
+  static __host__ __device__ int s16(int S) { return (S + 15) & ~15; }
+  static __host__ __device__ size_t smem_bytes(int S) { return (size_t)2 * s16(S) * PITCH * 2; }
+};
+
+template <int HD>
+__global__ void __launch_bounds__(256, 2)
+attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, SeqMap sm, int heads) {
+  using Cfg = AttnSeqCfg<HD>;
+  constexpr int PITCH = Cfg::PITCH;
+  constexpr int CH = HD / 8;       // 16-byte chunks per row
+  constexpr int K16 = HD / 16;     // k16 steps of QK^T
+  constexpr bool K8 = (HD % 16) == 8;
+  constexpr int NT = HD / 8;       // n-tiles of P.V
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  const int S = sm.S;
+  const int S16 = Cfg::s16(S);
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(attn_smem);
+  __nv_bfloat16* Vs = Ks + (size_t)S16 * PITCH;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int z = blockIdx.x / heads;
+  const int hh = blockIdx.x % heads;
+  const long long base = sm.base(z);
+  const size_t ldq = (size_t)3 * H;
+  const __nv_bfloat16* qptr = qkv + hh * HD;
+  const __nv_bfloat16* kptr = qkv + H + hh * HD;
+  const __nv_bfloat16* vptr = qkv + 2 * H + hh * HD;
+
+  // ---- K, V -> shared memory (rows >= S zero-filled)
+  for (int idx = tid; idx < S16 * CH; idx += 256) {
+    const int r = idx / CH, c = idx % CH;
+    const bool ok = r < S;
+    const size_t tok = (size_t)(base + (long long)(ok ? r : 0) * sm.seq_stride);
+    cp_async16(Ks + (size_t)r * PITCH + c * 8, kptr + tok * ldq + c * 8, ok);
+    cp_async16(Vs + (size_t)r * PITCH + c * 8, vptr + tok * ldq + c * 8, ok);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ldmatrix lane addressing.  K (non-transposed, B operand "col"): matrix m = lane / 8 -> keys (m / 2) * 8 + lane % 8,
+  // d-chunk m % 2.  V (transposed): matrix m -> keys (m % 2) * 8 + lane % 8, d-chunk m / 2.
+  const int lm = lane >> 3, lr = lane & 7;
+  const uint32_t k_lane_off = (uint32_t)(((lm >> 1) * 8 + lr) * PITCH + (lm & 1) * 8) * 2;
+  const uint32_t k_lane_off8 = (uint32_t)((((lm & 1)) * 8 + lr) * PITCH + 16) * 2;  // x2: keys (m & 1) * 8 + r, d 16..23
+  const uint32_t v_lane_off = (uint32_t)(((lm & 1) * 8 + lr) * PITCH + (lm >> 1) * 8) * 2;
+  const uint32_t ks_base = smem_u32(Ks), vs_base = smem_u32(Vs);
+  const int nkb = S16 / 16;
+
+  for (int q_base = warp * 32; q_base < S; q_base += 256) {
+    // ---- Q fragments (two m16 tiles) straight from global memory
+    uint32_t aq[2][K16 > 0 ? K16 : 1][4];
+    uint32_t aq8[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        const int row = q_base + mt * 16 + g + hr * 8;
+        const bool ok = row < S;
+        const __nv_bfloat16* qp = qptr + (size_t)(base + (long long)(ok ? row : 0) * sm.seq_stride) * ldq;
+#pragma unroll
+        for (int ks = 0; ks < K16; ++ks) {
+          aq[mt][ks][hr] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + t * 2) : 0u;
+          aq[mt][ks][hr + 2] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8 + t * 2) : 0u;
+        }
+        if constexpr (K8) aq8[mt][hr] = ok ? *reinterpret_cast<const uint32_t*>(qp + K16 * 16 + t * 2) : 0u;
+      }
+    }
+    float o[2][NT][4];
+    float l[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      l[mt][0] = l[mt][1] = 0.f;
+#pragma unroll
+      for (int d = 0; d < NT; ++d) o[mt][d][0] = o[mt][d][1] = o[mt][d][2] = o[mt][d][3] = 0.f;
+    }
+
+#pragma unroll 2
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint32_t krow = (uint32_t)(kb * 16 * PITCH * 2);
+      // K fragments: kf[ks][nt*2 + {0,1}] = (b0, b1) of n-tile nt for k16 step ks; kf8[nt] for the k8 tail
+      uint32_t kf[K16 > 0 ? K16 : 1][4];
+      uint32_t kf8[2];
+#pragma unroll
+      for (int ks = 0; ks < K16; ++ks) ldmatrix_x4(kf[ks], ks_base + krow + k_lane_off + ks * 32);
+      if constexpr (K8) ldmatrix_x2(kf8, ks_base + krow + k_lane_off8 + (K16 - 1) * 32);
+      float s[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma_bf16_16816_z(s[mt][nt], aq[mt][0], kf[0][2 * nt], kf[0][2 * nt + 1]);
+#pragma unroll
+          for (int ks = 1; ks < K16; ++ks) mma_bf16_16816(s[mt][nt], aq[mt][ks], kf[ks][2 * nt], kf[ks][2 * nt + 1]);
+          if constexpr (K8) mma_bf16_1688(s[mt][nt], aq8[mt], kf8[nt]);
+        }
+      }
+      // V fragments: vf[2 * d + {0,1}] = (b0, b1) of d-tile d (k = 16 keys)
+      uint32_t vf[2 * NT];
+#pragma unroll
+      for (int d2 = 0; d2 + 1 < NT; d2 += 2) ldmatrix_x4_trans(vf + 2 * d2, vs_base + krow + v_lane_off + d2 * 16);
+      if constexpr (NT % 2 == 1) {
+        uint32_t r0, r1;
+        ldmatrix_x2_trans(r0, r1, vs_base + krow + (uint32_t)((lane & 15) * PITCH + (NT - 1) * 8) * 2);
+        vf[2 * (NT - 1)] = r0, vf[2 * (NT - 1) + 1] = r1;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[mt][nt][e] = fast_exp2(s[mt][nt][e]);
+        }
+      }
+      if (kb == nkb - 1 && S16 != S) {  // zero the probabilities of the padding keys (zero-filled K rows give exp2(0) = 1)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (kb * 16 + nt * 8 + t * 2 + (e & 1) >= S) s[mt][nt][e] = 0.f;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        l[mt][0] += (s[mt][0][0] + s[mt][0][1]) + (s[mt][1][0] + s[mt][1][1]);
+        l[mt][1] += (s[mt][0][2] + s[mt][0][3]) + (s[mt][1][2] + s[mt][1][3]);
+        uint32_t ap[4];
+        ap[0] = pack_bf16x2(s[mt][0][0], s[mt][0][1]);
+        ap[1] = pack_bf16x2(s[mt][0][2], s[mt][0][3]);
+        ap[2] = pack_bf16x2(s[mt][1][0], s[mt][1][1]);
+        ap[3] = pack_bf16x2(s[mt][1][2], s[mt][1][3]);
+#pragma unroll
+        for (int d = 0; d < NT; ++d) mma_bf16_16816(o[mt][d], ap, vf[2 * d], vf[2 * d + 1]);
+      }
+    }
+
+    // ---- finalize: row sums across the quad, normalise, store bf16
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        float lv = l[mt][hr];
+        lv += __shfl_xor_sync(0xffffffffu, lv, 1);
+        lv += __shfl_xor_sync(0xffffffffu, lv, 2);
+        const float inv = 1.f / lv;
+        const int row = q_base + mt * 16 + g + hr * 8;
+        if (row < S) {
+          __nv_bfloat16* op = out + (size_t)(base + (long long)row * sm.seq_stride) * ldo + hh * HD + t * 2;
+#pragma unroll
+          for (int d = 0; d < NT; ++d)
+            *reinterpret_cast<uint32_t*>(op + d * 8) = pack_bf16x2(o[mt][d][2 * hr] * inv, o[mt][d][2 * hr + 1] * inv);
+        }
+      }
+    }
+  }
+}
+
 // One thread per (token, head); S <= 32 keys, contiguous or strided.  Online softmax in the exp2 domain.
 template <int HD>
 __global__ void __launch_bounds__(256)

@@ -1,0 +1,412 @@
+// Persistent, warp-specialised tcgen05 GEMM for the two big projections of every ParallelMLPAttentionV2 block
+// (mmdit.py:240-249):  D[rows, N] = A[rows, K] · B[N, K]^T, bf16 operands, fp32 accumulation in TMEM.
+//
+// One CTA per SM (grid = min(#SM, #m-blocks)); a CTA walks m-blocks  mb = blockIdx.x, + gridDim.x, ...  and, inside an
+// m-block, all n-tiles, so the 128 x K activation tile is fetched ONCE per m-block when it fits (A-resident mode,
+// K <= 512: linear1) and only the weight tiles stream through the TMA ring from L2.  Warp roles (320 threads):
+//   warp 0      : TMA producer (one lane): A k-blocks (resident or ring) + B ring, mbarrier complete_tx
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer, TWO accumulator stages (2 x BN TMEM columns)
+//   warps 2..9  : epilogue.  All 8 warps work on the same tile: warp w owns TMEM lanes 32*(w%4).. (hardware rule) and
+//                 the column half (w-2)/4.  Each thread pulls its BN/2 accumulators into registers with three
+//                 tcgen05.ld.x32, releases the TMEM stage at once (the MMA warp moves on to the tile after next while
+//                 the math runs from registers), applies the fused epilogue, stages bf16 / fp32 boxes of 32 rows in
+//                 swizzled shared memory (conflict-free thread-per-row writes) and hands them to the TMA unit:
+//                 plain tensor stores for linear1, f32 reduce-add (h += gate * (acc + bias), done at L2) for linear2.
+//                 No thread-level global stores, no uncoalesced traffic.
+// Every mbarrier wait is bounded (ptx.cuh: mbar_wait) so a protocol error is a failed launch, never a hung GPU.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace lam {
+
+constexpr int kWsThreads = 320;
+constexpr int kWsEpiWarps = 8;
+constexpr int kWsStageBytesPerWarp = 4096;  // two 2 KB box buffers
+constexpr int kWsMaxKBlocksResident = 8;
+
+struct WsCtx {
+  const CUtensorMap* o0;
+  const CUtensorMap* o1;
+  uint8_t* stage;    // this warp's 4 KB staging area
+  const float* smf;  // per-kernel fp32 constants in shared memory (bias, ...)
+  int lane;
+  int row0;          // first global row of this warp's 32-row slice
+  uint32_t nstore;   // boxes issued so far by this warp (selects the staging buffer)
+};
+
+// byte offset of (row r, 16-byte chunk c) inside a staged box whose rows are IB bytes wide; matches the TMA swizzle
+// mode chosen on the host for that width (32 B -> SWIZZLE_32B, 48 B -> none, 64 B -> SWIZZLE_64B).  In all three cases
+// the 8 threads of a quarter warp hit 8 distinct 16-byte bank groups.
+template <int IB>
+__device__ __forceinline__ uint32_t stage_off(int r, int c) {
+  static_assert(IB == 32 || IB == 48 || IB == 64, "unsupported staged row width");
+  if constexpr (IB == 32) return r * 32 + ((c ^ ((r >> 2) & 1)) << 4);
+  if constexpr (IB == 48) return r * 48 + (c << 4);
+  return r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+}
+
+__device__ __forceinline__ uint8_t* stage_begin(WsCtx& c) {
+  if (c.lane == 0) bulk_wait_read<1>();  // the store issued two boxes ago (same buffer) has finished reading
+  __syncwarp();
+  return c.stage + (c.nstore & 1) * 2048;
+}
+template <bool REDUCE>
+__device__ __forceinline__ void stage_commit(WsCtx& c, const CUtensorMap* tm, const uint8_t* buf, int col) {
+  fence_proxy_async();  // generic-proxy writes of every lane -> visible to the async proxy (TMA)
+  __syncwarp();
+  if (c.lane == 0) {
+    if constexpr (REDUCE) tma_reduce_add_2d(tm, buf, col, c.row0);
+    else tma_store_2d(tm, buf, col, c.row0);
+    bulk_commit();
+  }
+  ++c.nstore;
+}
+
+// ------------------------------------------------------------------------------------------------ linear1 epilogue
+// Columns [0,3H) are (K=3, heads, hd) q|k|v, columns [3H,3H+M) the MLP (mmdit.py:241-247):
+//   q,k : + bias -> RMSNorm over the head (fp32, eps 1e-6, * scale; mmdit.py:132-136) -> RoPE on interleaved pairs
+//         (mmdit.py:85-90) -> q additionally * (hd^-0.5 * log2 e) -> bf16 -> qkv[rows, 3H]
+//   v   : + bias -> bf16 -> qkv
+//   mlp : + bias -> erf-GELU (mmdit.py:11-18; ptx.cuh gelu_fast) -> bf16 -> act[:, H + j]   (A operand of linear2)
+template <int HD>
+struct EpiLinear1Ws {
+  struct Params {
+    const float* bias;      // [3H + M]
+    const float* q_scale;   // [HD]
+    const float* k_scale;   // [HD]
+    const float* rope_cos;  // [S, HD/2]
+    const float* rope_sin;
+    int H, M, rows;
+    int pos_div, pos_mod;   // rope position of a row = (row / pos_div) % pos_mod
+    float q_premul;         // hd^-0.5 * log2(e)
+  };
+  static __host__ __device__ int smem_floats(const Params& p) { return 3 * p.H + p.M + 2 * HD; }
+  static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
+    const int N = 3 * p.H + p.M;
+    for (int i = tid; i < N; i += nthreads) smf[i] = p.bias[i];
+    for (int i = tid; i < HD; i += nthreads) {
+      smf[N + i] = p.q_scale[i] * p.q_premul;
+      smf[N + HD + i] = p.k_scale[i];
+    }
+  }
+  // n-tile order: MLP (MUFU-heavy epilogue) and q/k/v tiles alternate so the epilogue load is even over time
+  template <int BN>
+  static __device__ __forceinline__ int tile_n0(const Params& p, int nt) {
+    const int nq = 3 * p.H / BN, nm = p.M / BN;
+    const int pairs = nq < nm ? nq : nm;
+    if (nt < 2 * pairs) return (nt & 1) ? (nt >> 1) * BN : 3 * p.H + (nt >> 1) * BN;
+    const int r = nt - 2 * pairs + pairs;
+    return nq > nm ? r * BN : 3 * p.H + r * BN;
+  }
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0h) {
+    constexpr int HALF = BN / 2;
+    static_assert(HALF % HD == 0 && HALF % 32 == 0, "a warp's column half must hold whole heads and whole 32-column boxes");
+    const int H3 = 3 * p.H;
+    if (n0h >= H3) {  // ---- MLP: GELU
+#pragma unroll
+      for (int b = 0; b < HALF / 32; ++b) {
+        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0h + b * 32);
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bv = bp[j];
+          const float y0 = gelu_fast(__uint_as_float(v[b * 32 + 4 * j + 0]) + bv.x);
+          const float y1 = gelu_fast(__uint_as_float(v[b * 32 + 4 * j + 1]) + bv.y);
+          const float y2 = gelu_fast(__uint_as_float(v[b * 32 + 4 * j + 2]) + bv.z);
+          const float y3 = gelu_fast(__uint_as_float(v[b * 32 + 4 * j + 3]) + bv.w);
+          w[2 * j] = pack_bf16x2(y0, y1);
+          w[2 * j + 1] = pack_bf16x2(y2, y3);
+        }
+        uint8_t* buf = stage_begin(c);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          *reinterpret_cast<uint4*>(buf + stage_off<64>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        stage_commit<false>(c, c.o1, buf, p.H + (n0h - H3) + b * 32);
+      }
+      return;
+    }
+    const int which = n0h / p.H;  // 0 q, 1 k, 2 v   (BN divides H, so a tile — and a half tile — is one kind)
+    if (which == 2) {
+#pragma unroll
+      for (int hi = 0; hi < HALF / HD; ++hi) {
+        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0h + hi * HD);
+        uint32_t w[HD / 2];
+#pragma unroll
+        for (int j = 0; j < HD / 4; ++j) {
+          const float4 bv = bp[j];
+          w[2 * j] = pack_bf16x2(__uint_as_float(v[hi * HD + 4 * j + 0]) + bv.x, __uint_as_float(v[hi * HD + 4 * j + 1]) + bv.y);
+          w[2 * j + 1] = pack_bf16x2(__uint_as_float(v[hi * HD + 4 * j + 2]) + bv.z, __uint_as_float(v[hi * HD + 4 * j + 3]) + bv.w);
+        }
+        uint8_t* buf = stage_begin(c);
+#pragma unroll
+        for (int ch = 0; ch < HD / 8; ++ch)
+          *reinterpret_cast<uint4*>(buf + stage_off<HD * 2>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        stage_commit<false>(c, c.o0, buf, n0h + hi * HD);
+      }
+      return;
+    }
+    // ---- q or k: RMSNorm + RoPE per head
+    const float* gam = c.smf + H3 + p.M + which * HD;  // q: scale * premul, k: scale
+    const int pos = row < p.rows ? (row / p.pos_div) % p.pos_mod : 0;
+    float cs[HD / 2], sn[HD / 2];
+#pragma unroll
+    for (int i = 0; i < HD / 2; i += 4) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * (HD / 2) + i));
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * (HD / 2) + i));
+      cs[i] = c4.x, cs[i + 1] = c4.y, cs[i + 2] = c4.z, cs[i + 3] = c4.w;
+      sn[i] = s4.x, sn[i + 1] = s4.y, sn[i + 2] = s4.z, sn[i + 3] = s4.w;
+    }
+#pragma unroll
+    for (int hi = 0; hi < HALF / HD; ++hi) {
+      const float4* bp = reinterpret_cast<const float4*>(c.smf + n0h + hi * HD);
+      const float4* gp = reinterpret_cast<const float4*>(gam);
+      float x[HD];
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < HD / 4; ++j) {
+        const float4 bv = bp[j];
+        x[4 * j + 0] = __uint_as_float(v[hi * HD + 4 * j + 0]) + bv.x;
+        x[4 * j + 1] = __uint_as_float(v[hi * HD + 4 * j + 1]) + bv.y;
+        x[4 * j + 2] = __uint_as_float(v[hi * HD + 4 * j + 2]) + bv.z;
+        x[4 * j + 3] = __uint_as_float(v[hi * HD + 4 * j + 3]) + bv.w;
+        ss = fmaf(x[4 * j + 0], x[4 * j + 0], ss);
+        ss = fmaf(x[4 * j + 1], x[4 * j + 1], ss);
+        ss = fmaf(x[4 * j + 2], x[4 * j + 2], ss);
+        ss = fmaf(x[4 * j + 3], x[4 * j + 3], ss);
+      }
+      const float rstd = rsqrtf(ss * (1.0f / HD) + 1e-6f);
+      uint32_t w[HD / 2];
+#pragma unroll
+      for (int j = 0; j < HD / 4; ++j) {
+        const float4 gv = gp[j];
+        const float e0 = x[4 * j + 0] * gv.x, d0 = x[4 * j + 1] * gv.y;
+        const float e1 = x[4 * j + 2] * gv.z, d1 = x[4 * j + 3] * gv.w;
+        const float c0 = cs[2 * j] * rstd, s0 = sn[2 * j] * rstd;
+        const float c1 = cs[2 * j + 1] * rstd, s1 = sn[2 * j + 1] * rstd;
+        w[2 * j] = pack_bf16x2(fmaf(c0, e0, -s0 * d0), fmaf(s0, e0, c0 * d0));
+        w[2 * j + 1] = pack_bf16x2(fmaf(c1, e1, -s1 * d1), fmaf(s1, e1, c1 * d1));
+      }
+      uint8_t* buf = stage_begin(c);
+#pragma unroll
+      for (int ch = 0; ch < HD / 8; ++ch)
+        *reinterpret_cast<uint4*>(buf + stage_off<HD * 2>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+      stage_commit<false>(c, c.o0, buf, n0h + hi * HD);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ linear2 epilogue
+// linear2 + gated residual (mmdit.py:248, latent_si_v31.py:54,61):  h[row, n] += gate[b(row), n] * (acc + bias[n]),
+// issued as a TMA f32 reduce-add so the SM never reads h.
+struct EpiLinear2Ws {
+  struct Params {
+    const float* bias;  // [H]
+    const float* gate;  // gate of sample b at gate + b * gate_stride, [H]
+    int gate_stride;
+    int rows_per_sample;  // T * L
+    int H, rows;
+  };
+  static __host__ __device__ int smem_floats(const Params& p) { return p.H; }
+  static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
+    for (int i = tid; i < p.H; i += nthreads) smf[i] = p.bias[i];
+  }
+  template <int BN>
+  static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0h) {
+    constexpr int HALF = BN / 2;
+    static_assert(HALF % 16 == 0, "16-column fp32 boxes");
+    const int b = (row < p.rows ? row : p.rows - 1) / p.rows_per_sample;
+    const float4* g = reinterpret_cast<const float4*>(p.gate + (size_t)b * p.gate_stride + n0h);
+    const float4* bp = reinterpret_cast<const float4*>(c.smf + n0h);
+#pragma unroll
+    for (int bx = 0; bx < HALF / 16; ++bx) {
+      float4 o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 gv = __ldg(g + bx * 4 + j);
+        const float4 bv = bp[bx * 4 + j];
+        o[j].x = gv.x * (__uint_as_float(v[bx * 16 + 4 * j + 0]) + bv.x);
+        o[j].y = gv.y * (__uint_as_float(v[bx * 16 + 4 * j + 1]) + bv.y);
+        o[j].z = gv.z * (__uint_as_float(v[bx * 16 + 4 * j + 2]) + bv.z);
+        o[j].w = gv.w * (__uint_as_float(v[bx * 16 + 4 * j + 3]) + bv.w);
+      }
+      uint8_t* buf = stage_begin(c);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<float4*>(buf + stage_off<64>(c.lane, ch)) = o[ch];
+      stage_commit<true>(c, c.o0, buf, n0h + bx * 16);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct WsSmemPlan {
+  int a_res_bytes, stage_bytes, ring_bytes, staging_bytes, const_bytes, bar_bytes, total;
+};
+static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_blocks, int stages, int a_resident, int const_floats) {
+  WsSmemPlan s;
+  constexpr int kABytes = kBlockM * kBlockK * 2;
+  s.a_res_bytes = a_resident ? num_k_blocks * kABytes : 0;
+  s.stage_bytes = (a_resident ? 0 : kABytes) + BN * kBlockK * 2;
+  s.ring_bytes = stages * s.stage_bytes;
+  s.staging_bytes = kWsEpiWarps * kWsStageBytesPerWarp;
+  s.const_bytes = (const_floats * 4 + 127) / 128 * 128;
+  s.bar_bytes = 512;
+  s.total = s.a_res_bytes + s.ring_bytes + s.staging_bytes + s.const_bytes + s.bar_bytes + 1024;  // +1024: manual alignment
+  return s;
+}
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(kWsThreads, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1, int num_m_blocks,
+               int num_n_tiles, int num_k_blocks, int stages, int a_resident, typename Epi::Params ep) {
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "two accumulator stages of BN columns must fit 512 TMEM columns");
+  constexpr int kABytes = kBlockM * kBlockK * 2;
+  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr uint32_t kTmemCols = tmem_cols_for(2 * BN);
+  constexpr int HALF = BN / 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const WsSmemPlan plan = ws_smem_plan(BN, num_k_blocks, stages, a_resident, Epi::smem_floats(ep));
+  uint8_t* a_res = smem;
+  uint8_t* ring = a_res + plan.a_res_bytes;
+  uint8_t* staging = ring + plan.ring_bytes;
+  float* smf = reinterpret_cast<float*>(staging + plan.staging_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smf) + plan.const_bytes);
+  uint64_t* full_bar = bars;                                   // [stages]  (stages <= 8)
+  uint64_t* empty_bar = bars + 8;                              // [stages]
+  uint64_t* a_full = bars + 16;                                // [num_k_blocks] (<= 8)
+  uint64_t* a_empty = bars + 24;
+  uint64_t* tmem_full = bars + 32;                             // [2]
+  uint64_t* tmem_empty = bars + 34;                            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_o0);
+    tma_prefetch_desc(&tmap_o1);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int k = 0; k < kWsMaxKBlocksResident; ++k) {
+      mbar_init(&a_full[k], 1);
+      mbar_init(&a_empty[k], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kWsEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp >= 2) Epi::load_consts(ep, smf, threadIdx.x - 64, kWsThreads - 64);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0, mb_iter = 0;
+      for (int mb = blockIdx.x; mb < num_m_blocks; mb += gridDim.x, ++mb_iter) {
+        for (int nt = 0; nt < num_n_tiles; ++nt) {
+          const int n0 = Epi::template tile_n0<BN>(ep, nt);
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            if (a_resident && nt == 0) {  // refill A k-block kb as soon as the previous m-block's last tile has consumed it
+              mbar_wait(&a_empty[kb], (mb_iter & 1) ^ 1);
+              mbar_arrive_expect_tx(&a_full[kb], kABytes);
+              tma_load_2d(&tmap_a, &a_full[kb], a_res + kb * kABytes, kb * kBlockK, mb * kBlockM);
+            }
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* dst = ring + s * plan.stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[s], plan.stage_bytes);
+            if (!a_resident) {
+              tma_load_2d(&tmap_a, &full_bar[s], dst, kb * kBlockK, mb * kBlockM);
+              dst += kABytes;
+            }
+            tma_load_2d(&tmap_b, &full_bar[s], dst, kb * kBlockK, n0);
+            if (++s == stages) s = 0, ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+      int s = 0;
+      uint32_t ph = 0, mb_iter = 0, tile = 0;
+      for (int mb = blockIdx.x; mb < num_m_blocks; mb += gridDim.x, ++mb_iter) {
+        for (int nt = 0; nt < num_n_tiles; ++nt, ++tile) {
+          const uint32_t acc = tile & 1, use = tile >> 1;
+          mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator stage
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            if (a_resident && nt == 0) mbar_wait(&a_full[kb], mb_iter & 1);
+            mbar_wait(&full_bar[s], ph);
+            tcgen05_fence_after();
+            const uint32_t st_addr = smem_u32(ring + s * plan.stage_bytes);
+            const uint32_t a_addr = a_resident ? smem_u32(a_res + kb * kABytes) : st_addr;
+            const uint32_t b_addr = a_resident ? st_addr : st_addr + kABytes;
+            const uint64_t a_desc = umma_desc_sw128(a_addr);
+            const uint64_t b_desc = umma_desc_sw128(b_addr);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(&empty_bar[s]);
+            if (a_resident && nt == num_n_tiles - 1) umma_commit(&a_empty[kb]);
+            if (++s == stages) s = 0, ph ^= 1;
+          }
+          umma_commit(&tmem_full[acc]);
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps, warp = (TMEM lane quarter, column half) =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    WsCtx c;
+    c.o0 = &tmap_o0, c.o1 = &tmap_o1;
+    c.stage = staging + (warp - 2) * kWsStageBytesPerWarp;
+    c.smf = smf, c.lane = lane, c.nstore = 0;
+    uint32_t tile = 0;
+    for (int mb = blockIdx.x; mb < num_m_blocks; mb += gridDim.x) {
+      c.row0 = mb * kBlockM + q * 32;
+      const int row = c.row0 + lane;
+      for (int nt = 0; nt < num_n_tiles; ++nt, ++tile) {
+        const uint32_t acc = tile & 1, use = tile >> 1;
+        const int n0h = Epi::template tile_n0<BN>(ep, nt) + half * HALF;
+        mbar_wait(&tmem_full[acc], use & 1);
+        tcgen05_fence_after();
+        uint32_t v[HALF];
+        tmem_ld_cols<HALF>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * HALF, v);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator stage is free again: the math runs from registers
+        Epi::template run<BN>(ep, c, v, row, n0h);
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();  // staged boxes must be read out before the CTA's shared memory goes away
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace lam

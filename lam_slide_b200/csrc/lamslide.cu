@@ -19,6 +19,7 @@
 
 #include "../../include/lamslide.h"
 #include "gemm_tc.cuh"
+#include "gemm_ws.cuh"
 #include "attn.cuh"
 #include "elementwise.cuh"
 #include "first_stage.cuh"
@@ -166,6 +167,40 @@ static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t 
   return 0;
 }
 
+// general 2-D row-major tensor map: [rows, cols] elements of `elem_bytes`, box = box_cols x box_rows (TMA stores / reduces
+// of the warp-specialised GEMM epilogues; the swizzle mode must match gemm_ws.cuh: stage_off)
+static int make_tmap_ex(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
+                        uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw) {
+  auto enc = get_tmap_encoder();
+  if (!enc) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)r);
+  return 0;
+}
+static CUtensorMapSwizzle swizzle_for_row_bytes(int bytes) {
+  return bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+static bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 // ================================================================================================ GEMM launch
 template <int BN>
 struct StagesFor {
@@ -189,11 +224,47 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int rows, i
   return 0;
 }
 
+// persistent warp-specialised GEMM (gemm_ws.cuh).  Returns 1 (and launches nothing) when the shape does not fit its
+// shared-memory plan; the caller then uses the one-tile-per-CTA kernel above.
+template <int BN, class Epi>
+static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& o0, const CUtensorMap& o1, int rows, int N,
+                          int K, const typename Epi::Params& ep, cudaStream_t st) {
+  constexpr int kSmemMax = 232448;  // 227 KB per CTA on sm_100
+  const int kblocks = K / kBlockK;
+  const int cf = Epi::smem_floats(ep);
+  int a_res = kblocks <= kWsMaxKBlocksResident ? 1 : 0, stages = 0;
+  for (int pass = 0; pass < 2 && !stages; ++pass) {
+    for (int s = 6; s >= 3; --s)
+      if (ws_smem_plan(BN, kblocks, s, a_res, cf).total <= kSmemMax) {
+        stages = s;
+        break;
+      }
+    if (!stages) {
+      if (!a_res) return 1;
+      a_res = 0;
+    }
+  }
+  if (!stages) return 1;
+  const WsSmemPlan plan = ws_smem_plan(BN, kblocks, stages, a_res, cf);
+  auto kern = gemm_ws_kernel<BN, Epi>;
+  static int configured = 0;
+  if (configured < plan.total) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    configured = kSmemMax;
+  }
+  const int mblocks = cdiv(rows, kBlockM);
+  const int grid = std::min(num_sms(), mblocks);
+  kern<<<grid, kWsThreads, plan.total, st>>>(ta, tb, o0, o1, mblocks, N / BN, kblocks, stages, a_res, ep);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // ================================================================================================ second stage handle
 struct BlockWeights {
   __nv_bfloat16* w1 = nullptr;  // [3H+M, H]
   __nv_bfloat16* w2 = nullptr;  // [H, H+M]
   float *b1 = nullptr, *b2 = nullptr, *gq = nullptr, *gk = nullptr;
+  float logit_bound = 0.f;  // max |q.k| * hd^-0.5 * log2(e) after QK-RMSNorm: hd^0.5 * log2(e) * max|gq| * max|gk|
   CUtensorMap tm_w1, tm_w2;
 };
 
@@ -370,6 +441,11 @@ extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, con
       TRY(A.upload_f32(b2->data, H, &bw.b2));
       TRY(A.upload_f32(gq->data, hd, &bw.gq));
       TRY(A.upload_f32(gk->data, hd, &bw.gk));
+      {
+        float mq = 0.f, mk = 0.f;
+        for (int j = 0; j < hd; ++j) mq = std::max(mq, std::fabs(gq->data[j])), mk = std::max(mk, std::fabs(gk->data[j]));
+        bw.logit_bound = std::sqrt((float)hd) * 1.4426950408889634f * mq * mk * 1.02f;  // 2 % slack: bf16 rounding of q, k
+      }
       TRY(make_tmap(&bw.tm_w1, bw.w1, 3 * H + M, H, bn1));
       TRY(make_tmap(&bw.tm_w2, bw.w2, H, H + M, bn2));
     }
@@ -437,6 +513,32 @@ static int launch_linear2(const lamslide_backbone* bb, const CUtensorMap& ta, co
   }
 }
 
+// warp-specialised variants; return 1 when the tiling is not covered (caller falls back to the kernels above)
+template <int HD>
+static int launch_linear1_ws(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, const CUtensorMap& qkv_st,
+                             const CUtensorMap& act_st, int rows, const typename EpiLinear1Ws<HD>::Params& ep, cudaStream_t st) {
+  const int N = 3 * bb->H + bb->M, K = bb->H;
+  if constexpr (HD == 24) {
+    if (bb->bn1 == 192) return launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
+  } else {
+    if (bb->bn1 == 128) return launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
+    if (bb->bn1 == 64) return launch_gemm_ws<64, EpiLinear1Ws<HD>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
+  }
+  return 1;
+}
+
+static int launch_linear2_ws(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, const CUtensorMap& h_red,
+                             int rows, const EpiLinear2Ws::Params& ep, cudaStream_t st) {
+  const int N = bb->H, K = bb->H + bb->M;
+  switch (bb->bn2) {
+    case 192: return launch_gemm_ws<192, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
+    case 128: return launch_gemm_ws<128, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
+    case 96: return launch_gemm_ws<96, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
+    case 64: return launch_gemm_ws<64, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
+    default: return 1;
+  }
+}
+
 static int launch_plain(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int rows, int N, int K, const EpiPlain::Params& ep,
                         cudaStream_t st) {
   switch (bn) {
@@ -452,10 +554,26 @@ static int launch_plain(int bn, const CUtensorMap& ta, const CUtensorMap& tb, in
   }
 }
 
+// mode: 0 = auto, 1 = force the streaming (online-max) flash kernel, 2 = force the whole-sequence kernel.
+// logit_bound: upper bound of |q.k| in the exp2 domain (<= 0: unknown) — the whole-sequence kernel skips the running maximum.
+constexpr float kSeqKernelMaxLogit = 64.f;
 template <int HD>
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H, int ldo, int heads, const SeqMap& sm, int n_seq,
-                            bool force_flash, cudaStream_t st) {
-  if (sm.S <= 32 && !force_flash) {
+                            int mode, float logit_bound, cudaStream_t st) {
+  const bool force_flash = mode == 1;
+  const size_t seq_smem = AttnSeqCfg<HD>::smem_bytes(sm.S);
+  static const bool legacy_attn = env_flag("LAMSLIDE_LEGACY_ATTN");
+  const bool seq_ok = seq_smem <= 232448 - 1024 && (mode == 2 || (!legacy_attn && logit_bound > 0.f && logit_bound <= kSeqKernelMaxLogit));
+  if (mode == 2 && !seq_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the whole-sequence attention kernel", sm.S);
+  if ((sm.S > 32 && seq_ok && !force_flash) || mode == 2) {
+    auto kern = attn_seq_kernel<HD>;
+    static size_t configured = 0;
+    if (configured < seq_smem) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+      configured = 232448 - 1024;
+    }
+    kern<<<(unsigned)(n_seq * heads), 256, seq_smem, st>>>(qkv, out, H, ldo, sm, heads);
+  } else if (sm.S <= 32 && !force_flash) {
     long long items = (long long)n_seq * sm.S * heads;
     attn_small_kernel<HD><<<cdiv(items, 256), 256, 0, st>>>(qkv, out, H, ldo, heads, sm, items);
   } else {
@@ -468,11 +586,11 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
 }
 
 static int attention_dispatch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H, int ldo, int heads, int hd, const SeqMap& sm,
-                              int n_seq, bool force_flash, cudaStream_t st) {
+                              int n_seq, int mode, float logit_bound, cudaStream_t st) {
   switch (hd) {
-    case 16: return launch_attention<16>(qkv, out, H, ldo, heads, sm, n_seq, force_flash, st);
-    case 24: return launch_attention<24>(qkv, out, H, ldo, heads, sm, n_seq, force_flash, st);
-    case 32: return launch_attention<32>(qkv, out, H, ldo, heads, sm, n_seq, force_flash, st);
+    case 16: return launch_attention<16>(qkv, out, H, ldo, heads, sm, n_seq, mode, logit_bound, st);
+    case 24: return launch_attention<24>(qkv, out, H, ldo, heads, sm, n_seq, mode, logit_bound, st);
+    case 32: return launch_attention<32>(qkv, out, H, ldo, heads, sm, n_seq, mode, logit_bound, st);
     default: return fail(LAMSLIDE_ERR_INVALID, "head_dim %d unsupported", hd);
   }
 }
@@ -508,6 +626,7 @@ static int ln_modulate(const lamslide_backbone* bb, const float* h, __nv_bfloat1
 struct ForwardCtx {
   BackboneWorkspace ws;
   CUtensorMap tm_u, tm_act, tm_u3;
+  CUtensorMap tm_qkv_st, tm_act_st, tm_h_red;  // epilogue stores of the warp-specialised GEMMs (32-row boxes)
 };
 
 static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, int L, void* workspace, size_t workspace_bytes,
@@ -522,6 +641,11 @@ static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, 
   TRY(make_tmap(&fc.tm_u, fc.ws.u, (uint64_t)n, bb->H, kBlockM));
   TRY(make_tmap(&fc.tm_act, fc.ws.act, (uint64_t)n, bb->H + bb->M, kBlockM));
   TRY(make_tmap(&fc.tm_u3, fc.ws.qkv, (uint64_t)n, 3 * bb->H, kBlockM));  // head input [hi | lo | hi] reuses the qkv buffer
+  TRY(make_tmap_ex(&fc.tm_qkv_st, fc.ws.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, 3 * bb->H, bb->hd, 32,
+                   swizzle_for_row_bytes(bb->hd * 2)));
+  TRY(make_tmap_ex(&fc.tm_act_st, fc.ws.act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, bb->H + bb->M, 32, 32,
+                   CU_TENSOR_MAP_SWIZZLE_64B));
+  TRY(make_tmap_ex(&fc.tm_h_red, fc.ws.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)n, bb->H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   const int half = bb->hd / 2;
   rope_table_kernel<<<cdiv(L * half, 256), 256, 0, st>>>(fc.ws.cos_s, fc.ws.sin_s, L, half, (double)bb->cfg.theta);
   LAUNCH_CHECK();
@@ -567,6 +691,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
     TRY(vec_linear(w.vec, H, bb->mod_w, bb->mod_b, nullptr, w.mod, bb->mod_width, B, bb->mod_width, H, 1, 0, st));
   }
   // 3. layers
+  static const bool legacy_gemm = env_flag("LAMSLIDE_LEGACY_GEMM");  // A/B switch: one-tile-per-CTA GEMM kernels
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)hd));
   for (int i = 0; i < bb->depth; ++i) {
     for (int s = 0; s < 2; ++s) {
@@ -589,10 +714,18 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
         n_seq = B * L;
         cs = w.cos_t, sn = w.sin_t, pos_div = L, pos_mod = T;
       }
-#define L1_PARAMS(HD_)                                                                                               \
-  ProfScope ps(PC_LINEAR1, st);                                                                                        \
-  typename EpiLinear1<HD_>::Params ep{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul}; \
-  TRY(launch_linear1<HD_>(bb, fc.tm_u, bw, n, ep, st));
+#define L1_PARAMS(HD_)                                                                                                 \
+  ProfScope ps(PC_LINEAR1, st);                                                                                          \
+  int r1 = 1;                                                                                                            \
+  if (!legacy_gemm) {                                                                                                    \
+    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, bw.gq, bw.gk, cs, sn, H, M, n, pos_div, pos_mod, q_premul};            \
+    r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_qkv_st, fc.tm_act_st, n, epw, st);                                \
+    if (r1 < 0) return r1;                                                                                               \
+  }                                                                                                                      \
+  if (r1 == 1) {                                                                                                         \
+    typename EpiLinear1<HD_>::Params ep{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul}; \
+    TRY(launch_linear1<HD_>(bb, fc.tm_u, bw, n, ep, st));                                                                \
+  }
       if (hd == 16) {
         L1_PARAMS(16)
       } else if (hd == 24) {
@@ -603,12 +736,20 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
 #undef L1_PARAMS
       {
         ProfScope ps(s == 0 ? PC_ATTN_SPATIAL : PC_ATTN_TEMPORAL, st);
-        TRY(attention_dispatch(w.qkv, w.act, H, H + M, heads, hd, sm, n_seq, false, st));
+        TRY(attention_dispatch(w.qkv, w.act, H, H + M, heads, hd, sm, n_seq, 0, bw.logit_bound, st));
       }
       {
         ProfScope ps(PC_LINEAR2, st);
-        EpiLinear2::Params e2{w.h, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, n};
-        TRY(launch_linear2(bb, fc.tm_act, bw, n, e2, st));
+        int r2 = 1;
+        if (!legacy_gemm) {
+          EpiLinear2Ws::Params e2w{bw.b2, modl + 2 * H, bb->mod_width, T * L, H, n};
+          r2 = launch_linear2_ws(bb, fc.tm_act, bw, fc.tm_h_red, n, e2w, st);
+          if (r2 < 0) return r2;
+        }
+        if (r2 == 1) {
+          EpiLinear2::Params e2{w.h, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, n};
+          TRY(launch_linear2(bb, fc.tm_act, bw, n, e2, st));
+        }
       }
     }
   }
@@ -1259,5 +1400,95 @@ extern "C" int lamslide_debug_attention(const void* qkv_bf16, void* out_bf16, in
   SeqMap sm = temporal ? SeqMap{T, L, T * L, 1, L} : SeqMap{L, 1, L, 0, 1};
   int n_seq = temporal ? B * L : B * T;
   return attention_dispatch((const __nv_bfloat16*)qkv_bf16, (__nv_bfloat16*)out_bf16, H, ldo, heads, H / heads, sm, n_seq,
-                            force_flash != 0, (cudaStream_t)stream);
+                            force_flash, 0.f, (cudaStream_t)stream);
+}
+
+// ---- linear1 / linear2 with their fused epilogues in isolation (tests/test_gpu_kernels.py).  Debug only: allocates and syncs.
+template <int HD>
+static int debug_linear1_impl(const void* u, const void* w1, const float* bias, const float* gq, const float* gk, void* qkv, void* act,
+                              int rows, int H, int M, int pos_div, int pos_mod, float theta, int legacy, cudaStream_t st) {
+  const int N = 3 * H + M, half = HD / 2;
+  const int bn = HD == 24 ? pick_bn({192, 96}, H, M, HD) : pick_bn({128, 64}, H, M, HD);
+  if (!bn) return fail(LAMSLIDE_ERR_INVALID, "no linear1 tiling for H %d M %d hd %d", H, M, HD);
+  float *cs = nullptr, *sn = nullptr;
+  CUDA_TRY(cudaMalloc(&cs, (size_t)pos_mod * half * 4));
+  CUDA_TRY(cudaMalloc(&sn, (size_t)pos_mod * half * 4));
+  rope_table_kernel<<<cdiv(pos_mod * half, 256), 256, 0, st>>>(cs, sn, pos_mod, half, (double)theta);
+  CUtensorMap ta, tb, tq, tact;
+  int rc = make_tmap(&ta, u, rows, H, kBlockM);
+  if (!rc) rc = make_tmap(&tb, w1, N, H, bn);
+  if (!rc) rc = make_tmap_ex(&tq, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, 3 * H, HD, 32, swizzle_for_row_bytes(HD * 2));
+  if (!rc) rc = make_tmap_ex(&tact, act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, H + M, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)HD));
+  if (!rc) {
+    if (!legacy) {
+      typename EpiLinear1Ws<HD>::Params ep{bias, gq, gk, cs, sn, H, M, rows, pos_div, pos_mod, q_premul};
+      if constexpr (HD == 24) {
+        rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, tq, tact, rows, N, H, ep, st) : 1;
+      } else {
+        rc = bn == 128 ? launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, tq, tact, rows, N, H, ep, st)
+                       : launch_gemm_ws<64, EpiLinear1Ws<HD>>(ta, tb, tq, tact, rows, N, H, ep, st);
+      }
+      if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear1 kernel does not cover H %d M %d hd %d", H, M, HD);
+    } else {
+      typename EpiLinear1<HD>::Params ep{bias, gq, gk, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod, q_premul};
+      if constexpr (HD == 24) {
+        rc = bn == 192 ? launch_gemm<192, EpiLinear1<24>>(ta, tb, rows, N, H, ep, st) : launch_gemm<96, EpiLinear1<24>>(ta, tb, rows, N, H, ep, st);
+      } else {
+        rc = bn == 128 ? launch_gemm<128, EpiLinear1<HD>>(ta, tb, rows, N, H, ep, st) : launch_gemm<64, EpiLinear1<HD>>(ta, tb, rows, N, H, ep, st);
+      }
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(cs);
+  cudaFree(sn);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(LAMSLIDE_ERR_CUDA, "debug_linear1: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int lamslide_debug_linear1(const void* u_bf16, const void* w1_bf16, const float* bias, const float* q_scale,
+                                      const float* k_scale, void* qkv_bf16, void* act_bf16, int32_t rows, int32_t H, int32_t M,
+                                      int32_t heads, int32_t pos_div, int32_t pos_mod, float theta, int32_t legacy, void* stream) {
+  if (!u_bf16 || !w1_bf16 || !bias || !q_scale || !k_scale || !qkv_bf16 || !act_bf16 || heads <= 0 || H % heads)
+    return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (H / heads) {
+    case 16: return debug_linear1_impl<16>(u_bf16, w1_bf16, bias, q_scale, k_scale, qkv_bf16, act_bf16, rows, H, M, pos_div, pos_mod, theta, legacy, st);
+    case 24: return debug_linear1_impl<24>(u_bf16, w1_bf16, bias, q_scale, k_scale, qkv_bf16, act_bf16, rows, H, M, pos_div, pos_mod, theta, legacy, st);
+    case 32: return debug_linear1_impl<32>(u_bf16, w1_bf16, bias, q_scale, k_scale, qkv_bf16, act_bf16, rows, H, M, pos_div, pos_mod, theta, legacy, st);
+    default: return fail(LAMSLIDE_ERR_INVALID, "head_dim %d unsupported", H / heads);
+  }
+}
+
+extern "C" int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16, const float* bias, const float* gate, float* h,
+                                      int32_t rows, int32_t H, int32_t M, int32_t rows_per_sample, int32_t legacy, void* stream) {
+  if (!act_bf16 || !w2_bf16 || !bias || !gate || !h) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int bn = pick_bn({192, 128, 96, 64}, H, 0, 0);
+  if (!bn) return fail(LAMSLIDE_ERR_INVALID, "no linear2 tiling for H %d", H);
+  CUtensorMap ta, tb, th;
+  TRY(make_tmap(&ta, act_bf16, rows, H + M, kBlockM));
+  TRY(make_tmap(&tb, w2_bf16, H, H + M, bn));
+  TRY(make_tmap_ex(&th, h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  int rc;
+  if (!legacy) {
+    EpiLinear2Ws::Params ep{bias, gate, H, rows_per_sample, H, rows};
+    switch (bn) {
+      case 192: rc = launch_gemm_ws<192, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
+      case 128: rc = launch_gemm_ws<128, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
+      case 96: rc = launch_gemm_ws<96, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
+      default: rc = launch_gemm_ws<64, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
+    }
+    if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear2 kernel does not cover H %d M %d", H, M);
+  } else {
+    EpiLinear2::Params ep{h, bias, gate, H, rows_per_sample, H, rows};
+    switch (bn) {
+      case 192: rc = launch_gemm<192, EpiLinear2>(ta, tb, rows, H, H + M, ep, st); break;
+      case 128: rc = launch_gemm<128, EpiLinear2>(ta, tb, rows, H, H + M, ep, st); break;
+      case 96: rc = launch_gemm<96, EpiLinear2>(ta, tb, rows, H, H + M, ep, st); break;
+      default: rc = launch_gemm<64, EpiLinear2>(ta, tb, rows, H, H + M, ep, st); break;
+    }
+  }
+  return rc;
 }

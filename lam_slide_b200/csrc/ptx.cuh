@@ -158,6 +158,50 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r) {  // N in 
   }
 }
 
+// 32 lanes x 32-bit, 32 consecutive columns.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// N consecutive columns (N a multiple of 16) into r[0..N): issues the widest loads available; caller does tmem_ld_wait().
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
+  static_assert(N % 16 == 0 && N > 0, "tmem_ld_cols: N must be a positive multiple of 16");
+#pragma unroll
+  for (int c = 0; c + 32 <= N; c += 32) tmem_ld32(taddr + c, r + c);
+  if constexpr (N % 32 != 0) tmem_ld16(taddr + (N / 32) * 32, r + (N / 32) * 32);
+}
+
+// ------------------------------------------------------------------ TMA stores (shared -> global), bulk async-groups
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// global[tile] += shared[tile] (element type from the tensor map; f32 here), performed by the TMA unit at L2.
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N of this thread's bulk groups still reading shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ------------------------------------------------------------------ legacy warp MMA (attention v1) + ldmatrix + cp.async
 __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -167,6 +211,31 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
 }
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t smem_addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_addr));
+}
+// first MMA of an accumulation chain: C = 0 (no register zeroing needed)
+__device__ __forceinline__ void mma_bf16_16816_z(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
+}
+// m16n8k8: A = {a0: (row g, k 2t..2t+1), a1: (row g+8, ...)}, B = {b0: (k 2t..2t+1, n g)}
+__device__ __forceinline__ void mma_bf16_1688(float* c, const uint32_t* a, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t* r, uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t* r, uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   int sz = valid ? 16 : 0;  // src-size 0 => zero fill
@@ -212,5 +281,17 @@ __device__ __forceinline__ float erf_as(float x) {
 }
 // exact-erf GELU of the reference (mmdit.py:11-18): x * 0.5 * (1 + erf(x / sqrt(2)))
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+
+// exact-erf GELU evaluated as x * sigmoid(2 g(x)), g(x) = x (c0 + c1 x^2 + c2 x^4) ~ atanh(erf(x / sqrt 2)):
+// |abs err| <= 2.6e-5 over the reals (fit: scripts/fit_gelu.py), relative accuracy kept in the tails by the sigmoid form.
+// 8 FMA-pipe instructions + ex2 + rcp per element — the linear1 epilogue evaluates it for 57 % of its columns.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float t = fminf(x * x, 70.0f);  // g is monotone for x^2 <= 70; beyond, sigmoid is saturated anyway
+  // -2 log2(e) * (c0, c1, c2)
+  float p = fmaf(t, 1.01426306e-3f, -1.06775724e-1f);
+  p = fmaf(p, t, -2.30112134f);
+  const float e = fast_exp2(x * p);
+  return x * fast_rcp(1.0f + e);
+}
 
 }  // namespace lam

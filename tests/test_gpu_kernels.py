@@ -73,3 +73,107 @@ def test_attention_matches_softmax_reference(B, T, L, H, heads, temporal, flash)
     assert float(out[:, H:].float().abs().max()) == 0.0  # columns beyond H untouched
     assert max_rel(got, ref) < 2e-2
     assert float((got - ref).abs().mean() / ref.abs().mean()) < 5e-3
+
+
+@pytest.mark.parametrize("B,T,L,H,heads,temporal", [
+    (2, 1000, 2, 384, 16, 1), (1, 300, 2, 384, 16, 1), (2, 7, 192, 256, 16, 0), (2, 130, 3, 128, 4, 1), (1, 129, 2, 384, 16, 1),
+    (1, 64, 1, 256, 16, 1), (1, 1040, 1, 384, 16, 1), (3, 33, 2, 256, 16, 1),
+])
+def test_whole_sequence_attention_matches_softmax_reference(B, T, L, H, heads, temporal):
+    """mode 2: K/V of the whole sequence resident in shared memory, softmax without the running maximum."""
+    L_ = _lib()
+    lib = L_.load()
+    n = B * T * L
+    g = torch.Generator(device="cpu").manual_seed(n + H + 1)
+    qkv = (torch.randn(n, 3 * H, generator=g)).to(torch.bfloat16).cuda()
+    ldo = H + 64
+    out = torch.zeros(n, ldo, dtype=torch.bfloat16, device="cuda")
+    L_.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, L, H, heads, ldo, temporal, 2,
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = _attention_reference(qkv, B, T, L, H, heads, bool(temporal))
+    got = out[:, :H].float()
+    assert torch.isfinite(got).all()
+    assert float(out[:, H:].float().abs().max()) == 0.0
+    assert max_rel(got, ref) < 2e-2
+    assert float((got - ref).abs().mean() / ref.abs().mean()) < 5e-3
+
+
+def _linear1_reference(u, w1, bias, gq, gk, H, M, heads, pos_div, pos_mod, theta=10000.0):
+    hd = H // heads
+    z = u.double() @ w1.double().t() + bias.double()
+    rows = z.shape[0]
+    qkv, mlp = z[:, :3 * H], z[:, 3 * H:]
+    q, k, v = (qkv[:, i * H:(i + 1) * H].reshape(rows, heads, hd) for i in range(3))
+    pos = (torch.arange(rows, device=z.device) // pos_div) % pos_mod
+    omega = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.float64, device=z.device) / hd))
+    ang = pos.double()[:, None] * omega[None, :]
+    cos, sin = ang.cos()[:, None, :], ang.sin()[:, None, :]
+
+    def norm_rope(x, g):
+        x = x * torch.rsqrt((x * x).mean(-1, keepdim=True) + 1e-6) * g.double()
+        xe, xo = x[..., 0::2], x[..., 1::2]
+        return torch.stack([cos * xe - sin * xo, sin * xe + cos * xo], dim=-1).reshape(rows, heads, hd)
+
+    q = norm_rope(q, gq) * (math.log2(math.e) / math.sqrt(hd))
+    k = norm_rope(k, gk)
+    qkv_ref = torch.cat([q.reshape(rows, H), k.reshape(rows, H), v.reshape(rows, H)], dim=1)
+    mlp_ref = 0.5 * mlp * (1.0 + torch.erf(mlp / math.sqrt(2.0)))
+    return qkv_ref, mlp_ref
+
+
+@pytest.mark.parametrize("rows,H,M,heads,pos_div,pos_mod,legacy", [
+    (1000, 384, 1536, 16, 2, 500, 0), (1000, 384, 1536, 16, 2, 500, 1), (20000 + 37, 384, 1536, 16, 1, 2, 0),
+    (333, 256, 1024, 16, 8, 20, 0), (4096, 256, 512, 16, 192, 30, 0), (777, 128, 256, 4, 2, 20, 0), (128 * 150, 384, 1536, 16, 2, 1000, 0),
+])
+def test_linear1_fused_epilogue(rows, H, M, heads, pos_div, pos_mod, legacy):
+    """linear1 + bias + QK-RMSNorm + RoPE + q pre-scale + erf-GELU (mmdit.py:241-247) vs an fp64 restatement."""
+    L_ = _lib()
+    lib = L_.load()
+    hd = H // heads
+    g = torch.Generator(device="cpu").manual_seed(rows + H)
+    u = torch.randn(rows, H, generator=g).to(torch.bfloat16).cuda()
+    w1 = (torch.randn(3 * H + M, H, generator=g) / math.sqrt(H)).to(torch.bfloat16).cuda()
+    bias = (0.1 * torch.randn(3 * H + M, generator=g)).cuda()
+    gq = (1.0 + 0.1 * torch.randn(hd, generator=g)).cuda()
+    gk = (1.0 + 0.1 * torch.randn(hd, generator=g)).cuda()
+    qkv = torch.full((rows, 3 * H), float("nan"), dtype=torch.bfloat16, device="cuda")
+    act = torch.zeros(rows, H + M, dtype=torch.bfloat16, device="cuda")
+    L_.check(lib.lamslide_debug_linear1(u.data_ptr(), w1.data_ptr(), bias.data_ptr(), gq.data_ptr(), gk.data_ptr(), qkv.data_ptr(),
+                                        act.data_ptr(), rows, H, M, heads, pos_div, pos_mod, 10000.0, legacy,
+                                        torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    qkv_ref, mlp_ref = _linear1_reference(u, w1, bias, gq, gk, H, M, heads, pos_div, pos_mod)
+    assert torch.isfinite(qkv.float()).all()
+    assert float(act[:, :H].float().abs().max()) == 0.0  # the attention half of act is not linear1's to write
+    for name, got, ref in (("q", qkv[:, :H], qkv_ref[:, :H]), ("k", qkv[:, H:2 * H], qkv_ref[:, H:2 * H]),
+                           ("v", qkv[:, 2 * H:], qkv_ref[:, 2 * H:]), ("mlp", act[:, H:], mlp_ref)):
+        err = (got.double() - ref).abs()
+        tol = 2.0 ** -8 * ref.abs() + 2e-3  # bf16 rounding of the result (+ small absolute slack)
+        assert bool((err <= tol).all()), f"{name}: max err {float(err.max()):.3e} at {int(err.argmax())}"
+        assert float(err.mean() / ref.abs().mean()) < 3e-3, name
+
+
+@pytest.mark.parametrize("rows,H,M,rps,legacy", [
+    (1000, 384, 1536, 250, 0), (1000, 384, 1536, 250, 1), (20000 + 37, 384, 1536, 2000, 0), (333, 256, 1024, 160, 0),
+    (777, 128, 256, 40, 0), (128 * 150, 384, 1536, 2000, 0),
+])
+def test_linear2_gated_residual(rows, H, M, rps, legacy):
+    """h += gate[b] * (act @ w2^T + bias) (mmdit.py:248, latent_si_v31.py:54) vs fp64."""
+    L_ = _lib()
+    lib = L_.load()
+    g = torch.Generator(device="cpu").manual_seed(rows + M)
+    nb = (rows + rps - 1) // rps
+    act = torch.randn(rows, H + M, generator=g).to(torch.bfloat16).cuda()
+    w2 = (torch.randn(H, H + M, generator=g) / math.sqrt(H + M)).to(torch.bfloat16).cuda()
+    bias = (0.1 * torch.randn(H, generator=g)).cuda()
+    gate = torch.randn(nb, H, generator=g).cuda()
+    h0 = torch.randn(rows, H, generator=g).cuda()
+    h = h0.clone()
+    L_.check(lib.lamslide_debug_linear2(act.data_ptr(), w2.data_ptr(), bias.data_ptr(), gate.data_ptr(), h.data_ptr(), rows, H, M,
+                                        rps, legacy, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    b_of_row = torch.arange(rows, device="cuda") // rps
+    ref = h0.double() + gate.double()[b_of_row] * (act.double() @ w2.double().t() + bias.double())
+    assert torch.isfinite(h).all()
+    assert max_rel(h, ref) < 2e-5

@@ -172,6 +172,11 @@ int lamslide_debug_linear1(const void* u_bf16, const void* w1_bf16, const float*
 int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16, const float* bias, const float* gate, float* h, int32_t rows,
                            int32_t H, int32_t M, int32_t rows_per_sample, int32_t legacy, void* stream);
 
+/* the TMA + tcgen05 main loop of the persistent GEMM alone (no epilogue work, nothing stored): profiling aid that
+ * separates "operand feed + tensor pipe" from "epilogue" for a shape.  block_n in {192, 128, 64}. */
+int lamslide_debug_gemm_mainloop(const void* a_bf16, const void* b_bf16, int32_t rows, int32_t N, int32_t K, int32_t block_n,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,12 +3,12 @@
 //
 // One CTA per SM (grid = min(#SM, #m-blocks)); a CTA walks m-blocks  mb = blockIdx.x, + gridDim.x, ...  and, inside an
 // m-block, all n-tiles, so the 128 x K activation tile is fetched ONCE per m-block when it fits (A-resident mode,
-// K <= 512: linear1) and only the weight tiles stream through the TMA ring from L2.  Warp roles (320 threads):
+// K <= 512: linear1) and only the weight tiles stream through the TMA ring from L2.  Warp roles (576 threads):
 //   warp 0      : TMA producer (one lane): A k-blocks (resident or ring) + B ring, mbarrier complete_tx
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer, TWO accumulator stages (2 x BN TMEM columns)
-//   warps 2..9  : epilogue.  All 8 warps work on the same tile: warp w owns TMEM lanes 32*(w%4).. (hardware rule) and
-//                 the column half (w-2)/4.  Each thread pulls its BN/2 accumulators into registers with three
-//                 tcgen05.ld.x32, releases the TMEM stage at once (the MMA warp moves on to the tile after next while
+//   warps 2..17 : epilogue.  All 16 warps work on the same tile: warp w owns TMEM lanes 32*(w%4).. (hardware rule) and
+//                 the column quarter (w-2)/4.  Each thread pulls its BN/4 accumulators into registers with
+//                 tcgen05.ld, releases the TMEM stage at once (the MMA warp moves on to the tile after next while
 //                 the math runs from registers), applies the fused epilogue, stages bf16 / fp32 boxes of 32 rows in
 //                 swizzled shared memory (conflict-free thread-per-row writes) and hands them to the TMA unit:
 //                 plain tensor stores for linear1, f32 reduce-add (h += gate * (acc + bias), done at L2) for linear2.
@@ -19,19 +19,18 @@
 
 namespace lam {
 
-constexpr int kWsThreads = 320;
-constexpr int kWsEpiWarps = 8;
-constexpr int kWsStageBytesPerWarp = 4096;  // two 2 KB box buffers
+constexpr int kWsEpiWarps = 16;                      // 4 TMEM lane quarters x 4 column quarters
+constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // + TMA warp + MMA warp
+constexpr int kWsStageBytesPerWarp = 2048;           // one staged box (<= 32 rows x 64 B) per warp
 constexpr int kWsMaxKBlocksResident = 8;
 
 struct WsCtx {
   const CUtensorMap* o0;
   const CUtensorMap* o1;
-  uint8_t* stage;    // this warp's 4 KB staging area
+  uint8_t* stage;    // this warp's staging box
   const float* smf;  // per-kernel fp32 constants in shared memory (bias, ...)
   int lane;
   int row0;          // first global row of this warp's 32-row slice
-  uint32_t nstore;   // boxes issued so far by this warp (selects the staging buffer)
 };
 
 // byte offset of (row r, 16-byte chunk c) inside a staged box whose rows are IB bytes wide; matches the TMA swizzle
@@ -45,10 +44,12 @@ __device__ __forceinline__ uint32_t stage_off(int r, int c) {
   return r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
 }
 
+// The math of a box runs BEFORE stage_begin, so the TMA read-out of the previous box overlaps it; with >= 4 epilogue warps
+// per scheduler a warp that does wait here is covered by the others.
 __device__ __forceinline__ uint8_t* stage_begin(WsCtx& c) {
-  if (c.lane == 0) bulk_wait_read<1>();  // the store issued two boxes ago (same buffer) has finished reading
+  if (c.lane == 0) bulk_wait_read<0>();  // the previous box of this warp has been read out of shared memory
   __syncwarp();
-  return c.stage + (c.nstore & 1) * 2048;
+  return c.stage;
 }
 template <bool REDUCE>
 __device__ __forceinline__ void stage_commit(WsCtx& c, const CUtensorMap* tm, const uint8_t* buf, int col) {
@@ -59,7 +60,6 @@ __device__ __forceinline__ void stage_commit(WsCtx& c, const CUtensorMap* tm, co
     else tma_store_2d(tm, buf, col, c.row0);
     bulk_commit();
   }
-  ++c.nstore;
 }
 
 // ------------------------------------------------------------------------------------------------ linear1 epilogue
@@ -98,39 +98,40 @@ struct EpiLinear1Ws {
     const int r = nt - 2 * pairs + pairs;
     return nq > nm ? r * BN : 3 * p.H + r * BN;
   }
+  // v: this thread's BN/4 accumulators (row `row`, columns n0w .. n0w + BN/4)
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0h) {
-    constexpr int HALF = BN / 2;
-    static_assert(HALF % HD == 0 && HALF % 32 == 0, "a warp's column half must hold whole heads and whole 32-column boxes");
+  static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0w) {
+    constexpr int QW = BN / 4;
+    static_assert(QW % HD == 0 && QW % 16 == 0, "a warp's column quarter must hold whole heads and whole 16-column boxes");
     const int H3 = 3 * p.H;
-    if (n0h >= H3) {  // ---- MLP: GELU
+    if (n0w >= H3) {  // ---- MLP: GELU, 16-column boxes (32-byte rows, SWIZZLE_32B)
 #pragma unroll
-      for (int b = 0; b < HALF / 32; ++b) {
-        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0h + b * 32);
-        uint32_t w[16];
+      for (int b = 0; b < QW / 16; ++b) {
+        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w + b * 16);
+        uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           const float4 bv = bp[j];
-          const float y0 = gelu_fast(__uint_as_float(v[b * 32 + 4 * j + 0]) + bv.x);
-          const float y1 = gelu_fast(__uint_as_float(v[b * 32 + 4 * j + 1]) + bv.y);
-          const float y2 = gelu_fast(__uint_as_float(v[b * 32 + 4 * j + 2]) + bv.z);
-          const float y3 = gelu_fast(__uint_as_float(v[b * 32 + 4 * j + 3]) + bv.w);
+          const float y0 = gelu_fast(__uint_as_float(v[b * 16 + 4 * j + 0]) + bv.x);
+          const float y1 = gelu_fast(__uint_as_float(v[b * 16 + 4 * j + 1]) + bv.y);
+          const float y2 = gelu_fast(__uint_as_float(v[b * 16 + 4 * j + 2]) + bv.z);
+          const float y3 = gelu_fast(__uint_as_float(v[b * 16 + 4 * j + 3]) + bv.w);
           w[2 * j] = pack_bf16x2(y0, y1);
           w[2 * j + 1] = pack_bf16x2(y2, y3);
         }
         uint8_t* buf = stage_begin(c);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          *reinterpret_cast<uint4*>(buf + stage_off<64>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-        stage_commit<false>(c, c.o1, buf, p.H + (n0h - H3) + b * 32);
+        for (int ch = 0; ch < 2; ++ch)
+          *reinterpret_cast<uint4*>(buf + stage_off<32>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        stage_commit<false>(c, c.o1, buf, p.H + (n0w - H3) + b * 16);
       }
       return;
     }
-    const int which = n0h / p.H;  // 0 q, 1 k, 2 v   (BN divides H, so a tile — and a half tile — is one kind)
+    const int which = n0w / p.H;  // 0 q, 1 k, 2 v   (BN divides H, so a tile — and a slice of it — is one kind)
     if (which == 2) {
 #pragma unroll
-      for (int hi = 0; hi < HALF / HD; ++hi) {
-        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0h + hi * HD);
+      for (int hi = 0; hi < QW / HD; ++hi) {
+        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w + hi * HD);
         uint32_t w[HD / 2];
 #pragma unroll
         for (int j = 0; j < HD / 4; ++j) {
@@ -142,7 +143,7 @@ struct EpiLinear1Ws {
 #pragma unroll
         for (int ch = 0; ch < HD / 8; ++ch)
           *reinterpret_cast<uint4*>(buf + stage_off<HD * 2>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-        stage_commit<false>(c, c.o0, buf, n0h + hi * HD);
+        stage_commit<false>(c, c.o0, buf, n0w + hi * HD);
       }
       return;
     }
@@ -158,8 +159,8 @@ struct EpiLinear1Ws {
       sn[i] = s4.x, sn[i + 1] = s4.y, sn[i + 2] = s4.z, sn[i + 3] = s4.w;
     }
 #pragma unroll
-    for (int hi = 0; hi < HALF / HD; ++hi) {
-      const float4* bp = reinterpret_cast<const float4*>(c.smf + n0h + hi * HD);
+    for (int hi = 0; hi < QW / HD; ++hi) {
+      const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w + hi * HD);
       const float4* gp = reinterpret_cast<const float4*>(gam);
       float x[HD];
       float ss = 0.f;
@@ -191,7 +192,7 @@ struct EpiLinear1Ws {
 #pragma unroll
       for (int ch = 0; ch < HD / 8; ++ch)
         *reinterpret_cast<uint4*>(buf + stage_off<HD * 2>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-      stage_commit<false>(c, c.o0, buf, n0h + hi * HD);
+      stage_commit<false>(c, c.o0, buf, n0w + hi * HD);
     }
   }
 };
@@ -214,14 +215,14 @@ struct EpiLinear2Ws {
   template <int BN>
   static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
   template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0h) {
-    constexpr int HALF = BN / 2;
-    static_assert(HALF % 16 == 0, "16-column fp32 boxes");
+  static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0w) {
+    constexpr int QW = BN / 4;
+    static_assert(QW % 16 == 0, "16-column fp32 boxes");
     const int b = (row < p.rows ? row : p.rows - 1) / p.rows_per_sample;
-    const float4* g = reinterpret_cast<const float4*>(p.gate + (size_t)b * p.gate_stride + n0h);
-    const float4* bp = reinterpret_cast<const float4*>(c.smf + n0h);
+    const float4* g = reinterpret_cast<const float4*>(p.gate + (size_t)b * p.gate_stride + n0w);
+    const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w);
 #pragma unroll
-    for (int bx = 0; bx < HALF / 16; ++bx) {
+    for (int bx = 0; bx < QW / 16; ++bx) {
       float4 o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -235,9 +236,22 @@ struct EpiLinear2Ws {
       uint8_t* buf = stage_begin(c);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<float4*>(buf + stage_off<64>(c.lane, ch)) = o[ch];
-      stage_commit<true>(c, c.o0, buf, n0h + bx * 16);
+      stage_commit<true>(c, c.o0, buf, n0w + bx * 16);
     }
   }
+};
+
+// drains the accumulator and stores nothing: isolates the TMA + MMA main loop (lamslide_debug_gemm_mainloop)
+struct EpiNullWs {
+  struct Params {
+    int dummy;
+  };
+  static __host__ __device__ int smem_floats(const Params&) { return 0; }
+  static __device__ void load_consts(const Params&, float*, int, int) {}
+  template <int BN>
+  static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
+  template <int BN>
+  static __device__ __forceinline__ void run(const Params&, WsCtx&, const uint32_t*, int, int) {}
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -262,11 +276,11 @@ __global__ void __launch_bounds__(kWsThreads, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1, int num_m_blocks,
                int num_n_tiles, int num_k_blocks, int stages, int a_resident, typename Epi::Params ep) {
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "two accumulator stages of BN columns must fit 512 TMEM columns");
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "two accumulator stages of BN columns must fit 512 TMEM columns");
   constexpr int kABytes = kBlockM * kBlockK * 2;
   constexpr int kBBytes = BN * kBlockK * 2;
   constexpr uint32_t kTmemCols = tmem_cols_for(2 * BN);
-  constexpr int HALF = BN / 2;
+  constexpr int QW = BN / 4;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -373,29 +387,29 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: 8 warps, warp = (TMEM lane quarter, column half) =====
+    // ===== epilogue: 16 warps, warp = (TMEM lane quarter, column quarter) =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cq = (warp - 2) >> 2;
     WsCtx c;
     c.o0 = &tmap_o0, c.o1 = &tmap_o1;
     c.stage = staging + (warp - 2) * kWsStageBytesPerWarp;
-    c.smf = smf, c.lane = lane, c.nstore = 0;
+    c.smf = smf, c.lane = lane;
     uint32_t tile = 0;
     for (int mb = blockIdx.x; mb < num_m_blocks; mb += gridDim.x) {
       c.row0 = mb * kBlockM + q * 32;
       const int row = c.row0 + lane;
       for (int nt = 0; nt < num_n_tiles; ++nt, ++tile) {
         const uint32_t acc = tile & 1, use = tile >> 1;
-        const int n0h = Epi::template tile_n0<BN>(ep, nt) + half * HALF;
+        const int n0w = Epi::template tile_n0<BN>(ep, nt) + cq * QW;
         mbar_wait(&tmem_full[acc], use & 1);
         tcgen05_fence_after();
-        uint32_t v[HALF];
-        tmem_ld_cols<HALF>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * HALF, v);
+        uint32_t v[QW];
+        tmem_ld_cols<QW>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cq * QW, v);
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator stage is free again: the math runs from registers
-        Epi::template run<BN>(ep, c, v, row, n0h);
+        Epi::template run<BN>(ep, c, v, row, n0w);
       }
     }
     if (lane == 0) bulk_wait_read<0>();  // staged boxes must be read out before the CTA's shared memory goes away

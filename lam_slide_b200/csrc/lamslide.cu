@@ -522,7 +522,9 @@ static int launch_linear1_ws(const lamslide_backbone* bb, const CUtensorMap& ta,
     if (bb->bn1 == 192) return launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
   } else {
     if (bb->bn1 == 128) return launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
-    if (bb->bn1 == 64) return launch_gemm_ws<64, EpiLinear1Ws<HD>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
+    if constexpr (HD == 16) {
+      if (bb->bn1 == 64) return launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
+    }
   }
   return 1;
 }
@@ -533,7 +535,6 @@ static int launch_linear2_ws(const lamslide_backbone* bb, const CUtensorMap& ta,
   switch (bb->bn2) {
     case 192: return launch_gemm_ws<192, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
     case 128: return launch_gemm_ws<128, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
-    case 96: return launch_gemm_ws<96, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
     case 64: return launch_gemm_ws<64, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
     default: return 1;
   }
@@ -643,8 +644,8 @@ static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, 
   TRY(make_tmap(&fc.tm_u3, fc.ws.qkv, (uint64_t)n, 3 * bb->H, kBlockM));  // head input [hi | lo | hi] reuses the qkv buffer
   TRY(make_tmap_ex(&fc.tm_qkv_st, fc.ws.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, 3 * bb->H, bb->hd, 32,
                    swizzle_for_row_bytes(bb->hd * 2)));
-  TRY(make_tmap_ex(&fc.tm_act_st, fc.ws.act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, bb->H + bb->M, 32, 32,
-                   CU_TENSOR_MAP_SWIZZLE_64B));
+  TRY(make_tmap_ex(&fc.tm_act_st, fc.ws.act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, bb->H + bb->M, 16, 32,
+                   CU_TENSOR_MAP_SWIZZLE_32B));
   TRY(make_tmap_ex(&fc.tm_h_red, fc.ws.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)n, bb->H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   const int half = bb->hd / 2;
   rope_table_kernel<<<cdiv(L * half, 256), 256, 0, st>>>(fc.ws.cos_s, fc.ws.sin_s, L, half, (double)bb->cfg.theta);
@@ -1418,7 +1419,7 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
   int rc = make_tmap(&ta, u, rows, H, kBlockM);
   if (!rc) rc = make_tmap(&tb, w1, N, H, bn);
   if (!rc) rc = make_tmap_ex(&tq, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, 3 * H, HD, 32, swizzle_for_row_bytes(HD * 2));
-  if (!rc) rc = make_tmap_ex(&tact, act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, H + M, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (!rc) rc = make_tmap_ex(&tact, act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, H + M, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B);
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)HD));
   if (!rc) {
     if (!legacy) {
@@ -1426,8 +1427,9 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
       if constexpr (HD == 24) {
         rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, tq, tact, rows, N, H, ep, st) : 1;
       } else {
-        rc = bn == 128 ? launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, tq, tact, rows, N, H, ep, st)
-                       : launch_gemm_ws<64, EpiLinear1Ws<HD>>(ta, tb, tq, tact, rows, N, H, ep, st);
+        if (bn == 128) rc = launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, tq, tact, rows, N, H, ep, st);
+        else if constexpr (HD == 16) rc = launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, tb, tq, tact, rows, N, H, ep, st);
+        else rc = 1;
       }
       if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear1 kernel does not cover H %d M %d hd %d", H, M, HD);
     } else {
@@ -1477,8 +1479,8 @@ extern "C" int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16,
     switch (bn) {
       case 192: rc = launch_gemm_ws<192, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
       case 128: rc = launch_gemm_ws<128, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
-      case 96: rc = launch_gemm_ws<96, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
-      default: rc = launch_gemm_ws<64, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
+      case 64: rc = launch_gemm_ws<64, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
+      default: rc = 1; break;
     }
     if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear2 kernel does not cover H %d M %d", H, M);
   } else {
@@ -1490,5 +1492,25 @@ extern "C" int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16,
       default: rc = launch_gemm<64, EpiLinear2>(ta, tb, rows, H, H + M, ep, st); break;
     }
   }
+  return rc;
+}
+
+// the TMA + tcgen05 main loop of the persistent kernel alone (accumulators are drained and dropped): what the loads and
+// the tensor pipe can sustain for a shape, independent of any epilogue.  block_n in {192, 128, 64}.
+extern "C" int lamslide_debug_gemm_mainloop(const void* a_bf16, const void* b_bf16, int32_t rows, int32_t N, int32_t K, int32_t block_n,
+                                            void* stream) {
+  if (!a_bf16 || !b_bf16 || N % block_n) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  CUtensorMap ta, tb;
+  TRY(make_tmap(&ta, a_bf16, rows, K, kBlockM));
+  TRY(make_tmap(&tb, b_bf16, N, K, block_n));
+  EpiNullWs::Params ep{0};
+  int rc;
+  switch (block_n) {
+    case 192: rc = launch_gemm_ws<192, EpiNullWs>(ta, tb, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    case 128: rc = launch_gemm_ws<128, EpiNullWs>(ta, tb, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    case 64: rc = launch_gemm_ws<64, EpiNullWs>(ta, tb, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    default: return fail(LAMSLIDE_ERR_INVALID, "block_n %d unsupported", block_n);
+  }
+  if (rc == 1) return fail(LAMSLIDE_ERR_INVALID, "shape does not fit the persistent kernel");
   return rc;
 }

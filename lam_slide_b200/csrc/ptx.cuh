@@ -282,16 +282,21 @@ __device__ __forceinline__ float erf_as(float x) {
 // exact-erf GELU of the reference (mmdit.py:11-18): x * 0.5 * (1 + erf(x / sqrt(2)))
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
 
-// exact-erf GELU evaluated as x * sigmoid(2 g(x)), g(x) = x (c0 + c1 x^2 + c2 x^4) ~ atanh(erf(x / sqrt 2)):
-// |abs err| <= 2.6e-5 over the reals (fit: scripts/fit_gelu.py), relative accuracy kept in the tails by the sigmoid form.
-// 8 FMA-pipe instructions + ex2 + rcp per element — the linear1 epilogue evaluates it for 57 % of its columns.
+// exact-erf GELU evaluated as 0.5 x (1 + tanh(g(x))), g(x) = x (c0 + c1 x^2 + c2 x^4) ~ atanh(erf(x / sqrt 2)):
+// fit error <= 2.6e-5 abs over the reals (scripts/fit_gelu.py) + MUFU.TANH (measured on B200: <= 8e-6 abs, 2.7e-6 for
+// |x| > 2; scripts/mufu_bench.cu).  8 FMA-pipe instructions + one MUFU per element — the linear1 epilogue evaluates it
+// for 57 % of its columns, so it is the instruction budget of that kernel.
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float t = fminf(x * x, 70.0f);  // g is monotone for x^2 <= 70; beyond, sigmoid is saturated anyway
-  // -2 log2(e) * (c0, c1, c2)
-  float p = fmaf(t, 1.01426306e-3f, -1.06775724e-1f);
-  p = fmaf(p, t, -2.30112134f);
-  const float e = fast_exp2(x * p);
-  return x * fast_rcp(1.0f + e);
+  const float t = fminf(x * x, 70.0f);  // g is monotone for x^2 <= 70; beyond, tanh is saturated anyway
+  float p = fmaf(t, -3.515167885575763e-4f, 3.700564602253205e-2f);
+  p = fmaf(p, t, 7.975078842851064e-1f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, fast_tanh(x * p), hx);
 }
 
 }  // namespace lam

@@ -1,0 +1,42 @@
+"""Developer timing aid (not a test): CUDA-event timings of the persistent GEMM main loop alone (no epilogue) for the
+linear1 / linear2 shapes of the 4AA config, to separate "operand feed + tensor pipe" from "epilogue".
+Usage: python scripts/gpu_time_kernels.py [rows]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lam_slide_b200 import _lib as L  # noqa: E402
+
+
+def time_fn(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e3  # us
+
+
+def main():
+    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 128000
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    for (N, K, bn) in [(2688, 384, 192), (2688, 384, 128), (384, 1920, 192), (384, 1920, 128), (1152, 384, 192)]:
+        a = torch.randn(rows, K, device="cuda").to(torch.bfloat16)
+        b = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+        us = time_fn(lambda: L.check(lib.lamslide_debug_gemm_mainloop(a.data_ptr(), b.data_ptr(), rows, N, K, bn, st)))
+        print(f"mainloop rows={rows} N={N} K={K} bn={bn}: {us:8.1f} us  {2.0 * rows * N * K / us * 1e-6:7.1f} TFLOP/s", flush=True)
+        c = torch.empty(rows, N, device="cuda", dtype=torch.bfloat16)
+        us = time_fn(lambda: torch.matmul(a, b.t(), out=c))
+        print(f"   cuBLAS bf16 (same shape, bf16 out, no epilogue): {us:8.1f} us  {2.0 * rows * N * K / us * 1e-6:7.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,7 @@ namespace lam {
 
 constexpr int kWsEpiWarps = 16;                      // 4 TMEM lane quarters x 4 column quarters
 constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // + TMA warp + MMA warp
-constexpr int kWsStageBytesPerWarp = 2048;           // one staged box (<= 32 rows x 64 B) per warp
+constexpr int kWsStageBytesPerWarp = 2560;           // one staged box (<= 32 rows x 80 B) per warp
 constexpr int kWsMaxKBlocksResident = 8;
 
 struct WsCtx {
@@ -68,6 +68,10 @@ __device__ __forceinline__ void stage_commit(WsCtx& c, const CUtensorMap* tm, co
 //         (mmdit.py:85-90) -> q additionally * (hd^-0.5 * log2 e) -> bf16 -> qkv[rows, 3H]
 //   v   : + bias -> bf16 -> qkv
 //   mlp : + bias -> erf-GELU (mmdit.py:11-18; ptx.cuh gelu_fast) -> bf16 -> act[:, H + j]   (A operand of linear2)
+// Output path: a warp owns a 32-row x (BN/4)-column slab and emits it in chunks of HD columns: thread-per-row packs the
+// chunk into a padded shared-memory box (pitch = odd number of 16-byte units: conflict-free), then the warp stores the box
+// with row-contiguous 16-byte st.global (HD * 2 contiguous bytes per row).  (Small-box TMA stores were tried first and
+// were bound by the TMA unit's per-row rate: 1.5 k rows of 32-48 B per tile.)
 template <int HD>
 struct EpiLinear1Ws {
   struct Params {
@@ -76,10 +80,15 @@ struct EpiLinear1Ws {
     const float* k_scale;   // [HD]
     const float* rope_cos;  // [S, HD/2]
     const float* rope_sin;
+    __nv_bfloat16* qkv;     // [rows, 3H]
+    __nv_bfloat16* act;     // [rows, H + M]
     int H, M, rows;
     int pos_div, pos_mod;   // rope position of a row = (row / pos_div) % pos_mod
     float q_premul;         // hd^-0.5 * log2(e)
   };
+  static constexpr int CH = HD / 8;                         // 16-byte chunks per staged row
+  static constexpr int PITCH = (CH % 2 == 0 ? CH + 1 : CH) * 16;  // bytes
+  static_assert(32 * PITCH <= kWsStageBytesPerWarp, "staging box too large");
   static __host__ __device__ int smem_floats(const Params& p) { return 3 * p.H + p.M + 2 * HD; }
   static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
     const int N = 3 * p.H + p.M;
@@ -98,32 +107,43 @@ struct EpiLinear1Ws {
     const int r = nt - 2 * pairs + pairs;
     return nq > nm ? r * BN : 3 * p.H + r * BN;
   }
+  // packed chunk (HD bf16 of this thread's row) -> staging box -> row-contiguous global stores by the whole warp
+  static __device__ __forceinline__ void emit(const Params& p, WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col) {
+    __syncwarp();  // the previous box has been read out by every lane
+#pragma unroll
+    for (int ch = 0; ch < CH; ++ch)
+      *reinterpret_cast<uint4*>(c.stage + c.lane * PITCH + ch * 16) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int id = c.lane + 32 * k;
+      const int r = id / CH, ch = id % CH;
+      const uint4 val = *reinterpret_cast<const uint4*>(c.stage + r * PITCH + ch * 16);
+      if (c.row0 + r < p.rows) *reinterpret_cast<uint4*>(out + (size_t)(c.row0 + r) * ld + col + ch * 8) = val;
+    }
+  }
   // v: this thread's BN/4 accumulators (row `row`, columns n0w .. n0w + BN/4)
   template <int BN>
   static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0w) {
     constexpr int QW = BN / 4;
-    static_assert(QW % HD == 0 && QW % 16 == 0, "a warp's column quarter must hold whole heads and whole 16-column boxes");
+    static_assert(QW % HD == 0, "a warp's column quarter must hold whole heads");
     const int H3 = 3 * p.H;
-    if (n0w >= H3) {  // ---- MLP: GELU, 16-column boxes (32-byte rows, SWIZZLE_32B)
+    if (n0w >= H3) {  // ---- MLP: GELU
 #pragma unroll
-      for (int b = 0; b < QW / 16; ++b) {
-        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w + b * 16);
-        uint32_t w[8];
+      for (int hi = 0; hi < QW / HD; ++hi) {
+        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w + hi * HD);
+        uint32_t w[HD / 2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < HD / 4; ++j) {
           const float4 bv = bp[j];
-          const float y0 = gelu_fast(__uint_as_float(v[b * 16 + 4 * j + 0]) + bv.x);
-          const float y1 = gelu_fast(__uint_as_float(v[b * 16 + 4 * j + 1]) + bv.y);
-          const float y2 = gelu_fast(__uint_as_float(v[b * 16 + 4 * j + 2]) + bv.z);
-          const float y3 = gelu_fast(__uint_as_float(v[b * 16 + 4 * j + 3]) + bv.w);
+          const float y0 = gelu_fast(__uint_as_float(v[hi * HD + 4 * j + 0]) + bv.x);
+          const float y1 = gelu_fast(__uint_as_float(v[hi * HD + 4 * j + 1]) + bv.y);
+          const float y2 = gelu_fast(__uint_as_float(v[hi * HD + 4 * j + 2]) + bv.z);
+          const float y3 = gelu_fast(__uint_as_float(v[hi * HD + 4 * j + 3]) + bv.w);
           w[2 * j] = pack_bf16x2(y0, y1);
           w[2 * j + 1] = pack_bf16x2(y2, y3);
         }
-        uint8_t* buf = stage_begin(c);
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
-          *reinterpret_cast<uint4*>(buf + stage_off<32>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-        stage_commit<false>(c, c.o1, buf, p.H + (n0w - H3) + b * 16);
+        emit(p, c, w, p.act, p.H + p.M, p.H + (n0w - H3) + hi * HD);
       }
       return;
     }
@@ -139,11 +159,7 @@ struct EpiLinear1Ws {
           w[2 * j] = pack_bf16x2(__uint_as_float(v[hi * HD + 4 * j + 0]) + bv.x, __uint_as_float(v[hi * HD + 4 * j + 1]) + bv.y);
           w[2 * j + 1] = pack_bf16x2(__uint_as_float(v[hi * HD + 4 * j + 2]) + bv.z, __uint_as_float(v[hi * HD + 4 * j + 3]) + bv.w);
         }
-        uint8_t* buf = stage_begin(c);
-#pragma unroll
-        for (int ch = 0; ch < HD / 8; ++ch)
-          *reinterpret_cast<uint4*>(buf + stage_off<HD * 2>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-        stage_commit<false>(c, c.o0, buf, n0w + hi * HD);
+        emit(p, c, w, p.qkv, H3, n0w + hi * HD);
       }
       return;
     }
@@ -188,11 +204,7 @@ struct EpiLinear1Ws {
         w[2 * j] = pack_bf16x2(fmaf(c0, e0, -s0 * d0), fmaf(s0, e0, c0 * d0));
         w[2 * j + 1] = pack_bf16x2(fmaf(c1, e1, -s1 * d1), fmaf(s1, e1, c1 * d1));
       }
-      uint8_t* buf = stage_begin(c);
-#pragma unroll
-      for (int ch = 0; ch < HD / 8; ++ch)
-        *reinterpret_cast<uint4*>(buf + stage_off<HD * 2>(c.lane, ch)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-      stage_commit<false>(c, c.o0, buf, n0w + hi * HD);
+      emit(p, c, w, p.qkv, H3, n0w + hi * HD);
     }
   }
 };

@@ -719,7 +719,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   ProfScope ps(PC_LINEAR1, st);                                                                                          \
   int r1 = 1;                                                                                                            \
   if (!legacy_gemm) {                                                                                                    \
-    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, bw.gq, bw.gk, cs, sn, H, M, n, pos_div, pos_mod, q_premul};            \
+    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul};            \
     r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_qkv_st, fc.tm_act_st, n, epw, st);                                \
     if (r1 < 0) return r1;                                                                                               \
   }                                                                                                                      \
@@ -1423,7 +1423,7 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)HD));
   if (!rc) {
     if (!legacy) {
-      typename EpiLinear1Ws<HD>::Params ep{bias, gq, gk, cs, sn, H, M, rows, pos_div, pos_mod, q_premul};
+      typename EpiLinear1Ws<HD>::Params ep{bias, gq, gk, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod, q_premul};
       if constexpr (HD == 24) {
         rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, tq, tact, rows, N, H, ep, st) : 1;
       } else {

@@ -129,6 +129,28 @@ embed_in_kernel(const float* __restrict__ x, const float* __restrict__ xc, const
   }
 }
 
+// ---- A operand of the tensor-core input embedding: row = [x_hi | x_lo | x_hi | xc_hi | xc_lo | xc_hi] (6D bf16), hi = bf16(v),
+// lo = bf16(v - hi).  With the weight packed as [Wx_hi | Wx_hi | Wx_lo | Wc_hi | Wc_hi | Wc_lo] an ordinary bf16 GEMM evaluates
+// v_hi w_hi + v_lo w_hi + v_hi w_lo for both inputs (~16 mantissa bits).  One thread per 4 consecutive input floats.
+__global__ void __launch_bounds__(256)
+split3_embed_kernel(const float4* __restrict__ x, const float4* __restrict__ xc, __nv_bfloat16* __restrict__ a, long long n_tok, int D) {
+  const int q = D / 4;  // float4 per row per input
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tok * 2 * q) return;
+  const long long tok = idx / (2 * q);
+  const int r = (int)(idx % (2 * q));
+  const int which = r / q, j = r % q;
+  const float4 v = which == 0 ? x[tok * q + j] : xc[tok * q + j];
+  const uint2 hi = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
+  const float2 f01 = __bfloat1622float2(h2[0]), f23 = __bfloat1622float2(h2[1]);
+  const uint2 lo = make_uint2(pack_bf16x2(v.x - f01.x, v.y - f01.y), pack_bf16x2(v.z - f23.x, v.w - f23.y));
+  uint2* row = reinterpret_cast<uint2*>(a + tok * 6 * D + (long long)which * 3 * D);
+  row[j] = hi;
+  row[q + j] = lo;
+  row[2 * q + j] = hi;
+}
+
 // ---- in-place LayerNorm without affine over rows of width H (F.layer_norm at latent_si_v31.py:174, eps 1e-5); warp per row
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(float* __restrict__ h, int rows, int H, float eps) {
   int row = blockIdx.x * 8 + (threadIdx.x >> 5);

@@ -1,5 +1,5 @@
-// Persistent, warp-specialised tcgen05 GEMM for the two big projections of every ParallelMLPAttentionV2 block
-// (mmdit.py:240-249):  D[rows, N] = A[rows, K] · B[N, K]^T, bf16 operands, fp32 accumulation in TMEM.
+// Persistent, warp-specialised tcgen05 GEMM for the big projections of the second-stage transformer
+// (mmdit.py:240-249, latent_si_v31.py:172):  D[rows, N] = A[rows, K] · B[N, K]^T, bf16 operands, fp32 accumulation in TMEM.
 //
 // One CTA per SM (grid = min(#SM, #m-blocks)); a CTA walks m-blocks  mb = blockIdx.x, + gridDim.x, ...  and, inside an
 // m-block, all n-tiles, so the 128 x K activation tile is fetched ONCE per m-block when it fits (A-resident mode,
@@ -7,12 +7,12 @@
 //   warp 0      : TMA producer (one lane): A k-blocks (resident or ring) + B ring, mbarrier complete_tx
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer, TWO accumulator stages (2 x BN TMEM columns)
 //   warps 2..17 : epilogue.  All 16 warps work on the same tile: warp w owns TMEM lanes 32*(w%4).. (hardware rule) and
-//                 the column quarter (w-2)/4.  Each thread pulls its BN/4 accumulators into registers with
-//                 tcgen05.ld, releases the TMEM stage at once (the MMA warp moves on to the tile after next while
-//                 the math runs from registers), applies the fused epilogue, stages bf16 / fp32 boxes of 32 rows in
-//                 swizzled shared memory (conflict-free thread-per-row writes) and hands them to the TMA unit:
-//                 plain tensor stores for linear1, f32 reduce-add (h += gate * (acc + bias), done at L2) for linear2.
-//                 No thread-level global stores, no uncoalesced traffic.
+//                 the column quarter (w-2)/4, which it walks in chunks of Epi::CW columns: tcgen05.ld -> registers ->
+//                 fused math -> padded shared-memory box (thread-per-row writes, conflict-free) -> row-contiguous
+//                 16-byte global stores by the whole warp (linear1, embedding) or a TMA f32 reduce-add (linear2:
+//                 h += gate * (acc + bias), performed at L2).  The TMEM stage is released right after the LAST chunk has
+//                 been pulled into registers, i.e. before the tile's epilogue is finished, so the MMA warp (already
+//                 busy with the other stage) never waits for it.
 // Every mbarrier wait is bounded (ptx.cuh: mbar_wait) so a protocol error is a failed launch, never a hung GPU.
 #pragma once
 #include "gemm_tc.cuh"
@@ -27,40 +27,20 @@ constexpr int kWsMaxKBlocksResident = 8;
 struct WsCtx {
   const CUtensorMap* o0;
   const CUtensorMap* o1;
-  uint8_t* stage;    // this warp's staging box
-  const float* smf;  // per-kernel fp32 constants in shared memory (bias, ...)
+  uint32_t stage_s;  // this warp's staging box (32-bit shared address)
+  uint32_t smf_s;    // per-kernel fp32 constants in shared memory (bias, ...), 32-bit shared address
   int lane;
   int row0;          // first global row of this warp's 32-row slice
 };
 
-// byte offset of (row r, 16-byte chunk c) inside a staged box whose rows are IB bytes wide; matches the TMA swizzle
-// mode chosen on the host for that width (32 B -> SWIZZLE_32B, 48 B -> none, 64 B -> SWIZZLE_64B).  In all three cases
-// the 8 threads of a quarter warp hit 8 distinct 16-byte bank groups.
-template <int IB>
-__device__ __forceinline__ uint32_t stage_off(int r, int c) {
-  static_assert(IB == 32 || IB == 48 || IB == 64, "unsupported staged row width");
-  if constexpr (IB == 32) return r * 32 + ((c ^ ((r >> 2) & 1)) << 4);
-  if constexpr (IB == 48) return r * 48 + (c << 4);
-  return r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  const uint4 u = ld_shared_v4(addr);
+  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
 }
 
-// The math of a box runs BEFORE stage_begin, so the TMA read-out of the previous box overlaps it; with >= 4 epilogue warps
-// per scheduler a warp that does wait here is covered by the others.
-__device__ __forceinline__ uint8_t* stage_begin(WsCtx& c) {
-  if (c.lane == 0) bulk_wait_read<0>();  // the previous box of this warp has been read out of shared memory
-  __syncwarp();
-  return c.stage;
-}
-template <bool REDUCE>
-__device__ __forceinline__ void stage_commit(WsCtx& c, const CUtensorMap* tm, const uint8_t* buf, int col) {
-  fence_proxy_async();  // generic-proxy writes of every lane -> visible to the async proxy (TMA)
-  __syncwarp();
-  if (c.lane == 0) {
-    if constexpr (REDUCE) tma_reduce_add_2d(tm, buf, col, c.row0);
-    else tma_store_2d(tm, buf, col, c.row0);
-    bulk_commit();
-  }
-}
+// byte offset of (row r, 16-byte chunk c) inside a TMA-staged box with 64-byte rows (SWIZZLE_64B on the host side):
+// the 8 threads of a quarter warp hit 8 distinct 16-byte bank groups.
+__device__ __forceinline__ uint32_t stage_off64(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
 
 // ------------------------------------------------------------------------------------------------ linear1 epilogue
 // Columns [0,3H) are (K=3, heads, hd) q|k|v, columns [3H,3H+M) the MLP (mmdit.py:241-247):
@@ -68,10 +48,8 @@ __device__ __forceinline__ void stage_commit(WsCtx& c, const CUtensorMap* tm, co
 //         (mmdit.py:85-90) -> q additionally * (hd^-0.5 * log2 e) -> bf16 -> qkv[rows, 3H]
 //   v   : + bias -> bf16 -> qkv
 //   mlp : + bias -> erf-GELU (mmdit.py:11-18; ptx.cuh gelu_fast) -> bf16 -> act[:, H + j]   (A operand of linear2)
-// Output path: a warp owns a 32-row x (BN/4)-column slab and emits it in chunks of HD columns: thread-per-row packs the
-// chunk into a padded shared-memory box (pitch = odd number of 16-byte units: conflict-free), then the warp stores the box
-// with row-contiguous 16-byte st.global (HD * 2 contiguous bytes per row).  (Small-box TMA stores were tried first and
-// were bound by the TMA unit's per-row rate: 1.5 k rows of 32-48 B per tile.)
+// A chunk is one head (HD columns).  Output: thread-per-row packs the chunk into a padded shared-memory box (pitch = odd
+// number of 16-byte units), then the warp stores the box with row-contiguous 16-byte st.global (HD * 2 bytes per row).
 template <int HD>
 struct EpiLinear1Ws {
   struct Params {
@@ -86,9 +64,14 @@ struct EpiLinear1Ws {
     int pos_div, pos_mod;   // rope position of a row = (row / pos_div) % pos_mod
     float q_premul;         // hd^-0.5 * log2(e)
   };
-  static constexpr int CH = HD / 8;                         // 16-byte chunks per staged row
+  static constexpr int CW = HD;                                  // chunk width (columns)
+  static constexpr int CH = HD / 8;                              // 16-byte chunks per staged row
   static constexpr int PITCH = (CH % 2 == 0 ? CH + 1 : CH) * 16;  // bytes
   static_assert(32 * PITCH <= kWsStageBytesPerWarp, "staging box too large");
+  struct Tile {
+    int kind;  // 0 q, 1 k, 2 v, 3 mlp
+    float cs[HD / 2], sn[HD / 2];
+  };
   static __host__ __device__ int smem_floats(const Params& p) { return 3 * p.H + p.M + 2 * HD; }
   static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
     const int N = 3 * p.H + p.M;
@@ -107,111 +90,98 @@ struct EpiLinear1Ws {
     const int r = nt - 2 * pairs + pairs;
     return nq > nm ? r * BN : 3 * p.H + r * BN;
   }
+  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx&, Tile& t, int row, int n0w) {
+    t.kind = n0w >= 3 * p.H ? 3 : n0w / p.H;  // BN divides H, so a tile — and a slice of it — is one kind
+    if (t.kind < 2) {
+      const int pos = row < p.rows ? (row / p.pos_div) % p.pos_mod : 0;
+#pragma unroll
+      for (int i = 0; i < HD / 2; i += 4) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * (HD / 2) + i));
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * (HD / 2) + i));
+        t.cs[i] = c4.x, t.cs[i + 1] = c4.y, t.cs[i + 2] = c4.z, t.cs[i + 3] = c4.w;
+        t.sn[i] = s4.x, t.sn[i + 1] = s4.y, t.sn[i + 2] = s4.z, t.sn[i + 3] = s4.w;
+      }
+    }
+  }
   // packed chunk (HD bf16 of this thread's row) -> staging box -> row-contiguous global stores by the whole warp
-  static __device__ __forceinline__ void emit(const Params& p, WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col) {
+  static __device__ __forceinline__ void emit(const Params& p, const WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col) {
     __syncwarp();  // the previous box has been read out by every lane
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
-      *reinterpret_cast<uint4*>(c.stage + c.lane * PITCH + ch * 16) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+      st_shared_v4(c.stage_s + c.lane * PITCH + ch * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
       const int id = c.lane + 32 * k;
       const int r = id / CH, ch = id % CH;
-      const uint4 val = *reinterpret_cast<const uint4*>(c.stage + r * PITCH + ch * 16);
+      const uint4 val = ld_shared_v4(c.stage_s + r * PITCH + ch * 16);
       if (c.row0 + r < p.rows) *reinterpret_cast<uint4*>(out + (size_t)(c.row0 + r) * ld + col + ch * 8) = val;
     }
   }
-  // v: this thread's BN/4 accumulators (row `row`, columns n0w .. n0w + BN/4)
-  template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0w) {
-    constexpr int QW = BN / 4;
-    static_assert(QW % HD == 0, "a warp's column quarter must hold whole heads");
+  // v: HD accumulators of this thread's row, columns col .. col + HD
+  static __device__ __forceinline__ void chunk(const Params& p, const WsCtx& c, const Tile& t, const uint32_t* v, int col) {
     const int H3 = 3 * p.H;
-    if (n0w >= H3) {  // ---- MLP: GELU
-#pragma unroll
-      for (int hi = 0; hi < QW / HD; ++hi) {
-        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w + hi * HD);
-        uint32_t w[HD / 2];
-#pragma unroll
-        for (int j = 0; j < HD / 4; ++j) {
-          const float4 bv = bp[j];
-          const float y0 = gelu_fast(__uint_as_float(v[hi * HD + 4 * j + 0]) + bv.x);
-          const float y1 = gelu_fast(__uint_as_float(v[hi * HD + 4 * j + 1]) + bv.y);
-          const float y2 = gelu_fast(__uint_as_float(v[hi * HD + 4 * j + 2]) + bv.z);
-          const float y3 = gelu_fast(__uint_as_float(v[hi * HD + 4 * j + 3]) + bv.w);
-          w[2 * j] = pack_bf16x2(y0, y1);
-          w[2 * j + 1] = pack_bf16x2(y2, y3);
-        }
-        emit(p, c, w, p.act, p.H + p.M, p.H + (n0w - H3) + hi * HD);
-      }
-      return;
-    }
-    const int which = n0w / p.H;  // 0 q, 1 k, 2 v   (BN divides H, so a tile — and a slice of it — is one kind)
-    if (which == 2) {
-#pragma unroll
-      for (int hi = 0; hi < QW / HD; ++hi) {
-        const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w + hi * HD);
-        uint32_t w[HD / 2];
-#pragma unroll
-        for (int j = 0; j < HD / 4; ++j) {
-          const float4 bv = bp[j];
-          w[2 * j] = pack_bf16x2(__uint_as_float(v[hi * HD + 4 * j + 0]) + bv.x, __uint_as_float(v[hi * HD + 4 * j + 1]) + bv.y);
-          w[2 * j + 1] = pack_bf16x2(__uint_as_float(v[hi * HD + 4 * j + 2]) + bv.z, __uint_as_float(v[hi * HD + 4 * j + 3]) + bv.w);
-        }
-        emit(p, c, w, p.qkv, H3, n0w + hi * HD);
-      }
-      return;
-    }
-    // ---- q or k: RMSNorm + RoPE per head
-    const float* gam = c.smf + H3 + p.M + which * HD;  // q: scale * premul, k: scale
-    const int pos = row < p.rows ? (row / p.pos_div) % p.pos_mod : 0;
-    float cs[HD / 2], sn[HD / 2];
-#pragma unroll
-    for (int i = 0; i < HD / 2; i += 4) {
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * (HD / 2) + i));
-      const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * (HD / 2) + i));
-      cs[i] = c4.x, cs[i + 1] = c4.y, cs[i + 2] = c4.z, cs[i + 3] = c4.w;
-      sn[i] = s4.x, sn[i + 1] = s4.y, sn[i + 2] = s4.z, sn[i + 3] = s4.w;
-    }
-#pragma unroll
-    for (int hi = 0; hi < QW / HD; ++hi) {
-      const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w + hi * HD);
-      const float4* gp = reinterpret_cast<const float4*>(gam);
-      float x[HD];
-      float ss = 0.f;
+    const uint32_t bias_s = c.smf_s + col * 4;
+    uint32_t w[HD / 2];
+    if (t.kind == 3) {  // ---- MLP: GELU
 #pragma unroll
       for (int j = 0; j < HD / 4; ++j) {
-        const float4 bv = bp[j];
-        x[4 * j + 0] = __uint_as_float(v[hi * HD + 4 * j + 0]) + bv.x;
-        x[4 * j + 1] = __uint_as_float(v[hi * HD + 4 * j + 1]) + bv.y;
-        x[4 * j + 2] = __uint_as_float(v[hi * HD + 4 * j + 2]) + bv.z;
-        x[4 * j + 3] = __uint_as_float(v[hi * HD + 4 * j + 3]) + bv.w;
-        ss = fmaf(x[4 * j + 0], x[4 * j + 0], ss);
-        ss = fmaf(x[4 * j + 1], x[4 * j + 1], ss);
-        ss = fmaf(x[4 * j + 2], x[4 * j + 2], ss);
-        ss = fmaf(x[4 * j + 3], x[4 * j + 3], ss);
+        const float4 bv = ld_shared_f4(bias_s + j * 16);
+        const float y0 = gelu_fast(__uint_as_float(v[4 * j + 0]) + bv.x);
+        const float y1 = gelu_fast(__uint_as_float(v[4 * j + 1]) + bv.y);
+        const float y2 = gelu_fast(__uint_as_float(v[4 * j + 2]) + bv.z);
+        const float y3 = gelu_fast(__uint_as_float(v[4 * j + 3]) + bv.w);
+        w[2 * j] = pack_bf16x2(y0, y1);
+        w[2 * j + 1] = pack_bf16x2(y2, y3);
       }
-      const float rstd = rsqrtf(ss * (1.0f / HD) + 1e-6f);
-      uint32_t w[HD / 2];
+      emit(p, c, w, p.act, p.H + p.M, p.H + (col - H3));
+      return;
+    }
+    if (t.kind == 2) {  // ---- v: bias only
 #pragma unroll
       for (int j = 0; j < HD / 4; ++j) {
-        const float4 gv = gp[j];
-        const float e0 = x[4 * j + 0] * gv.x, d0 = x[4 * j + 1] * gv.y;
-        const float e1 = x[4 * j + 2] * gv.z, d1 = x[4 * j + 3] * gv.w;
-        const float c0 = cs[2 * j] * rstd, s0 = sn[2 * j] * rstd;
-        const float c1 = cs[2 * j + 1] * rstd, s1 = sn[2 * j + 1] * rstd;
-        w[2 * j] = pack_bf16x2(fmaf(c0, e0, -s0 * d0), fmaf(s0, e0, c0 * d0));
-        w[2 * j + 1] = pack_bf16x2(fmaf(c1, e1, -s1 * d1), fmaf(s1, e1, c1 * d1));
+        const float4 bv = ld_shared_f4(bias_s + j * 16);
+        w[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j + 0]) + bv.x, __uint_as_float(v[4 * j + 1]) + bv.y);
+        w[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bv.z, __uint_as_float(v[4 * j + 3]) + bv.w);
       }
-      emit(p, c, w, p.qkv, H3, n0w + hi * HD);
+      emit(p, c, w, p.qkv, H3, col);
+      return;
     }
+    // ---- q or k: RMSNorm + RoPE over the head
+    const uint32_t gam_s = c.smf_s + (H3 + p.M + t.kind * HD) * 4;  // q: scale * premul, k: scale
+    float x[HD];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < HD / 4; ++j) {
+      const float4 bv = ld_shared_f4(bias_s + j * 16);
+      x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv.x;
+      x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
+      x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
+      x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+      ss = fmaf(x[4 * j + 0], x[4 * j + 0], ss);
+      ss = fmaf(x[4 * j + 1], x[4 * j + 1], ss);
+      ss = fmaf(x[4 * j + 2], x[4 * j + 2], ss);
+      ss = fmaf(x[4 * j + 3], x[4 * j + 3], ss);
+    }
+    const float rstd = rsqrtf(ss * (1.0f / HD) + 1e-6f);
+#pragma unroll
+    for (int j = 0; j < HD / 4; ++j) {
+      const float4 gv = ld_shared_f4(gam_s + j * 16);
+      const float e0 = x[4 * j + 0] * gv.x, d0 = x[4 * j + 1] * gv.y;
+      const float e1 = x[4 * j + 2] * gv.z, d1 = x[4 * j + 3] * gv.w;
+      const float c0 = t.cs[2 * j] * rstd, s0 = t.sn[2 * j] * rstd;
+      const float c1 = t.cs[2 * j + 1] * rstd, s1 = t.sn[2 * j + 1] * rstd;
+      w[2 * j] = pack_bf16x2(fmaf(c0, e0, -s0 * d0), fmaf(s0, e0, c0 * d0));
+      w[2 * j + 1] = pack_bf16x2(fmaf(c1, e1, -s1 * d1), fmaf(s1, e1, c1 * d1));
+    }
+    emit(p, c, w, p.qkv, H3, col);
   }
+  static __device__ __forceinline__ void finish(const WsCtx&) {}
 };
 
 // ------------------------------------------------------------------------------------------------ linear2 epilogue
 // linear2 + gated residual (mmdit.py:248, latent_si_v31.py:54,61):  h[row, n] += gate[b(row), n] * (acc + bias[n]),
-// issued as a TMA f32 reduce-add so the SM never reads h.
+// issued as a TMA f32 reduce-add (16-column boxes, 64-byte rows, SWIZZLE_64B) so the SM never reads h.
 struct EpiLinear2Ws {
   struct Params {
     const float* bias;  // [H]
@@ -220,37 +190,97 @@ struct EpiLinear2Ws {
     int rows_per_sample;  // T * L
     int H, rows;
   };
+  static constexpr int CW = 16;
+  struct Tile {
+    const float* gate;
+  };
   static __host__ __device__ int smem_floats(const Params& p) { return p.H; }
   static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
     for (int i = tid; i < p.H; i += nthreads) smf[i] = p.bias[i];
   }
   template <int BN>
   static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
-  template <int BN>
-  static __device__ __forceinline__ void run(const Params& p, WsCtx& c, const uint32_t* v, int row, int n0w) {
-    constexpr int QW = BN / 4;
-    static_assert(QW % 16 == 0, "16-column fp32 boxes");
+  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx&, Tile& t, int row, int) {
     const int b = (row < p.rows ? row : p.rows - 1) / p.rows_per_sample;
-    const float4* g = reinterpret_cast<const float4*>(p.gate + (size_t)b * p.gate_stride + n0w);
-    const float4* bp = reinterpret_cast<const float4*>(c.smf + n0w);
+    t.gate = p.gate + (size_t)b * p.gate_stride;
+  }
+  static __device__ __forceinline__ void chunk(const Params&, const WsCtx& c, const Tile& t, const uint32_t* v, int col) {
+    float4 o[4];
 #pragma unroll
-    for (int bx = 0; bx < QW / 16; ++bx) {
-      float4 o[4];
+    for (int j = 0; j < 4; ++j) {
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(t.gate + col) + j);
+      const float4 bv = ld_shared_f4(c.smf_s + col * 4 + j * 16);
+      o[j].x = gv.x * (__uint_as_float(v[4 * j + 0]) + bv.x);
+      o[j].y = gv.y * (__uint_as_float(v[4 * j + 1]) + bv.y);
+      o[j].z = gv.z * (__uint_as_float(v[4 * j + 2]) + bv.z);
+      o[j].w = gv.w * (__uint_as_float(v[4 * j + 3]) + bv.w);
+    }
+    if (c.lane == 0) bulk_wait_read<0>();  // the previous box of this warp has been read out of shared memory
+    __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 gv = __ldg(g + bx * 4 + j);
-        const float4 bv = bp[bx * 4 + j];
-        o[j].x = gv.x * (__uint_as_float(v[bx * 16 + 4 * j + 0]) + bv.x);
-        o[j].y = gv.y * (__uint_as_float(v[bx * 16 + 4 * j + 1]) + bv.y);
-        o[j].z = gv.z * (__uint_as_float(v[bx * 16 + 4 * j + 2]) + bv.z);
-        o[j].w = gv.w * (__uint_as_float(v[bx * 16 + 4 * j + 3]) + bv.w);
-      }
-      uint8_t* buf = stage_begin(c);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<float4*>(buf + stage_off<64>(c.lane, ch)) = o[ch];
-      stage_commit<true>(c, c.o0, buf, n0w + bx * 16);
+    for (int ch = 0; ch < 4; ++ch)
+      st_shared_v4(c.stage_s + stage_off64(c.lane, ch), __float_as_uint(o[ch].x), __float_as_uint(o[ch].y), __float_as_uint(o[ch].z),
+                   __float_as_uint(o[ch].w));
+    fence_proxy_async();  // generic-proxy writes of every lane -> visible to the async proxy (TMA)
+    __syncwarp();
+    if (c.lane == 0) {
+      tma_reduce_add_2d_s(c.o0, c.stage_s, col, c.row0);
+      bulk_commit();
     }
   }
+  static __device__ __forceinline__ void finish(const WsCtx& c) {
+    if (c.lane == 0) bulk_wait_read<0>();  // staged boxes must be read out before the CTA's shared memory goes away
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ input embedding epilogue
+// h[row, n] = acc + (bx + bc)[n] + E_mask[mask[row]][n]   (latent_si_v31.py:172), fp32, staged row-contiguous stores.
+// The GEMM operands are the bf16 hi/lo split of [x | x_cond] and of [Wx | Wc] (elementwise.cuh: split3_embed_kernel),
+// so the product carries ~16 mantissa bits.
+struct EpiEmbedWs {
+  struct Params {
+    const float* bias;        // [H] = x_in.bias + cond_to_emb.bias
+    const float* emask;       // [2, H] mask_to_emb.weight
+    const long long* mask;    // [rows] int64 in {0, 1}
+    float* h;                 // [rows, H]
+    int H, rows;
+  };
+  static constexpr int CW = 16;
+  static constexpr int PITCH = 80;  // 16 fp32 = 64 B per staged row, padded to an odd number of 16-byte units
+  static_assert(32 * PITCH <= kWsStageBytesPerWarp, "staging box too large");
+  struct Tile {
+    uint32_t em_s;  // shared address of this row's mask embedding
+  };
+  static __host__ __device__ int smem_floats(const Params& p) { return 3 * p.H; }
+  static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
+    for (int i = tid; i < p.H; i += nthreads) smf[i] = p.bias[i];
+    for (int i = tid; i < 2 * p.H; i += nthreads) smf[p.H + i] = p.emask[i];
+  }
+  template <int BN>
+  static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
+  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx& c, Tile& t, int row, int) {
+    const int m = row < p.rows ? (p.mask[row] != 0 ? 1 : 0) : 0;
+    t.em_s = c.smf_s + (p.H + m * p.H) * 4;
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, const WsCtx& c, const Tile& t, const uint32_t* v, int col) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 bv = ld_shared_f4(c.smf_s + col * 4 + j * 16), ev = ld_shared_f4(t.em_s + col * 4 + j * 16);
+      st_shared_v4(c.stage_s + c.lane * PITCH + j * 16, __float_as_uint(__uint_as_float(v[4 * j + 0]) + bv.x + ev.x),
+                   __float_as_uint(__uint_as_float(v[4 * j + 1]) + bv.y + ev.y), __float_as_uint(__uint_as_float(v[4 * j + 2]) + bv.z + ev.z),
+                   __float_as_uint(__uint_as_float(v[4 * j + 3]) + bv.w + ev.w));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int id = c.lane + 32 * k;
+      const int r = id >> 2, ch = id & 3;
+      const uint4 val = ld_shared_v4(c.stage_s + r * PITCH + ch * 16);
+      if (c.row0 + r < p.rows) *reinterpret_cast<uint4*>(p.h + (size_t)(c.row0 + r) * p.H + col + ch * 4) = val;
+    }
+  }
+  static __device__ __forceinline__ void finish(const WsCtx&) {}
 };
 
 // drains the accumulator and stores nothing: isolates the TMA + MMA main loop (lamslide_debug_gemm_mainloop)
@@ -258,12 +288,15 @@ struct EpiNullWs {
   struct Params {
     int dummy;
   };
+  static constexpr int CW = 16;
+  struct Tile {};
   static __host__ __device__ int smem_floats(const Params&) { return 0; }
   static __device__ void load_consts(const Params&, float*, int, int) {}
   template <int BN>
   static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
-  template <int BN>
-  static __device__ __forceinline__ void run(const Params&, WsCtx&, const uint32_t*, int, int) {}
+  static __device__ __forceinline__ void tile_begin(const Params&, const WsCtx&, Tile&, int, int) {}
+  static __device__ __forceinline__ void chunk(const Params&, const WsCtx&, const Tile&, const uint32_t*, int) {}
+  static __device__ __forceinline__ void finish(const WsCtx&) {}
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -284,15 +317,16 @@ static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_bloc
 }
 
 template <int BN, class Epi>
-__global__ void __launch_bounds__(kWsThreads, 1)
+__global__ void __maxnreg__(112)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1, int num_m_blocks,
                int num_n_tiles, int num_k_blocks, int stages, int a_resident, typename Epi::Params ep) {
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "two accumulator stages of BN columns must fit 512 TMEM columns");
   constexpr int kABytes = kBlockM * kBlockK * 2;
-  constexpr int kBBytes = BN * kBlockK * 2;
   constexpr uint32_t kTmemCols = tmem_cols_for(2 * BN);
   constexpr int QW = BN / 4;
+  constexpr int CW = Epi::CW;
+  static_assert(QW % CW == 0, "a warp's column quarter must hold whole epilogue chunks");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -316,8 +350,6 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    tma_prefetch_desc(&tmap_o0);
-    tma_prefetch_desc(&tmap_o1);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -404,8 +436,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int cq = (warp - 2) >> 2;
     WsCtx c;
     c.o0 = &tmap_o0, c.o1 = &tmap_o1;
-    c.stage = staging + (warp - 2) * kWsStageBytesPerWarp;
-    c.smf = smf, c.lane = lane;
+    c.stage_s = smem_u32(staging + (warp - 2) * kWsStageBytesPerWarp);
+    c.smf_s = smem_u32(smf);
+    c.lane = lane;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cq * QW;
     uint32_t tile = 0;
     for (int mb = blockIdx.x; mb < num_m_blocks; mb += gridDim.x) {
       c.row0 = mb * kBlockM + q * 32;
@@ -413,18 +447,25 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int nt = 0; nt < num_n_tiles; ++nt, ++tile) {
         const uint32_t acc = tile & 1, use = tile >> 1;
         const int n0w = Epi::template tile_n0<BN>(ep, nt) + cq * QW;
+        typename Epi::Tile ts;
+        Epi::tile_begin(ep, c, ts, row, n0w);
         mbar_wait(&tmem_full[acc], use & 1);
         tcgen05_fence_after();
-        uint32_t v[QW];
-        tmem_ld_cols<QW>(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cq * QW, v);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // accumulator stage is free again: the math runs from registers
-        Epi::template run<BN>(ep, c, v, row, n0w);
+#pragma unroll 1
+        for (int ck = 0; ck < QW / CW; ++ck) {
+          uint32_t v[CW];
+          tmem_ld<CW>(lane_taddr + acc * BN + ck * CW, v);
+          tmem_ld_wait();
+          if (ck == QW / CW - 1) {  // last chunk is in registers: hand the accumulator stage back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          Epi::chunk(ep, c, ts, v, n0w + ck * CW);
+        }
       }
     }
-    if (lane == 0) bulk_wait_read<0>();  // staged boxes must be read out before the CTA's shared memory goes away
+    Epi::finish(c);
   }
 
   tcgen05_fence_before();

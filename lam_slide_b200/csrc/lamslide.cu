@@ -276,6 +276,9 @@ struct lamslide_backbone {
   int mod_width = 0;  // depth * 6H + 2H
   Arena arena;
   float *wt_in = nullptr, *b_in = nullptr, *emask = nullptr;
+  __nv_bfloat16* w_emb = nullptr;  // [H, 6D] hi/lo split of [Wx | Wc] for the tensor-core input embedding (0 = not available)
+  CUtensorMap tm_wemb;
+  int bn_emb = 0;
   float *time_w1 = nullptr, *time_b1 = nullptr, *time_w2 = nullptr, *time_b2 = nullptr;
   float *vec_w1 = nullptr, *vec_b1 = nullptr, *vec_w2 = nullptr, *vec_b2 = nullptr;
   float *mod_w = nullptr, *mod_b = nullptr;
@@ -386,6 +389,22 @@ extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, con
     TRY(A.upload_f32(wt.data(), wt.size(), &bb->wt_in));
     TRY(A.upload_f32(bsum.data(), H, &bb->b_in));
     TRY(A.upload_f32(em->data, 2 * H, &bb->emask));
+    // tensor-core variant: [Wx_hi | Wx_hi | Wx_lo | Wc_hi | Wc_hi | Wc_lo], K = 6D (must tile by 64 and fit the act buffer)
+    bb->bn_emb = pick_bn({192, 128, 64}, H, 0, 0);
+    if ((6 * D) % 64 == 0 && 6 * D <= H + M && bb->bn_emb) {
+      std::vector<__nv_bfloat16> we((size_t)H * 6 * D);
+      for (int j = 0; j < H; ++j)
+        for (int k = 0; k < D; ++k) {
+          const float vx = wx->data[(size_t)j * D + k], vc = wc->data[(size_t)j * D + k];
+          const __nv_bfloat16 xh = __float2bfloat16_rn(vx), ch = __float2bfloat16_rn(vc);
+          const __nv_bfloat16 xl = __float2bfloat16_rn(vx - __bfloat162float(xh)), cl = __float2bfloat16_rn(vc - __bfloat162float(ch));
+          __nv_bfloat16* r = &we[(size_t)j * 6 * D];
+          r[k] = xh, r[D + k] = xh, r[2 * D + k] = xl;
+          r[3 * D + k] = ch, r[4 * D + k] = ch, r[5 * D + k] = cl;
+        }
+      TRY(A.upload(we.data(), we.size() * sizeof(__nv_bfloat16), (void**)&bb->w_emb));
+      TRY(make_tmap(&bb->tm_wemb, bb->w_emb, H, 6 * D, bb->bn_emb));
+    }
   }
   {
     GET(w1, "time_in.in_layer.weight", H, 256);
@@ -628,6 +647,7 @@ struct ForwardCtx {
   BackboneWorkspace ws;
   CUtensorMap tm_u, tm_act, tm_u3;
   CUtensorMap tm_qkv_st, tm_act_st, tm_h_red;  // epilogue stores of the warp-specialised GEMMs (32-row boxes)
+  CUtensorMap tm_emb_a;                         // [n, 6D] split input-embedding operand (lives in the act buffer)
 };
 
 static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, int L, void* workspace, size_t workspace_bytes,
@@ -646,6 +666,7 @@ static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, 
                    swizzle_for_row_bytes(bb->hd * 2)));
   TRY(make_tmap_ex(&fc.tm_act_st, fc.ws.act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, bb->H + bb->M, 16, 32,
                    CU_TENSOR_MAP_SWIZZLE_32B));
+  if (bb->w_emb) TRY(make_tmap(&fc.tm_emb_a, fc.ws.act, (uint64_t)n, 6 * bb->D, kBlockM));
   TRY(make_tmap_ex(&fc.tm_h_red, fc.ws.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)n, bb->H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   const int half = bb->hd / 2;
   rope_table_kernel<<<cdiv(L * half, 256), 256, 0, st>>>(fc.ws.cos_s, fc.ws.sin_s, L, half, (double)bb->cfg.theta);
@@ -666,8 +687,24 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   // 1. h = x_in(x) + cond_to_emb(x_cond) + mask_to_emb(mask) [+ layer_norm]
   {
     ProfScope ps(PC_EMBED, st);
+    static const bool legacy_embed = env_flag("LAMSLIDE_LEGACY_EMBED");
+    int re = 1;
+    if (bb->w_emb && !legacy_embed) {
+      const long long nthr = (long long)n * 2 * (D / 4);
+      split3_embed_kernel<<<cdiv(nthr, 256), 256, 0, st>>>((const float4*)x, (const float4*)x_cond, w.act, n, D);
+      LAUNCH_CHECK();
+      EpiEmbedWs::Params ee{bb->b_in, bb->emask, (const long long*)mask, w.h, H, n};
+      switch (bb->bn_emb) {
+        case 192: re = launch_gemm_ws<192, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        case 128: re = launch_gemm_ws<128, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        case 64: re = launch_gemm_ws<64, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        default: break;
+      }
+      if (re < 0) return re;
+    }
     size_t smem = (size_t)2 * D * 36 * sizeof(float);
-    if (H <= 256) {
+    if (re == 0) {
+    } else if (H <= 256) {
       embed_in_kernel<1><<<cdiv(n, 32), 256, smem, st>>>(x, x_cond, (const long long*)mask, bb->wt_in, bb->b_in, bb->emask, w.h, n, D, H);
     } else {
       embed_in_kernel<2><<<cdiv(n, 32), 256, smem, st>>>(x, x_cond, (const long long*)mask, bb->wt_in, bb->b_in, bb->emask, w.h, n, D, H);

@@ -212,7 +212,9 @@ struct AttnSeqCfg {
   static __host__ __device__ size_t smem_bytes(int S) { return (size_t)2 * s16(S) * PITCH * 2; }
 };
 
-template <int HD>
+// POLY_MASK: bit (mt * 8 + nt * 4 + e) set => that one of the 16 exponentials a thread evaluates per 16-key block is
+// computed with poly_exp2 on the FMA pipe instead of MUFU.EX2 (both pipes then run side by side).
+template <int HD, uint32_t POLY_MASK>
 __global__ void __launch_bounds__(256, 2)
 attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, SeqMap sm, int heads) {
   using Cfg = AttnSeqCfg<HD>;
@@ -320,7 +322,8 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) s[mt][nt][e] = fast_exp2(s[mt][nt][e]);
+          for (int e = 0; e < 4; ++e)
+            s[mt][nt][e] = ((POLY_MASK >> (mt * 8 + nt * 4 + e)) & 1u) ? poly_exp2(s[mt][nt][e]) : fast_exp2(s[mt][nt][e]);
         }
       }
       if (kb == nkb - 1 && S16 != S) {  // zero the probabilities of the padding keys (zero-filled K rows give exp2(0) = 1)

@@ -70,7 +70,7 @@ struct EpiLinear1Ws {
   static_assert(32 * PITCH <= kWsStageBytesPerWarp, "staging box too large");
   struct Tile {
     int kind;  // 0 q, 1 k, 2 v, 3 mlp
-    float cs[HD / 2], sn[HD / 2];
+    const float4 *cs, *sn;  // this row's RoPE table entries (L1-resident: re-read per head rather than held in 24 registers)
   };
   static __host__ __device__ int smem_floats(const Params& p) { return 3 * p.H + p.M + 2 * HD; }
   static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
@@ -92,16 +92,9 @@ struct EpiLinear1Ws {
   }
   static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx&, Tile& t, int row, int n0w) {
     t.kind = n0w >= 3 * p.H ? 3 : n0w / p.H;  // BN divides H, so a tile — and a slice of it — is one kind
-    if (t.kind < 2) {
-      const int pos = row < p.rows ? (row / p.pos_div) % p.pos_mod : 0;
-#pragma unroll
-      for (int i = 0; i < HD / 2; i += 4) {
-        const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * (HD / 2) + i));
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * (HD / 2) + i));
-        t.cs[i] = c4.x, t.cs[i + 1] = c4.y, t.cs[i + 2] = c4.z, t.cs[i + 3] = c4.w;
-        t.sn[i] = s4.x, t.sn[i + 1] = s4.y, t.sn[i + 2] = s4.z, t.sn[i + 3] = s4.w;
-      }
-    }
+    const int pos = row < p.rows ? (row / p.pos_div) % p.pos_mod : 0;
+    t.cs = reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * (HD / 2));
+    t.sn = reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * (HD / 2));
   }
   // packed chunk (HD bf16 of this thread's row) -> staging box -> row-contiguous global stores by the whole warp
   static __device__ __forceinline__ void emit(const Params& p, const WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col) {
@@ -165,14 +158,20 @@ struct EpiLinear1Ws {
     }
     const float rstd = rsqrtf(ss * (1.0f / HD) + 1e-6f);
 #pragma unroll
-    for (int j = 0; j < HD / 4; ++j) {
-      const float4 gv = ld_shared_f4(gam_s + j * 16);
-      const float e0 = x[4 * j + 0] * gv.x, d0 = x[4 * j + 1] * gv.y;
-      const float e1 = x[4 * j + 2] * gv.z, d1 = x[4 * j + 3] * gv.w;
-      const float c0 = t.cs[2 * j] * rstd, s0 = t.sn[2 * j] * rstd;
-      const float c1 = t.cs[2 * j + 1] * rstd, s1 = t.sn[2 * j + 1] * rstd;
-      w[2 * j] = pack_bf16x2(fmaf(c0, e0, -s0 * d0), fmaf(s0, e0, c0 * d0));
-      w[2 * j + 1] = pack_bf16x2(fmaf(c1, e1, -s1 * d1), fmaf(s1, e1, c1 * d1));
+    for (int j2 = 0; j2 < HD / 8; ++j2) {  // 8 columns = 4 rotation pairs per step
+      const float4 cv = __ldg(t.cs + j2), sv = __ldg(t.sn + j2);
+      const float cc[4] = {cv.x * rstd, cv.y * rstd, cv.z * rstd, cv.w * rstd};
+      const float sc[4] = {sv.x * rstd, sv.y * rstd, sv.z * rstd, sv.w * rstd};
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int j = 2 * j2 + h2;
+        const float4 gv = ld_shared_f4(gam_s + j * 16);
+        const float e0 = x[4 * j + 0] * gv.x, d0 = x[4 * j + 1] * gv.y;
+        const float e1 = x[4 * j + 2] * gv.z, d1 = x[4 * j + 3] * gv.w;
+        const float c0 = cc[2 * h2], s0 = sc[2 * h2], c1 = cc[2 * h2 + 1], s1 = sc[2 * h2 + 1];
+        w[2 * j] = pack_bf16x2(fmaf(c0, e0, -s0 * d0), fmaf(s0, e0, c0 * d0));
+        w[2 * j + 1] = pack_bf16x2(fmaf(c1, e1, -s1 * d1), fmaf(s1, e1, c1 * d1));
+      }
     }
     emit(p, c, w, p.qkv, H3, col);
   }
@@ -317,7 +316,7 @@ static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_bloc
 }
 
 template <int BN, class Epi>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(kWsThreads, 1)  // 18 warps are allocated as 20 (granularity 4): <= 96 registers per thread
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1, int num_m_blocks,
                int num_n_tiles, int num_k_blocks, int stages, int a_resident, typename Epi::Params ep) {

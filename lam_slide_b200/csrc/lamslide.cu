@@ -586,11 +586,15 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
   const bool seq_ok = seq_smem <= 232448 - 1024 && (mode == 2 || (!legacy_attn && logit_bound > 0.f && logit_bound <= kSeqKernelMaxLogit));
   if (mode == 2 && !seq_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the whole-sequence attention kernel", sm.S);
   if ((sm.S > 32 && seq_ok && !force_flash) || mode == 2) {
-    auto kern = attn_seq_kernel<HD>;
-    static size_t configured = 0;
-    if (configured < seq_smem) {
+    // share of the exponentials evaluated on the FMA pipe (poly_exp2) instead of MUFU: 4 of 16 by default
+    static const int poly = getenv("LAMSLIDE_ATTN_POLY") ? atoi(getenv("LAMSLIDE_ATTN_POLY")) : 4;
+    void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int) =
+        poly == 0 ? attn_seq_kernel<HD, 0x0000u> : poly == 2 ? attn_seq_kernel<HD, 0x0808u> : poly == 6 ? attn_seq_kernel<HD, 0xA8A8u>
+        : poly == 8 ? attn_seq_kernel<HD, 0xAAAAu> : attn_seq_kernel<HD, 0x8888u>;
+    static const void* configured = nullptr;
+    if (configured != (const void*)kern) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-      configured = 232448 - 1024;
+      configured = (const void*)kern;
     }
     kern<<<(unsigned)(n_seq * heads), 256, seq_smem, st>>>(qkv, out, H, ldo, sm, heads);
   } else if (sm.S <= 32 && !force_flash) {

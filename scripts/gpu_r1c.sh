@@ -9,6 +9,7 @@ for t in test_linear1_fused test_linear2_gated test_whole_sequence_attention; do
 done
 echo "######## mainloop timings" >> $LOG
 timeout 300 python scripts/gpu_time_kernels.py >> $LOG 2>&1
+for pp in 0 2 4 6 8; do LAMSLIDE_ATTN_POLY=$pp timeout 120 python scripts/gpu_time_kernels.py attn >> $LOG 2>&1; done
 echo "######## bench" >> $LOG
 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline $BENCH_ARGS > gpurun_out/bench_c.json 2> gpurun_out/bench_c.err
 cat gpurun_out/bench_c.json >> $LOG; tail -5 gpurun_out/bench_c.err >> $LOG

@@ -24,7 +24,22 @@ def time_fn(fn, iters=20):
     return a.elapsed_time(b) / iters * 1e3  # us
 
 
+def attn():
+    """temporal attention of the 4AA config at B = 64 (128 sequences x 16 heads, S = 1000, hd = 24), whole-sequence kernel"""
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    B, T, Lx, H, heads = 64, 1000, 2, 384, 16
+    n = B * T * Lx
+    qkv = (torch.randn(n, 3 * H, device="cuda") * 0.6).to(torch.bfloat16)
+    out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
+    us = time_fn(lambda: L.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, 2, st)), iters=10)
+    flops = 4.0 * 24 * T * T * heads * B * Lx
+    print(f"attn_seq LAMSLIDE_ATTN_POLY={os.environ.get('LAMSLIDE_ATTN_POLY', 'default')}: {us:8.1f} us  {flops / us * 1e-6:7.1f} TFLOP/s", flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "attn":
+        return attn()
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 128000
     lib = L.load()
     st = torch.cuda.current_stream().cuda_stream

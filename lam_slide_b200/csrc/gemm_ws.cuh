@@ -96,8 +96,20 @@ struct EpiLinear1Ws {
     t.cs = reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * (HD / 2));
     t.sn = reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * (HD / 2));
   }
-  // packed chunk (HD bf16 of this thread's row) -> staging box -> row-contiguous global stores by the whole warp
+  // packed chunk (HD bf16 of this thread's row).  kDirectStore: each thread writes its own HD * 2 contiguous bytes (no
+  // shared-memory round trip: shared-memory bandwidth is what the UMMA operand fetch and the TMA ring compete for);
+  // otherwise staging box -> row-contiguous global stores by the whole warp.
+  static constexpr bool kDirectStore = true;
   static __device__ __forceinline__ void emit(const Params& p, const WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col) {
+    if constexpr (kDirectStore) {
+      const int row = c.row0 + c.lane;
+      if (row < p.rows) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * ld + col);
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) dst[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+      }
+      return;
+    }
     __syncwarp();  // the previous box has been read out by every lane
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)

@@ -586,8 +586,10 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
   const bool seq_ok = seq_smem <= 232448 - 1024 && (mode == 2 || (!legacy_attn && logit_bound > 0.f && logit_bound <= kSeqKernelMaxLogit));
   if (mode == 2 && !seq_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the whole-sequence attention kernel", sm.S);
   if ((sm.S > 32 && seq_ok && !force_flash) || mode == 2) {
-    // share of the exponentials evaluated on the FMA pipe (poly_exp2) instead of MUFU: 4 of 16 by default
-    static const int poly = getenv("LAMSLIDE_ATTN_POLY") ? atoi(getenv("LAMSLIDE_ATTN_POLY")) : 4;
+    // share of the exponentials evaluated on the FMA pipe (poly_exp2) instead of MUFU (of 16 per thread and key block).
+    // Measured on B200 (4AA temporal attention): 0 -> 677 us, 2 -> 706, 4 -> 742, 8 -> 820: the kernel is issue-bound, so the
+    // extra FMA-pipe instructions cost more than the MUFU slots they free.  Default 0.
+    static const int poly = getenv("LAMSLIDE_ATTN_POLY") ? atoi(getenv("LAMSLIDE_ATTN_POLY")) : 0;
     void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int) =
         poly == 0 ? attn_seq_kernel<HD, 0x0000u> : poly == 2 ? attn_seq_kernel<HD, 0x0808u> : poly == 6 ? attn_seq_kernel<HD, 0xA8A8u>
         : poly == 8 ? attn_seq_kernel<HD, 0xAAAAu> : attn_seq_kernel<HD, 0x8888u>;

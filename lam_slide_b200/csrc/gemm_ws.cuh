@@ -63,6 +63,7 @@ struct EpiLinear1Ws {
     int H, M, rows;
     int pos_div, pos_mod;   // rope position of a row = (row / pos_div) % pos_mod
     float q_premul;         // hd^-0.5 * log2(e)
+    int debug;              // profiling aid (lamslide_debug_linear1): 1 = skip the global stores, 2 = skip the epilogue math
   };
   static constexpr int CW = HD;                                  // chunk width (columns)
   static constexpr int CH = HD / 8;                              // 16-byte chunks per staged row
@@ -99,7 +100,7 @@ struct EpiLinear1Ws {
   // packed chunk (HD bf16 of this thread's row).  kDirectStore: each thread writes its own HD * 2 contiguous bytes (no
   // shared-memory round trip: shared-memory bandwidth is what the UMMA operand fetch and the TMA ring compete for);
   // otherwise staging box -> row-contiguous global stores by the whole warp.
-  static constexpr bool kDirectStore = true;
+  static constexpr bool kDirectStore = false;  // measured on B200: direct 474 us vs staged 391 us per 4AA linear1 launch
   static __device__ __forceinline__ void emit(const Params& p, const WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col) {
     if constexpr (kDirectStore) {
       const int row = c.row0 + c.lane;
@@ -120,7 +121,7 @@ struct EpiLinear1Ws {
       const int id = c.lane + 32 * k;
       const int r = id / CH, ch = id % CH;
       const uint4 val = ld_shared_v4(c.stage_s + r * PITCH + ch * 16);
-      if (c.row0 + r < p.rows) *reinterpret_cast<uint4*>(out + (size_t)(c.row0 + r) * ld + col + ch * 8) = val;
+      if (c.row0 + r < p.rows && p.debug != 1) *reinterpret_cast<uint4*>(out + (size_t)(c.row0 + r) * ld + col + ch * 8) = val;
     }
   }
   // v: HD accumulators of this thread's row, columns col .. col + HD
@@ -128,6 +129,13 @@ struct EpiLinear1Ws {
     const int H3 = 3 * p.H;
     const uint32_t bias_s = c.smf_s + col * 4;
     uint32_t w[HD / 2];
+    if (p.debug == 2) {  // raw accumulators, no math
+#pragma unroll
+      for (int j = 0; j < HD / 2; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      if (t.kind == 3) emit(p, c, w, p.act, p.H + p.M, p.H + (col - H3));
+      else emit(p, c, w, p.qkv, H3, col);
+      return;
+    }
     if (t.kind == 3) {  // ---- MLP: GELU
 #pragma unroll
       for (int j = 0; j < HD / 4; ++j) {

@@ -182,10 +182,6 @@ static int make_tmap_ex(CUtensorMap* map, const void* ptr, CUtensorMapDataType d
   if (r != CUDA_SUCCESS) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)r);
   return 0;
 }
-static CUtensorMapSwizzle swizzle_for_row_bytes(int bytes) {
-  return bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
-}
-
 static bool env_flag(const char* name) {
   const char* v = getenv(name);
   return v && v[0] && v[0] != '0';
@@ -652,7 +648,7 @@ static int ln_modulate(const lamslide_backbone* bb, const float* h, __nv_bfloat1
 struct ForwardCtx {
   BackboneWorkspace ws;
   CUtensorMap tm_u, tm_act, tm_u3;
-  CUtensorMap tm_qkv_st, tm_act_st, tm_h_red;  // epilogue stores of the warp-specialised GEMMs (32-row boxes)
+  CUtensorMap tm_h_red;                         // f32 reduce-add of the linear2 epilogue (16-column x 32-row boxes)
   CUtensorMap tm_emb_a;                         // [n, 6D] split input-embedding operand (lives in the act buffer)
 };
 
@@ -668,10 +664,6 @@ static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, 
   TRY(make_tmap(&fc.tm_u, fc.ws.u, (uint64_t)n, bb->H, kBlockM));
   TRY(make_tmap(&fc.tm_act, fc.ws.act, (uint64_t)n, bb->H + bb->M, kBlockM));
   TRY(make_tmap(&fc.tm_u3, fc.ws.qkv, (uint64_t)n, 3 * bb->H, kBlockM));  // head input [hi | lo | hi] reuses the qkv buffer
-  TRY(make_tmap_ex(&fc.tm_qkv_st, fc.ws.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, 3 * bb->H, bb->hd, 32,
-                   swizzle_for_row_bytes(bb->hd * 2)));
-  TRY(make_tmap_ex(&fc.tm_act_st, fc.ws.act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, bb->H + bb->M, 16, 32,
-                   CU_TENSOR_MAP_SWIZZLE_32B));
   if (bb->w_emb) TRY(make_tmap(&fc.tm_emb_a, fc.ws.act, (uint64_t)n, 6 * bb->D, kBlockM));
   TRY(make_tmap_ex(&fc.tm_h_red, fc.ws.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)n, bb->H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   const int half = bb->hd / 2;
@@ -762,8 +754,8 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   ProfScope ps(PC_LINEAR1, st);                                                                                          \
   int r1 = 1;                                                                                                            \
   if (!legacy_gemm) {                                                                                                    \
-    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul};            \
-    r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_qkv_st, fc.tm_act_st, n, epw, st);                                \
+    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul, 0};            \
+    r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_u, fc.tm_u, n, epw, st);                                \
     if (r1 < 0) return r1;                                                                                               \
   }                                                                                                                      \
   if (r1 == 1) {                                                                                                         \
@@ -1454,42 +1446,46 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
   const int N = 3 * H + M, half = HD / 2;
   const int bn = HD == 24 ? pick_bn({192, 96}, H, M, HD) : pick_bn({128, 64}, H, M, HD);
   if (!bn) return fail(LAMSLIDE_ERR_INVALID, "no linear1 tiling for H %d M %d hd %d", H, M, HD);
-  float *cs = nullptr, *sn = nullptr;
-  CUDA_TRY(cudaMalloc(&cs, (size_t)pos_mod * half * 4));
-  CUDA_TRY(cudaMalloc(&sn, (size_t)pos_mod * half * 4));
-  rope_table_kernel<<<cdiv(pos_mod * half, 256), 256, 0, st>>>(cs, sn, pos_mod, half, (double)theta);
-  CUtensorMap ta, tb, tq, tact;
-  int rc = make_tmap(&ta, u, rows, H, kBlockM);
-  if (!rc) rc = make_tmap(&tb, w1, N, H, bn);
-  if (!rc) rc = make_tmap_ex(&tq, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, 3 * H, HD, 32, swizzle_for_row_bytes(HD * 2));
-  if (!rc) rc = make_tmap_ex(&tact, act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, H + M, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B);
+  static float *cs = nullptr, *sn = nullptr;  // debug hook: cached RoPE tables (not thread-safe)
+  static size_t cap = 0;
+  static int have_pos = 0, have_half = 0;
+  static float have_theta = 0.f;
+  const size_t need = (size_t)pos_mod * half * 4;
+  if (need > cap) {
+    cudaFree(cs), cudaFree(sn);
+    CUDA_TRY(cudaMalloc(&cs, need));
+    CUDA_TRY(cudaMalloc(&sn, need));
+    cap = need, have_pos = 0;
+  }
+  if (have_pos != pos_mod || have_half != half || have_theta != theta) {
+    rope_table_kernel<<<cdiv(pos_mod * half, 256), 256, 0, st>>>(cs, sn, pos_mod, half, (double)theta);
+    have_pos = pos_mod, have_half = half, have_theta = theta;
+  }
+  CUtensorMap ta, tb;
+  TRY(make_tmap(&ta, u, rows, H, kBlockM));
+  TRY(make_tmap(&tb, w1, N, H, bn));
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)HD));
-  if (!rc) {
-    if (!legacy) {
-      typename EpiLinear1Ws<HD>::Params ep{bias, gq, gk, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod, q_premul};
-      if constexpr (HD == 24) {
-        rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, tq, tact, rows, N, H, ep, st) : 1;
-      } else {
-        if (bn == 128) rc = launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, tq, tact, rows, N, H, ep, st);
-        else if constexpr (HD == 16) rc = launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, tb, tq, tact, rows, N, H, ep, st);
-        else rc = 1;
-      }
-      if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear1 kernel does not cover H %d M %d hd %d", H, M, HD);
+  int rc;
+  if (legacy != 1) {
+    typename EpiLinear1Ws<HD>::Params ep{bias, gq, gk, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod, q_premul,
+                                         legacy == 2 ? 1 : legacy == 3 ? 2 : 0};
+    if constexpr (HD == 24) {
+      rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, ta, ta, rows, N, H, ep, st) : 1;
     } else {
-      typename EpiLinear1<HD>::Params ep{bias, gq, gk, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod, q_premul};
-      if constexpr (HD == 24) {
-        rc = bn == 192 ? launch_gemm<192, EpiLinear1<24>>(ta, tb, rows, N, H, ep, st) : launch_gemm<96, EpiLinear1<24>>(ta, tb, rows, N, H, ep, st);
-      } else {
-        rc = bn == 128 ? launch_gemm<128, EpiLinear1<HD>>(ta, tb, rows, N, H, ep, st) : launch_gemm<64, EpiLinear1<HD>>(ta, tb, rows, N, H, ep, st);
-      }
+      if (bn == 128) rc = launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, ta, ta, rows, N, H, ep, st);
+      else if constexpr (HD == 16) rc = launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, tb, ta, ta, rows, N, H, ep, st);
+      else rc = 1;
+    }
+    if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear1 kernel does not cover H %d M %d hd %d", H, M, HD);
+  } else {
+    typename EpiLinear1<HD>::Params ep{bias, gq, gk, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod, q_premul};
+    if constexpr (HD == 24) {
+      rc = bn == 192 ? launch_gemm<192, EpiLinear1<24>>(ta, tb, rows, N, H, ep, st) : launch_gemm<96, EpiLinear1<24>>(ta, tb, rows, N, H, ep, st);
+    } else {
+      rc = bn == 128 ? launch_gemm<128, EpiLinear1<HD>>(ta, tb, rows, N, H, ep, st) : launch_gemm<64, EpiLinear1<HD>>(ta, tb, rows, N, H, ep, st);
     }
   }
-  cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(cs);
-  cudaFree(sn);
-  if (rc) return rc;
-  if (e != cudaSuccess) return fail(LAMSLIDE_ERR_CUDA, "debug_linear1: %s", cudaGetErrorString(e));
-  return 0;
+  return rc;
 }
 
 extern "C" int lamslide_debug_linear1(const void* u_bf16, const void* w1_bf16, const float* bias, const float* q_scale,

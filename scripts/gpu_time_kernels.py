@@ -37,9 +37,30 @@ def attn():
     print(f"attn_seq LAMSLIDE_ATTN_POLY={os.environ.get('LAMSLIDE_ATTN_POLY', 'default')}: {us:8.1f} us  {flops / us * 1e-6:7.1f} TFLOP/s", flush=True)
 
 
+def linear1():
+    """linear1 of the 4AA config at B = 64 (128000 rows): full kernel, math without stores, stores without math"""
+    import math
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rows, H, M, heads = 128000, 384, 1536, 16
+    u = torch.randn(rows, H, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn(3 * H + M, H, device="cuda") / math.sqrt(H)).to(torch.bfloat16)
+    bias = torch.randn(3 * H + M, device="cuda") * 0.1
+    gq = torch.ones(24, device="cuda")
+    gk = torch.ones(24, device="cuda")
+    qkv = torch.empty(rows, 3 * H, device="cuda", dtype=torch.bfloat16)
+    act = torch.empty(rows, H + M, device="cuda", dtype=torch.bfloat16)
+    for mode, name in [(0, "full"), (2, "math, no stores"), (3, "stores, no math"), (1, "legacy kernel")]:
+        us = time_fn(lambda: L.check(lib.lamslide_debug_linear1(u.data_ptr(), w1.data_ptr(), bias.data_ptr(), gq.data_ptr(), gk.data_ptr(),
+                                                                qkv.data_ptr(), act.data_ptr(), rows, H, M, heads, 2, 1000, 10000.0, mode, st)))
+        print(f"linear1 [{name}]: {us:8.1f} us  {2.0 * rows * (3 * H + M) * H / us * 1e-6:7.1f} TFLOP/s", flush=True)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "attn":
         return attn()
+    if len(sys.argv) > 1 and sys.argv[1] == "linear1":
+        return linear1()
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 128000
     lib = L.load()
     st = torch.cuda.current_stream().cuda_stream

@@ -21,7 +21,7 @@ namespace lam {
 
 constexpr int kWsEpiWarps = 16;                      // 4 TMEM lane quarters x 4 column quarters
 constexpr int kWsThreads = 64 + 32 * kWsEpiWarps;   // + TMA warp + MMA warp
-constexpr int kWsStageBytesPerWarp = 2560;           // one staged box (<= 32 rows x 80 B) per warp
+constexpr int kWsStageBytesPerWarp = 3072;           // one staged box (<= 32 rows x 96 B) per warp
 constexpr int kWsMaxKBlocksResident = 8;
 
 struct WsCtx {
@@ -54,33 +54,32 @@ template <int HD>
 struct EpiLinear1Ws {
   struct Params {
     const float* bias;      // [3H + M]
-    const float* q_scale;   // [HD]
-    const float* k_scale;   // [HD]
+    float gam[2][HD];       // [0]: query_norm.scale * hd^-0.5 * log2(e), [1]: key_norm.scale  (by value: constant-bank operands)
     const float* rope_cos;  // [S, HD/2]
     const float* rope_sin;
     __nv_bfloat16* qkv;     // [rows, 3H]
     __nv_bfloat16* act;     // [rows, H + M]
     int H, M, rows;
     int pos_div, pos_mod;   // rope position of a row = (row / pos_div) % pos_mod
-    float q_premul;         // hd^-0.5 * log2(e)
     int debug;              // profiling aid (lamslide_debug_linear1): 1 = skip the global stores, 2 = skip the epilogue math
   };
   static constexpr int CW = HD;                                  // chunk width (columns)
-  static constexpr int CH = HD / 8;                              // 16-byte chunks per staged row
-  static constexpr int PITCH = (CH % 2 == 0 ? CH + 1 : CH) * 16;  // bytes
+  static constexpr int CH = HD / 8;                              // 16-byte units per chunk row
+  // Global stores must cover whole 32-byte sectors (partial-sector writes ran at ~1.8 TB/s into L2 on B200 and bounded the
+  // kernel): when a chunk row (HD * 2 bytes) is not a multiple of 32 bytes, two consecutive chunks are staged side by side
+  // and written out together.
+  static constexpr bool kPair = (HD * 2) % 32 != 0;
+  static constexpr int UNITS = kPair ? 2 * CH : CH;             // 16-byte units per staged row
+  static constexpr int PITCH = (kPair ? UNITS : (UNITS % 2 == 0 ? UNITS + 1 : UNITS)) * 16;  // bytes (pairs: dense, 2-way conflicts on the writes only)
   static_assert(32 * PITCH <= kWsStageBytesPerWarp, "staging box too large");
   struct Tile {
     int kind;  // 0 q, 1 k, 2 v, 3 mlp
     const float4 *cs, *sn;  // this row's RoPE table entries (L1-resident: re-read per head rather than held in 24 registers)
   };
-  static __host__ __device__ int smem_floats(const Params& p) { return 3 * p.H + p.M + 2 * HD; }
+  static __host__ __device__ int smem_floats(const Params& p) { return 3 * p.H + p.M; }
   static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
     const int N = 3 * p.H + p.M;
     for (int i = tid; i < N; i += nthreads) smf[i] = p.bias[i];
-    for (int i = tid; i < HD; i += nthreads) {
-      smf[N + i] = p.q_scale[i] * p.q_premul;
-      smf[N + HD + i] = p.k_scale[i];
-    }
   }
   // n-tile order: MLP (MUFU-heavy epilogue) and q/k/v tiles alternate so the epilogue load is even over time
   template <int BN>
@@ -97,43 +96,36 @@ struct EpiLinear1Ws {
     t.cs = reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * (HD / 2));
     t.sn = reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * (HD / 2));
   }
-  // packed chunk (HD bf16 of this thread's row).  kDirectStore: each thread writes its own HD * 2 contiguous bytes (no
-  // shared-memory round trip: shared-memory bandwidth is what the UMMA operand fetch and the TMA ring compete for);
-  // otherwise staging box -> row-contiguous global stores by the whole warp.
-  static constexpr bool kDirectStore = false;  // measured on B200: direct 474 us vs staged 391 us per 4AA linear1 launch
-  static __device__ __forceinline__ void emit(const Params& p, const WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col) {
-    if constexpr (kDirectStore) {
-      const int row = c.row0 + c.lane;
-      if (row < p.rows) {
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * ld + col);
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) dst[ch] = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
-      }
-      return;
-    }
-    __syncwarp();  // the previous box has been read out by every lane
+  // packed chunk (HD bf16 of this thread's row, chunk index ck inside the warp's column quarter) -> staging box ->
+  // row-contiguous, sector-aligned 16-byte global stores by the whole warp.  (Direct per-thread row stores were measured at
+  // 474 us per 4AA launch against 391 us staged; small-box TMA stores were no better.)
+  static __device__ __forceinline__ void emit(const Params& p, const WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col, int ck) {
+    const int half = kPair ? (ck & 1) : 0;
+    if (half == 0) __syncwarp();  // the previous box has been read out by every lane
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
-      st_shared_v4(c.stage_s + c.lane * PITCH + ch * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+      st_shared_v4(c.stage_s + c.lane * PITCH + (half * CH + ch) * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+    if (kPair && half == 0) return;
     __syncwarp();
+    const int col0 = col - half * HD;  // first column of the staged row
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
+    for (int k = 0; k < UNITS; ++k) {
       const int id = c.lane + 32 * k;
-      const int r = id / CH, ch = id % CH;
+      const int r = id / UNITS, ch = id % UNITS;
       const uint4 val = ld_shared_v4(c.stage_s + r * PITCH + ch * 16);
-      if (c.row0 + r < p.rows && p.debug != 1) *reinterpret_cast<uint4*>(out + (size_t)(c.row0 + r) * ld + col + ch * 8) = val;
+      if (c.row0 + r < p.rows && p.debug != 1) *reinterpret_cast<uint4*>(out + (size_t)(c.row0 + r) * ld + col0 + ch * 8) = val;
     }
   }
   // v: HD accumulators of this thread's row, columns col .. col + HD
-  static __device__ __forceinline__ void chunk(const Params& p, const WsCtx& c, const Tile& t, const uint32_t* v, int col) {
+  static __device__ __forceinline__ void chunk(const Params& p, const WsCtx& c, const Tile& t, const uint32_t* v, int col, int ck) {
     const int H3 = 3 * p.H;
     const uint32_t bias_s = c.smf_s + col * 4;
     uint32_t w[HD / 2];
     if (p.debug == 2) {  // raw accumulators, no math
 #pragma unroll
       for (int j = 0; j < HD / 2; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-      if (t.kind == 3) emit(p, c, w, p.act, p.H + p.M, p.H + (col - H3));
-      else emit(p, c, w, p.qkv, H3, col);
+      if (t.kind == 3) emit(p, c, w, p.act, p.H + p.M, p.H + (col - H3), ck);
+      else emit(p, c, w, p.qkv, H3, col, ck);
       return;
     }
     if (t.kind == 3) {  // ---- MLP: GELU
@@ -147,7 +139,7 @@ struct EpiLinear1Ws {
         w[2 * j] = pack_bf16x2(y0, y1);
         w[2 * j + 1] = pack_bf16x2(y2, y3);
       }
-      emit(p, c, w, p.act, p.H + p.M, p.H + (col - H3));
+      emit(p, c, w, p.act, p.H + p.M, p.H + (col - H3), ck);
       return;
     }
     if (t.kind == 2) {  // ---- v: bias only
@@ -157,11 +149,10 @@ struct EpiLinear1Ws {
         w[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j + 0]) + bv.x, __uint_as_float(v[4 * j + 1]) + bv.y);
         w[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bv.z, __uint_as_float(v[4 * j + 3]) + bv.w);
       }
-      emit(p, c, w, p.qkv, H3, col);
+      emit(p, c, w, p.qkv, H3, col, ck);
       return;
     }
     // ---- q or k: RMSNorm + RoPE over the head
-    const uint32_t gam_s = c.smf_s + (H3 + p.M + t.kind * HD) * 4;  // q: scale * premul, k: scale
     float x[HD];
     float ss = 0.f;
 #pragma unroll
@@ -185,7 +176,8 @@ struct EpiLinear1Ws {
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
         const int j = 2 * j2 + h2;
-        const float4 gv = ld_shared_f4(gam_s + j * 16);
+        const float4 gv = t.kind == 0 ? make_float4(p.gam[0][4 * j], p.gam[0][4 * j + 1], p.gam[0][4 * j + 2], p.gam[0][4 * j + 3])
+                                      : make_float4(p.gam[1][4 * j], p.gam[1][4 * j + 1], p.gam[1][4 * j + 2], p.gam[1][4 * j + 3]);
         const float e0 = x[4 * j + 0] * gv.x, d0 = x[4 * j + 1] * gv.y;
         const float e1 = x[4 * j + 2] * gv.z, d1 = x[4 * j + 3] * gv.w;
         const float c0 = cc[2 * h2], s0 = sc[2 * h2], c1 = cc[2 * h2 + 1], s1 = sc[2 * h2 + 1];
@@ -193,7 +185,7 @@ struct EpiLinear1Ws {
         w[2 * j + 1] = pack_bf16x2(fmaf(c1, e1, -s1 * d1), fmaf(s1, e1, c1 * d1));
       }
     }
-    emit(p, c, w, p.qkv, H3, col);
+    emit(p, c, w, p.qkv, H3, col, ck);
   }
   static __device__ __forceinline__ void finish(const WsCtx&) {}
 };
@@ -223,7 +215,7 @@ struct EpiLinear2Ws {
     const int b = (row < p.rows ? row : p.rows - 1) / p.rows_per_sample;
     t.gate = p.gate + (size_t)b * p.gate_stride;
   }
-  static __device__ __forceinline__ void chunk(const Params&, const WsCtx& c, const Tile& t, const uint32_t* v, int col) {
+  static __device__ __forceinline__ void chunk(const Params&, const WsCtx& c, const Tile& t, const uint32_t* v, int col, int) {
     float4 o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -281,7 +273,7 @@ struct EpiEmbedWs {
     const int m = row < p.rows ? (p.mask[row] != 0 ? 1 : 0) : 0;
     t.em_s = c.smf_s + (p.H + m * p.H) * 4;
   }
-  static __device__ __forceinline__ void chunk(const Params& p, const WsCtx& c, const Tile& t, const uint32_t* v, int col) {
+  static __device__ __forceinline__ void chunk(const Params& p, const WsCtx& c, const Tile& t, const uint32_t* v, int col, int) {
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -314,7 +306,7 @@ struct EpiNullWs {
   template <int BN>
   static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
   static __device__ __forceinline__ void tile_begin(const Params&, const WsCtx&, Tile&, int, int) {}
-  static __device__ __forceinline__ void chunk(const Params&, const WsCtx&, const Tile&, const uint32_t*, int) {}
+  static __device__ __forceinline__ void chunk(const Params&, const WsCtx&, const Tile&, const uint32_t*, int, int) {}
   static __device__ __forceinline__ void finish(const WsCtx&) {}
 };
 
@@ -329,9 +321,9 @@ static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_bloc
   s.stage_bytes = (a_resident ? 0 : kABytes) + BN * kBlockK * 2;
   s.ring_bytes = stages * s.stage_bytes;
   s.staging_bytes = kWsEpiWarps * kWsStageBytesPerWarp;
-  s.const_bytes = (const_floats * 4 + 127) / 128 * 128;
-  s.bar_bytes = 512;
-  s.total = s.a_res_bytes + s.ring_bytes + s.staging_bytes + s.const_bytes + s.bar_bytes + 1024;  // +1024: manual alignment
+  s.const_bytes = (const_floats * 4 + 15) / 16 * 16;
+  s.bar_bytes = 320;  // 37 mbarriers + the TMEM base slot
+  s.total = s.a_res_bytes + s.ring_bytes + s.staging_bytes + s.const_bytes + s.bar_bytes;  // dynamic smem base is 1024-aligned (checked)
   return s;
 }
 
@@ -347,8 +339,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int CW = Epi::CW;
   static_assert(QW % CW == 0, "a warp's column quarter must hold whole epilogue chunks");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128-byte-swizzled operand tiles need a 1024-byte aligned base
   const WsSmemPlan plan = ws_smem_plan(BN, num_k_blocks, stages, a_resident, Epi::smem_floats(ep));
   uint8_t* a_res = smem;
   uint8_t* ring = a_res + plan.a_res_bytes;
@@ -480,7 +473,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           }
-          Epi::chunk(ep, c, ts, v, n0w + ck * CW);
+          Epi::chunk(ep, c, ts, v, n0w + ck * CW, ck);
         }
       }
     }

@@ -225,7 +225,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int rows, i
 template <int BN, class Epi>
 static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& o0, const CUtensorMap& o1, int rows, int N,
                           int K, const typename Epi::Params& ep, cudaStream_t st) {
-  constexpr int kSmemMax = 232448;  // 227 KB per CTA on sm_100
+  constexpr int kSmemMax = 232448;  // 227 KB of dynamic shared memory per CTA on sm_100
   const int kblocks = K / kBlockK;
   const int cf = Epi::smem_floats(ep);
   int a_res = kblocks <= kWsMaxKBlocksResident ? 1 : 0, stages = 0;
@@ -260,6 +260,7 @@ struct BlockWeights {
   __nv_bfloat16* w1 = nullptr;  // [3H+M, H]
   __nv_bfloat16* w2 = nullptr;  // [H, H+M]
   float *b1 = nullptr, *b2 = nullptr, *gq = nullptr, *gk = nullptr;
+  float gq_h[32] = {0}, gk_h[32] = {0};  // host copies of the QK-norm scales (passed by value to the persistent linear1 kernel)
   float logit_bound = 0.f;  // max |q.k| * hd^-0.5 * log2(e) after QK-RMSNorm: hd^0.5 * log2(e) * max|gq| * max|gk|
   CUtensorMap tm_w1, tm_w2;
 };
@@ -456,6 +457,7 @@ extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, con
       TRY(A.upload_f32(b2->data, H, &bw.b2));
       TRY(A.upload_f32(gq->data, hd, &bw.gq));
       TRY(A.upload_f32(gk->data, hd, &bw.gk));
+      for (int j = 0; j < hd; ++j) bw.gq_h[j] = gq->data[j], bw.gk_h[j] = gk->data[j];
       {
         float mq = 0.f, mk = 0.f;
         for (int j = 0; j < hd; ++j) mq = std::max(mq, std::fabs(gq->data[j])), mk = std::max(mk, std::fabs(gk->data[j]));
@@ -754,7 +756,8 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   ProfScope ps(PC_LINEAR1, st);                                                                                          \
   int r1 = 1;                                                                                                            \
   if (!legacy_gemm) {                                                                                                    \
-    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul, 0};            \
+    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, {}, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, 0};                                \
+    for (int j = 0; j < HD_; ++j) epw.gam[0][j] = bw.gq_h[j] * q_premul, epw.gam[1][j] = bw.gk_h[j];                                         \
     r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_u, fc.tm_u, n, epw, st);                                \
     if (r1 < 0) return r1;                                                                                               \
   }                                                                                                                      \
@@ -1467,8 +1470,18 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)HD));
   int rc;
   if (legacy != 1) {
-    typename EpiLinear1Ws<HD>::Params ep{bias, gq, gk, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod, q_premul,
+    typename EpiLinear1Ws<HD>::Params ep{bias, {}, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod,
                                          legacy == 2 ? 1 : legacy == 3 ? 2 : 0};
+    {  // debug hook: the scales arrive as device pointers; fetch them once per distinct pointer pair (not thread-safe)
+      static const float *last_q = nullptr, *last_k = nullptr;
+      static float hq[32], hk[32];
+      if (last_q != gq || last_k != gk) {
+        CUDA_TRY(cudaMemcpy(hq, gq, HD * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(hk, gk, HD * 4, cudaMemcpyDeviceToHost));
+        last_q = gq, last_k = gk;
+      }
+      for (int j = 0; j < HD; ++j) ep.gam[0][j] = hq[j] * q_premul, ep.gam[1][j] = hk[j];
+    }
     if constexpr (HD == 24) {
       rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, ta, ta, rows, N, H, ep, st) : 1;
     } else {

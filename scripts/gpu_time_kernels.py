@@ -42,7 +42,8 @@ def linear1():
     import math
     lib = L.load()
     st = torch.cuda.current_stream().cuda_stream
-    rows, H, M, heads = 128000, 384, 1536, 16
+    rows = int(sys.argv[2]) if len(sys.argv) > 2 else 128000
+    H, M, heads = 384, 1536, 16
     u = torch.randn(rows, H, device="cuda").to(torch.bfloat16)
     w1 = (torch.randn(3 * H + M, H, device="cuda") / math.sqrt(H)).to(torch.bfloat16)
     bias = torch.randn(3 * H + M, device="cuda") * 0.1
@@ -53,7 +54,7 @@ def linear1():
     for mode, name in [(0, "full"), (2, "math, no stores"), (3, "stores, no math"), (1, "legacy kernel")]:
         us = time_fn(lambda: L.check(lib.lamslide_debug_linear1(u.data_ptr(), w1.data_ptr(), bias.data_ptr(), gq.data_ptr(), gk.data_ptr(),
                                                                 qkv.data_ptr(), act.data_ptr(), rows, H, M, heads, 2, 1000, 10000.0, mode, st)))
-        print(f"linear1 [{name}]: {us:8.1f} us  {2.0 * rows * (3 * H + M) * H / us * 1e-6:7.1f} TFLOP/s", flush=True)
+        print(f"linear1 rows={rows} [{name}]: {us:8.1f} us  {2.0 * rows * (3 * H + M) * H / us * 1e-6:7.1f} TFLOP/s", flush=True)
 
 
 def main():

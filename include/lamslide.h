@@ -164,7 +164,8 @@ int lamslide_debug_attention(const void* qkv_bf16, void* out_bf16, int32_t B, in
 /* linear1 of one ParallelMLPAttentionV2 block with its fused epilogue (mmdit.py:241-247: bias, QK-RMSNorm, RoPE, q pre-scale,
  * erf-GELU) in isolation: u [rows,H] bf16, w1 [3H+M,H] bf16 -> qkv [rows,3H] bf16, act[:, H:] of [rows,H+M] bf16.
  * The rope position of a row is (row / pos_div) % pos_mod.  legacy: 0 persistent kernel, 1 one-tile-per-CTA kernel,
- * 2 / 3 profiling aids of the persistent kernel (2: epilogue math without the global stores, 3: stores without the math). */
+ * 2 / 3 profiling aids of the persistent kernel (2: epilogue math without the global stores, 3: stores without the math);
+ * + 16: run the persistent kernel as single CTAs instead of 2-CTA clusters that multicast the weight tiles. */
 int lamslide_debug_linear1(const void* u_bf16, const void* w1_bf16, const float* bias, const float* q_scale, const float* k_scale,
                            void* qkv_bf16, void* act_bf16, int32_t rows, int32_t H, int32_t M, int32_t heads, int32_t pos_div,
                            int32_t pos_mod, float theta, int32_t legacy, void* stream);
@@ -174,7 +175,8 @@ int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16, const floa
                            int32_t H, int32_t M, int32_t rows_per_sample, int32_t legacy, void* stream);
 
 /* the TMA + tcgen05 main loop of the persistent GEMM alone (no epilogue work, nothing stored): profiling aid that
- * separates "operand feed + tensor pipe" from "epilogue" for a shape.  block_n in {192, 128, 64}. */
+ * separates "operand feed + tensor pipe" from "epilogue" for a shape.  |block_n| in {192, 128, 64}; negative: single CTAs
+ * instead of 2-CTA clusters with weight-tile multicast. */
 int lamslide_debug_gemm_mainloop(const void* a_bf16, const void* b_bf16, int32_t rows, int32_t N, int32_t K, int32_t block_n,
                                  void* stream);
 

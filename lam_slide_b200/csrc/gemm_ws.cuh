@@ -327,7 +327,10 @@ static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_bloc
   return s;
 }
 
-template <int BN, class Epi>
+// CL = cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring m-blocks and walk the n-tiles in
+// lockstep; each loads HALF of every weight tile and multicasts it to both, so the L2 -> SM weight traffic — the resource
+// that bounds the one-CTA version (every SM re-reads all of W per 128 rows: 2.2 GB per 4AA linear1 launch at ~10 TB/s) — halves.
+template <int BN, int CL, class Epi>
 __global__ void __launch_bounds__(kWsThreads, 1)  // 18 warps are allocated as 20 (granularity 4): <= 96 registers per thread
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1, int num_m_blocks,
@@ -358,13 +361,19 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int m_first = (blockIdx.x / CL) * CL;          // first m-block of this CTA's cluster
+  const int m_step = (gridDim.x / CL) * CL;            // m-blocks per sweep of the whole grid
+  constexpr uint16_t kClusterMask = (1u << CL) - 1;
+  constexpr int kBSlice = BN / CL;                     // weight-tile rows this CTA fetches (and multicasts)
+  static_assert(BN % (8 * CL) == 0, "a multicast slice must be whole 8-row swizzle atoms");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);  // released by the MMA warp of every CTA of the cluster
     }
     for (int k = 0; k < kWsMaxKBlocksResident; ++k) {
       mbar_init(&a_full[k], 1);
@@ -380,6 +389,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp >= 2) Epi::load_consts(ep, smf, threadIdx.x - 64, kWsThreads - 64);
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast traffic / remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -388,7 +398,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0, mb_iter = 0;
-      for (int mb = blockIdx.x; mb < num_m_blocks; mb += gridDim.x, ++mb_iter) {
+      for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++mb_iter) {
+        const int mb = mbase + cta_rank;  // may be past the end in the last sweep: the TMA zero-fills, nothing is stored
         for (int nt = 0; nt < num_n_tiles; ++nt) {
           const int n0 = Epi::template tile_n0<BN>(ep, nt);
           for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -404,7 +415,11 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               tma_load_2d(&tmap_a, &full_bar[s], dst, kb * kBlockK, mb * kBlockM);
               dst += kABytes;
             }
-            tma_load_2d(&tmap_b, &full_bar[s], dst, kb * kBlockK, n0);
+            if constexpr (CL == 1) {
+              tma_load_2d(&tmap_b, &full_bar[s], dst, kb * kBlockK, n0);
+            } else {
+              tma_load_2d_mc(&tmap_b, &full_bar[s], dst + cta_rank * kBSlice * (kBlockK * 2), kb * kBlockK, n0 + cta_rank * kBSlice, kClusterMask);
+            }
             if (++s == stages) s = 0, ph ^= 1;
           }
         }
@@ -416,7 +431,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
       int s = 0;
       uint32_t ph = 0, mb_iter = 0, tile = 0;
-      for (int mb = blockIdx.x; mb < num_m_blocks; mb += gridDim.x, ++mb_iter) {
+      for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++mb_iter) {
         for (int nt = 0; nt < num_n_tiles; ++nt, ++tile) {
           const uint32_t acc = tile & 1, use = tile >> 1;
           mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator stage
@@ -434,7 +449,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(&empty_bar[s]);
+            if constexpr (CL == 1) umma_commit(&empty_bar[s]);
+            else umma_commit_mc(&empty_bar[s], kClusterMask);
             if (a_resident && nt == num_n_tiles - 1) umma_commit(&a_empty[kb]);
             if (++s == stages) s = 0, ph ^= 1;
           }
@@ -453,7 +469,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     c.lane = lane;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cq * QW;
     uint32_t tile = 0;
-    for (int mb = blockIdx.x; mb < num_m_blocks; mb += gridDim.x) {
+    for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step) {
+      const int mb = mbase + cta_rank;
       c.row0 = mb * kBlockM + q * 32;
       const int row = c.row0 + lane;
       for (int nt = 0; nt < num_n_tiles; ++nt, ++tile) {
@@ -482,6 +499,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);

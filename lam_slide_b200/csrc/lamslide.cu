@@ -221,10 +221,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int rows, i
 }
 
 // persistent warp-specialised GEMM (gemm_ws.cuh).  Returns 1 (and launches nothing) when the shape does not fit its
-// shared-memory plan; the caller then uses the one-tile-per-CTA kernel above.
+// shared-memory plan; the caller then uses the one-tile-per-CTA kernel above.  tb_half: the weight map with a box of BN / 2
+// rows — when given (and the grid is large enough) the kernel runs as 2-CTA clusters that multicast the weight tiles.
 template <int BN, class Epi>
-static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& o0, const CUtensorMap& o1, int rows, int N,
-                          int K, const typename Epi::Params& ep, cudaStream_t st) {
+static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_half, const CUtensorMap& o0, int rows,
+                          int N, int K, const typename Epi::Params& ep, cudaStream_t st) {
   constexpr int kSmemMax = 232448;  // 227 KB of dynamic shared memory per CTA on sm_100
   const int kblocks = K / kBlockK;
   const int cf = Epi::smem_floats(ep);
@@ -242,15 +243,37 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   }
   if (!stages) return 1;
   const WsSmemPlan plan = ws_smem_plan(BN, kblocks, stages, a_res, cf);
-  auto kern = gemm_ws_kernel<BN, Epi>;
-  static int configured = 0;
-  if (configured < plan.total) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    configured = kSmemMax;
-  }
   const int mblocks = cdiv(rows, kBlockM);
-  const int grid = std::min(num_sms(), mblocks);
-  kern<<<grid, kWsThreads, plan.total, st>>>(ta, tb, o0, o1, mblocks, N / BN, kblocks, stages, a_res, ep);
+  static const bool no_cluster = env_flag("LAMSLIDE_NO_CLUSTER");
+  const bool use_cluster = tb_half && !no_cluster && mblocks >= 2 && num_sms() >= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kWsThreads);
+  cfg.dynamicSmemBytes = plan.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (use_cluster) {
+    auto kern = gemm_ws_kernel<BN, 2, Epi>;
+    static bool configured = false;
+    if (!configured) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+      configured = true;
+    }
+    const int grid = std::min(num_sms() / 2 * 2, cdiv(mblocks, 2) * 2);
+    cfg.gridDim = dim3(grid);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, *tb_half, o0, o0, mblocks, N / BN, kblocks, stages, a_res, ep));
+  } else {
+    auto kern = gemm_ws_kernel<BN, 1, Epi>;
+    static bool configured = false;
+    if (!configured) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+      configured = true;
+    }
+    cfg.gridDim = dim3(std::min(num_sms(), mblocks));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, o0, o0, mblocks, N / BN, kblocks, stages, a_res, ep));
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -263,6 +286,7 @@ struct BlockWeights {
   float gq_h[32] = {0}, gk_h[32] = {0};  // host copies of the QK-norm scales (passed by value to the persistent linear1 kernel)
   float logit_bound = 0.f;  // max |q.k| * hd^-0.5 * log2(e) after QK-RMSNorm: hd^0.5 * log2(e) * max|gq| * max|gk|
   CUtensorMap tm_w1, tm_w2;
+  CUtensorMap tm_w1_h, tm_w2_h;  // boxes of half a tile: 2-CTA clusters fetch half a weight tile each and multicast it
 };
 
 struct lamslide_backbone {
@@ -274,7 +298,7 @@ struct lamslide_backbone {
   Arena arena;
   float *wt_in = nullptr, *b_in = nullptr, *emask = nullptr;
   __nv_bfloat16* w_emb = nullptr;  // [H, 6D] hi/lo split of [Wx | Wc] for the tensor-core input embedding (0 = not available)
-  CUtensorMap tm_wemb;
+  CUtensorMap tm_wemb, tm_wemb_h;
   int bn_emb = 0;
   float *time_w1 = nullptr, *time_b1 = nullptr, *time_w2 = nullptr, *time_b2 = nullptr;
   float *vec_w1 = nullptr, *vec_b1 = nullptr, *vec_w2 = nullptr, *vec_b2 = nullptr;
@@ -401,6 +425,7 @@ extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, con
         }
       TRY(A.upload(we.data(), we.size() * sizeof(__nv_bfloat16), (void**)&bb->w_emb));
       TRY(make_tmap(&bb->tm_wemb, bb->w_emb, H, 6 * D, bb->bn_emb));
+      TRY(make_tmap(&bb->tm_wemb_h, bb->w_emb, H, 6 * D, bb->bn_emb / 2));
     }
   }
   {
@@ -465,6 +490,8 @@ extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, con
       }
       TRY(make_tmap(&bw.tm_w1, bw.w1, 3 * H + M, H, bn1));
       TRY(make_tmap(&bw.tm_w2, bw.w2, H, H + M, bn2));
+      TRY(make_tmap(&bw.tm_w1_h, bw.w1, 3 * H + M, H, bn1 / 2));
+      TRY(make_tmap(&bw.tm_w2_h, bw.w2, H, H + M, bn2 / 2));
     }
   }
   {
@@ -532,15 +559,15 @@ static int launch_linear2(const lamslide_backbone* bb, const CUtensorMap& ta, co
 
 // warp-specialised variants; return 1 when the tiling is not covered (caller falls back to the kernels above)
 template <int HD>
-static int launch_linear1_ws(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, const CUtensorMap& qkv_st,
-                             const CUtensorMap& act_st, int rows, const typename EpiLinear1Ws<HD>::Params& ep, cudaStream_t st) {
+static int launch_linear1_ws(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, int rows,
+                             const typename EpiLinear1Ws<HD>::Params& ep, cudaStream_t st) {
   const int N = 3 * bb->H + bb->M, K = bb->H;
   if constexpr (HD == 24) {
-    if (bb->bn1 == 192) return launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
+    if (bb->bn1 == 192) return launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, bw.tm_w1, &bw.tm_w1_h, ta, rows, N, K, ep, st);
   } else {
-    if (bb->bn1 == 128) return launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
+    if (bb->bn1 == 128) return launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, bw.tm_w1, &bw.tm_w1_h, ta, rows, N, K, ep, st);
     if constexpr (HD == 16) {
-      if (bb->bn1 == 64) return launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, bw.tm_w1, qkv_st, act_st, rows, N, K, ep, st);
+      if (bb->bn1 == 64) return launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, bw.tm_w1, &bw.tm_w1_h, ta, rows, N, K, ep, st);
     }
   }
   return 1;
@@ -550,9 +577,9 @@ static int launch_linear2_ws(const lamslide_backbone* bb, const CUtensorMap& ta,
                              int rows, const EpiLinear2Ws::Params& ep, cudaStream_t st) {
   const int N = bb->H, K = bb->H + bb->M;
   switch (bb->bn2) {
-    case 192: return launch_gemm_ws<192, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
-    case 128: return launch_gemm_ws<128, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
-    case 64: return launch_gemm_ws<64, EpiLinear2Ws>(ta, bw.tm_w2, h_red, h_red, rows, N, K, ep, st);
+    case 192: return launch_gemm_ws<192, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, rows, N, K, ep, st);
+    case 128: return launch_gemm_ws<128, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, rows, N, K, ep, st);
+    case 64: return launch_gemm_ws<64, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, rows, N, K, ep, st);
     default: return 1;
   }
 }
@@ -695,9 +722,9 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
       LAUNCH_CHECK();
       EpiEmbedWs::Params ee{bb->b_in, bb->emask, (const long long*)mask, w.h, H, n};
       switch (bb->bn_emb) {
-        case 192: re = launch_gemm_ws<192, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
-        case 128: re = launch_gemm_ws<128, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
-        case 64: re = launch_gemm_ws<64, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        case 192: re = launch_gemm_ws<192, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        case 128: re = launch_gemm_ws<128, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        case 64: re = launch_gemm_ws<64, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
         default: break;
       }
       if (re < 0) return re;
@@ -758,7 +785,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   if (!legacy_gemm) {                                                                                                    \
     typename EpiLinear1Ws<HD_>::Params epw{bw.b1, {}, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, 0};                                \
     for (int j = 0; j < HD_; ++j) epw.gam[0][j] = bw.gq_h[j] * q_premul, epw.gam[1][j] = bw.gk_h[j];                                         \
-    r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_u, fc.tm_u, n, epw, st);                                \
+    r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, n, epw, st);                                \
     if (r1 < 0) return r1;                                                                                               \
   }                                                                                                                      \
   if (r1 == 1) {                                                                                                         \
@@ -1464,9 +1491,12 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
     rope_table_kernel<<<cdiv(pos_mod * half, 256), 256, 0, st>>>(cs, sn, pos_mod, half, (double)theta);
     have_pos = pos_mod, have_half = half, have_theta = theta;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tbh_map;
   TRY(make_tmap(&ta, u, rows, H, kBlockM));
   TRY(make_tmap(&tb, w1, N, H, bn));
+  TRY(make_tmap(&tbh_map, w1, N, H, bn / 2));
+  const CUtensorMap* tbh = (legacy & 16) ? nullptr : &tbh_map;  // +16: force the one-CTA (no multicast) variant
+  legacy &= 15;
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)HD));
   int rc;
   if (legacy != 1) {
@@ -1483,10 +1513,10 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
       for (int j = 0; j < HD; ++j) ep.gam[0][j] = hq[j] * q_premul, ep.gam[1][j] = hk[j];
     }
     if constexpr (HD == 24) {
-      rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, ta, ta, rows, N, H, ep, st) : 1;
+      rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, tbh, ta, rows, N, H, ep, st) : 1;
     } else {
-      if (bn == 128) rc = launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, ta, ta, rows, N, H, ep, st);
-      else if constexpr (HD == 16) rc = launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, tb, ta, ta, rows, N, H, ep, st);
+      if (bn == 128) rc = launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, tbh, ta, rows, N, H, ep, st);
+      else if constexpr (HD == 16) rc = launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, tb, tbh, ta, rows, N, H, ep, st);
       else rc = 1;
     }
     if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear1 kernel does not cover H %d M %d hd %d", H, M, HD);
@@ -1521,17 +1551,20 @@ extern "C" int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16,
   cudaStream_t st = (cudaStream_t)stream;
   const int bn = pick_bn({192, 128, 96, 64}, H, 0, 0);
   if (!bn) return fail(LAMSLIDE_ERR_INVALID, "no linear2 tiling for H %d", H);
-  CUtensorMap ta, tb, th;
+  CUtensorMap ta, tb, tbh_map, th;
   TRY(make_tmap(&ta, act_bf16, rows, H + M, kBlockM));
   TRY(make_tmap(&tb, w2_bf16, H, H + M, bn));
+  TRY(make_tmap(&tbh_map, w2_bf16, H, H + M, bn / 2));
+  const CUtensorMap* tbh = (legacy & 16) ? nullptr : &tbh_map;
+  legacy &= 15;
   TRY(make_tmap_ex(&th, h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   int rc;
   if (!legacy) {
     EpiLinear2Ws::Params ep{bias, gate, H, rows_per_sample, H, rows};
     switch (bn) {
-      case 192: rc = launch_gemm_ws<192, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
-      case 128: rc = launch_gemm_ws<128, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
-      case 64: rc = launch_gemm_ws<64, EpiLinear2Ws>(ta, tb, th, th, rows, H, H + M, ep, st); break;
+      case 192: rc = launch_gemm_ws<192, EpiLinear2Ws>(ta, tb, tbh, th, rows, H, H + M, ep, st); break;
+      case 128: rc = launch_gemm_ws<128, EpiLinear2Ws>(ta, tb, tbh, th, rows, H, H + M, ep, st); break;
+      case 64: rc = launch_gemm_ws<64, EpiLinear2Ws>(ta, tb, tbh, th, rows, H, H + M, ep, st); break;
       default: rc = 1; break;
     }
     if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear2 kernel does not cover H %d M %d", H, M);
@@ -1551,16 +1584,20 @@ extern "C" int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16,
 // the tensor pipe can sustain for a shape, independent of any epilogue.  block_n in {192, 128, 64}.
 extern "C" int lamslide_debug_gemm_mainloop(const void* a_bf16, const void* b_bf16, int32_t rows, int32_t N, int32_t K, int32_t block_n,
                                             void* stream) {
-  if (!a_bf16 || !b_bf16 || N % block_n) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
-  CUtensorMap ta, tb;
+  if (!a_bf16 || !b_bf16 || block_n == 0 || N % block_n) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  const bool one_cta = block_n < 0;  // negative block_n: force the one-CTA (no multicast) variant
+  if (one_cta) block_n = -block_n;
+  CUtensorMap ta, tb, tbh_map;
   TRY(make_tmap(&ta, a_bf16, rows, K, kBlockM));
   TRY(make_tmap(&tb, b_bf16, N, K, block_n));
+  TRY(make_tmap(&tbh_map, b_bf16, N, K, block_n / 2));
+  const CUtensorMap* tbh = one_cta ? nullptr : &tbh_map;
   EpiNullWs::Params ep{0};
   int rc;
   switch (block_n) {
-    case 192: rc = launch_gemm_ws<192, EpiNullWs>(ta, tb, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
-    case 128: rc = launch_gemm_ws<128, EpiNullWs>(ta, tb, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
-    case 64: rc = launch_gemm_ws<64, EpiNullWs>(ta, tb, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    case 192: rc = launch_gemm_ws<192, EpiNullWs>(ta, tb, tbh, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    case 128: rc = launch_gemm_ws<128, EpiNullWs>(ta, tb, tbh, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    case 64: rc = launch_gemm_ws<64, EpiNullWs>(ta, tb, tbh, ta, rows, N, K, ep, (cudaStream_t)stream); break;
     default: return fail(LAMSLIDE_ERR_INVALID, "block_n %d unsupported", block_n);
   }
   if (rc == 1) return fail(LAMSLIDE_ERR_INVALID, "shape does not fit the persistent kernel");

@@ -125,6 +125,7 @@ def _linear1_reference(u, w1, bias, gq, gk, H, M, heads, pos_div, pos_mod, theta
 @pytest.mark.parametrize("rows,H,M,heads,pos_div,pos_mod,legacy", [
     (1000, 384, 1536, 16, 2, 500, 0), (1000, 384, 1536, 16, 2, 500, 1), (20000 + 37, 384, 1536, 16, 1, 2, 0),
     (333, 256, 1024, 16, 8, 20, 0), (4096, 256, 512, 16, 192, 30, 0), (777, 128, 256, 4, 2, 20, 0), (128 * 150, 384, 1536, 16, 2, 1000, 0),
+    (20000 + 37, 384, 1536, 16, 1, 2, 16), (128 * 151, 384, 1536, 16, 2, 1000, 0), (100, 384, 1536, 16, 2, 50, 0), (129, 256, 1024, 16, 8, 20, 0),
 ])
 def test_linear1_fused_epilogue(rows, H, M, heads, pos_div, pos_mod, legacy):
     """linear1 + bias + QK-RMSNorm + RoPE + q pre-scale + erf-GELU (mmdit.py:241-247) vs an fp64 restatement."""
@@ -156,7 +157,8 @@ def test_linear1_fused_epilogue(rows, H, M, heads, pos_div, pos_mod, legacy):
 
 @pytest.mark.parametrize("rows,H,M,rps,legacy", [
     (1000, 384, 1536, 250, 0), (1000, 384, 1536, 250, 1), (20000 + 37, 384, 1536, 2000, 0), (333, 256, 1024, 160, 0),
-    (777, 128, 256, 40, 0), (128 * 150, 384, 1536, 2000, 0),
+    (777, 128, 256, 40, 0), (128 * 150, 384, 1536, 2000, 0), (20000 + 37, 384, 1536, 2000, 16), (128 * 151, 384, 1536, 2000, 0),
+    (100, 384, 1536, 50, 0),
 ])
 def test_linear2_gated_residual(rows, H, M, rps, legacy):
     """h += gate[b] * (act @ w2^T + bias) (mmdit.py:248, latent_si_v31.py:54) vs fp64."""

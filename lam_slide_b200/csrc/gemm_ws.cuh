@@ -64,6 +64,7 @@ struct EpiLinear1Ws {
     int debug;              // profiling aid (lamslide_debug_linear1): 1 = skip the global stores, 2 = skip the epilogue math
   };
   static constexpr int CW = HD;                                  // chunk width (columns)
+  static constexpr int kStageBytes = kWsStageBytesPerWarp;
   static constexpr int CH = HD / 8;                              // 16-byte units per chunk row
   // Global stores must cover whole 32-byte sectors (partial-sector writes ran at ~1.8 TB/s into L2 on B200 and bounded the
   // kernel): when a chunk row (HD * 2 bytes) is not a multiple of 32 bytes, two consecutive chunks are staged side by side
@@ -202,6 +203,7 @@ struct EpiLinear2Ws {
     int H, rows;
   };
   static constexpr int CW = 16;
+  static constexpr int kStageBytes = 2048;  // one 32-row x 64-byte box
   struct Tile {
     const float* gate;
   };
@@ -257,8 +259,8 @@ struct EpiEmbedWs {
     int H, rows;
   };
   static constexpr int CW = 16;
+  static constexpr int kStageBytes = 2560;
   static constexpr int PITCH = 80;  // 16 fp32 = 64 B per staged row, padded to an odd number of 16-byte units
-  static_assert(32 * PITCH <= kWsStageBytesPerWarp, "staging box too large");
   struct Tile {
     uint32_t em_s;  // shared address of this row's mask embedding
   };
@@ -300,6 +302,7 @@ struct EpiNullWs {
     int dummy;
   };
   static constexpr int CW = 16;
+  static constexpr int kStageBytes = 0;
   struct Tile {};
   static __host__ __device__ int smem_floats(const Params&) { return 0; }
   static __device__ void load_consts(const Params&, float*, int, int) {}
@@ -314,13 +317,14 @@ struct EpiNullWs {
 struct WsSmemPlan {
   int a_res_bytes, stage_bytes, ring_bytes, staging_bytes, const_bytes, bar_bytes, total;
 };
-static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_blocks, int stages, int a_resident, int const_floats) {
+static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_blocks, int stages, int a_resident, int const_floats,
+                                                          int stage_bytes_per_warp = kWsStageBytesPerWarp) {
   WsSmemPlan s;
   constexpr int kABytes = kBlockM * kBlockK * 2;
   s.a_res_bytes = a_resident ? num_k_blocks * kABytes : 0;
   s.stage_bytes = (a_resident ? 0 : kABytes) + BN * kBlockK * 2;
   s.ring_bytes = stages * s.stage_bytes;
-  s.staging_bytes = kWsEpiWarps * kWsStageBytesPerWarp;
+  s.staging_bytes = kWsEpiWarps * stage_bytes_per_warp;
   s.const_bytes = (const_floats * 4 + 15) / 16 * 16;
   s.bar_bytes = 320;  // 37 mbarriers + the TMEM base slot
   s.total = s.a_res_bytes + s.ring_bytes + s.staging_bytes + s.const_bytes + s.bar_bytes;  // dynamic smem base is 1024-aligned (checked)
@@ -345,7 +349,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128-byte-swizzled operand tiles need a 1024-byte aligned base
-  const WsSmemPlan plan = ws_smem_plan(BN, num_k_blocks, stages, a_resident, Epi::smem_floats(ep));
+  const WsSmemPlan plan = ws_smem_plan(BN, num_k_blocks, stages, a_resident, Epi::smem_floats(ep), Epi::kStageBytes);
   uint8_t* a_res = smem;
   uint8_t* ring = a_res + plan.a_res_bytes;
   uint8_t* staging = ring + plan.ring_bytes;
@@ -464,7 +468,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int cq = (warp - 2) >> 2;
     WsCtx c;
     c.o0 = &tmap_o0, c.o1 = &tmap_o1;
-    c.stage_s = smem_u32(staging + (warp - 2) * kWsStageBytesPerWarp);
+    c.stage_s = smem_u32(staging + (warp - 2) * Epi::kStageBytes);
     c.smf_s = smem_u32(smf);
     c.lane = lane;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cq * QW;

@@ -230,9 +230,12 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   const int kblocks = K / kBlockK;
   const int cf = Epi::smem_floats(ep);
   int a_res = kblocks <= kWsMaxKBlocksResident ? 1 : 0, stages = 0;
+  static const int max_stages = getenv("LAMSLIDE_WS_STAGES") ? atoi(getenv("LAMSLIDE_WS_STAGES")) : 8;  // profiling aid
+  static const bool no_resident = env_flag("LAMSLIDE_WS_NO_RESIDENT");
+  if (no_resident) a_res = 0;
   for (int pass = 0; pass < 2 && !stages; ++pass) {
-    for (int s = 6; s >= 3; --s)
-      if (ws_smem_plan(BN, kblocks, s, a_res, cf).total <= kSmemMax) {
+    for (int s = std::min(8, max_stages); s >= 2; --s)
+      if (ws_smem_plan(BN, kblocks, s, a_res, cf, Epi::kStageBytes).total <= kSmemMax) {
         stages = s;
         break;
       }
@@ -242,7 +245,7 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     }
   }
   if (!stages) return 1;
-  const WsSmemPlan plan = ws_smem_plan(BN, kblocks, stages, a_res, cf);
+  const WsSmemPlan plan = ws_smem_plan(BN, kblocks, stages, a_res, cf, Epi::kStageBytes);
   const int mblocks = cdiv(rows, kBlockM);
   static const bool no_cluster = env_flag("LAMSLIDE_NO_CLUSTER");
   const bool use_cluster = tb_half && !no_cluster && mblocks >= 2 && num_sms() >= 2;
@@ -1496,6 +1499,7 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
   TRY(make_tmap(&tb, w1, N, H, bn));
   TRY(make_tmap(&tbh_map, w1, N, H, bn / 2));
   const CUtensorMap* tbh = (legacy & 16) ? nullptr : &tbh_map;  // +16: force the one-CTA (no multicast) variant
+  const bool flags32 = (legacy & 32) != 0;
   legacy &= 15;
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)HD));
   int rc;
@@ -1505,7 +1509,7 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
     {  // debug hook: the scales arrive as device pointers; fetch them once per distinct pointer pair (not thread-safe)
       static const float *last_q = nullptr, *last_k = nullptr;
       static float hq[32], hk[32];
-      if (last_q != gq || last_k != gk) {
+      if (!(flags32) || last_q != gq || last_k != gk) {  // +32: the scales are unchanged since the last call (timing loops)
         CUDA_TRY(cudaMemcpy(hq, gq, HD * 4, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(hk, gk, HD * 4, cudaMemcpyDeviceToHost));
         last_q = gq, last_k = gk;

@@ -317,12 +317,13 @@ struct EpiNullWs {
 struct WsSmemPlan {
   int a_res_bytes, stage_bytes, ring_bytes, staging_bytes, const_bytes, bar_bytes, total;
 };
+// cl = 1: one CTA per tile row block; cl = 2: CTA pair (each CTA stages its own A rows and HALF of every weight tile)
 static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_blocks, int stages, int a_resident, int const_floats,
-                                                          int stage_bytes_per_warp = kWsStageBytesPerWarp) {
+                                                          int stage_bytes_per_warp, int cl) {
   WsSmemPlan s;
   constexpr int kABytes = kBlockM * kBlockK * 2;
   s.a_res_bytes = a_resident ? num_k_blocks * kABytes : 0;
-  s.stage_bytes = (a_resident ? 0 : kABytes) + BN * kBlockK * 2;
+  s.stage_bytes = (a_resident ? 0 : kABytes) + (BN / cl) * kBlockK * 2;
   s.ring_bytes = stages * s.stage_bytes;
   s.staging_bytes = kWsEpiWarps * stage_bytes_per_warp;
   s.const_bytes = (const_floats * 4 + 15) / 16 * 16;
@@ -331,25 +332,35 @@ static inline __host__ __device__ WsSmemPlan ws_smem_plan(int BN, int num_k_bloc
   return s;
 }
 
-// CL = cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring m-blocks and walk the n-tiles in
-// lockstep; each loads HALF of every weight tile and multicasts it to both, so the L2 -> SM weight traffic — the resource
-// that bounds the one-CTA version (every SM re-reads all of W per 128 rows: 2.2 GB per 4AA linear1 launch at ~10 TB/s) — halves.
+// CL = 1: every CTA is on its own (tcgen05 cta_group::1, M = 128).
+// CL = 2: CTA pairs (2-CTA clusters, tcgen05 cta_group::2, M = 256): the two CTAs own neighbouring m-blocks and walk the n-tiles
+// together; each stages its own 128 A rows and HALF of every weight tile, the leader's MMA thread issues one 256-row MMA per
+// k-step that reads both halves.  Per SM this halves the weight bytes that cross the L2 -> SM port, land in shared memory and are
+// fetched by the tensor core — the one-CTA version tops out at ~1.1 PFLOP/s (operand-feed bound, not L2- or latency-bound:
+// deeper rings and weight-tile multicast left it unchanged).  Protocol (same barrier offsets in both CTAs):
+//   full[s], a_full[kb]  : on the leader only; both producers' TMA loads complete_tx there (leader arms 2x the bytes)
+//   empty[s], a_empty[kb]: per CTA; the leader's MMA thread commits to both CTAs
+//   tmem_full[acc]       : per CTA; the leader's MMA thread commits to both CTAs
+//   tmem_empty[acc]      : on the leader; the epilogue warps of BOTH CTAs arrive (the peer's through its cluster address)
 template <int BN, int CL, class Epi>
 __global__ void __launch_bounds__(kWsThreads, 1)  // 18 warps are allocated as 20 (granularity 4): <= 96 registers per thread
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o0, const __grid_constant__ CUtensorMap tmap_o1, int num_m_blocks,
                int num_n_tiles, int num_k_blocks, int stages, int a_resident, typename Epi::Params ep) {
+  static_assert(CL == 1 || CL == 2, "cluster size 1 or 2");
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "two accumulator stages of BN columns must fit 512 TMEM columns");
   constexpr int kABytes = kBlockM * kBlockK * 2;
   constexpr uint32_t kTmemCols = tmem_cols_for(2 * BN);
   constexpr int QW = BN / 4;
   constexpr int CW = Epi::CW;
   static_assert(QW % CW == 0, "a warp's column quarter must hold whole epilogue chunks");
+  constexpr int kBRows = BN / CL;  // weight-tile rows staged by this CTA
+  static_assert(kBRows % 8 == 0, "whole 8-row swizzle atoms");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128-byte-swizzled operand tiles need a 1024-byte aligned base
-  const WsSmemPlan plan = ws_smem_plan(BN, num_k_blocks, stages, a_resident, Epi::smem_floats(ep), Epi::kStageBytes);
+  const WsSmemPlan plan = ws_smem_plan(BN, num_k_blocks, stages, a_resident, Epi::smem_floats(ep), Epi::kStageBytes, CL);
   uint8_t* a_res = smem;
   uint8_t* ring = a_res + plan.a_res_bytes;
   uint8_t* staging = ring + plan.ring_bytes;
@@ -366,18 +377,16 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
   const int m_first = (blockIdx.x / CL) * CL;          // first m-block of this CTA's cluster
   const int m_step = (gridDim.x / CL) * CL;            // m-blocks per sweep of the whole grid
-  constexpr uint16_t kClusterMask = (1u << CL) - 1;
-  constexpr int kBSlice = BN / CL;                     // weight-tile rows this CTA fetches (and multicasts)
-  static_assert(BN % (8 * CL) == 0, "a multicast slice must be whole 8-row swizzle atoms");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);  // released by the MMA warp of every CTA of the cluster
+      mbar_init(&empty_bar[s], 1);
     }
     for (int k = 0; k < kWsMaxKBlocksResident; ++k) {
       mbar_init(&a_full[k], 1);
@@ -385,15 +394,18 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kWsEpiWarps);
+      mbar_init(&tmem_empty[s], CL * kWsEpiWarps);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (CL == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    else tmem_alloc_pair<kTmemCols>(tmem_slot);
+  }
   if (warp >= 2) Epi::load_consts(ep, smf, threadIdx.x - 64, kWsThreads - 64);
   tcgen05_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast traffic / remote arrive
+  if constexpr (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before any TMA completion / remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -405,24 +417,35 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++mb_iter) {
         const int mb = mbase + cta_rank;  // may be past the end in the last sweep: the TMA zero-fills, nothing is stored
         for (int nt = 0; nt < num_n_tiles; ++nt) {
-          const int n0 = Epi::template tile_n0<BN>(ep, nt);
+          const int n0 = Epi::template tile_n0<BN>(ep, nt) + cta_rank * kBRows;
           for (int kb = 0; kb < num_k_blocks; ++kb) {
             if (a_resident && nt == 0) {  // refill A k-block kb as soon as the previous m-block's last tile has consumed it
               mbar_wait(&a_empty[kb], (mb_iter & 1) ^ 1);
-              mbar_arrive_expect_tx(&a_full[kb], kABytes);
-              tma_load_2d(&tmap_a, &a_full[kb], a_res + kb * kABytes, kb * kBlockK, mb * kBlockM);
+              if constexpr (CL == 1) {
+                mbar_arrive_expect_tx(&a_full[kb], kABytes);
+                tma_load_2d(&tmap_a, &a_full[kb], a_res + kb * kABytes, kb * kBlockK, mb * kBlockM);
+              } else {
+                if (leader) mbar_arrive_expect_tx(&a_full[kb], 2 * kABytes);
+                tma_load_2d_pair(&tmap_a, mapa_u32(smem_u32(&a_full[kb]), 0), a_res + kb * kABytes, kb * kBlockK, mb * kBlockM);
+              }
             }
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* dst = ring + s * plan.stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[s], plan.stage_bytes);
-            if (!a_resident) {
-              tma_load_2d(&tmap_a, &full_bar[s], dst, kb * kBlockK, mb * kBlockM);
-              dst += kABytes;
-            }
             if constexpr (CL == 1) {
+              mbar_arrive_expect_tx(&full_bar[s], plan.stage_bytes);
+              if (!a_resident) {
+                tma_load_2d(&tmap_a, &full_bar[s], dst, kb * kBlockK, mb * kBlockM);
+                dst += kABytes;
+              }
               tma_load_2d(&tmap_b, &full_bar[s], dst, kb * kBlockK, n0);
             } else {
-              tma_load_2d_mc(&tmap_b, &full_bar[s], dst + cta_rank * kBSlice * (kBlockK * 2), kb * kBlockK, n0 + cta_rank * kBSlice, kClusterMask);
+              if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * plan.stage_bytes);
+              const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+              if (!a_resident) {
+                tma_load_2d_pair(&tmap_a, bar, dst, kb * kBlockK, mb * kBlockM);
+                dst += kABytes;
+              }
+              tma_load_2d_pair(&tmap_b, bar, dst, kb * kBlockK, n0);
             }
             if (++s == stages) s = 0, ph ^= 1;
           }
@@ -430,15 +453,15 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    // ===== MMA issuer (one thread; in a CTA pair only the leader's) =====
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CL, BN);
       int s = 0;
       uint32_t ph = 0, mb_iter = 0, tile = 0;
       for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++mb_iter) {
         for (int nt = 0; nt < num_n_tiles; ++nt, ++tile) {
           const uint32_t acc = tile & 1, use = tile >> 1;
-          mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator stage
+          mbar_wait(&tmem_empty[acc], (use & 1) ^ 1);  // the epilogue (of both CTAs) has drained this accumulator stage
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -451,14 +474,21 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t a_desc = umma_desc_sw128(a_addr);
             const uint64_t b_desc = umma_desc_sw128(b_addr);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            if constexpr (CL == 1) umma_commit(&empty_bar[s]);
-            else umma_commit_mc(&empty_bar[s], kClusterMask);
-            if (a_resident && nt == num_n_tiles - 1) umma_commit(&a_empty[kb]);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              if constexpr (CL == 1) umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              else umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
+            if constexpr (CL == 1) {
+              umma_commit(&empty_bar[s]);
+              if (a_resident && nt == num_n_tiles - 1) umma_commit(&a_empty[kb]);
+            } else {
+              umma_commit_pair(&empty_bar[s]);
+              if (a_resident && nt == num_n_tiles - 1) umma_commit_pair(&a_empty[kb]);
+            }
             if (++s == stages) s = 0, ph ^= 1;
           }
-          umma_commit(&tmem_full[acc]);
+          if constexpr (CL == 1) umma_commit(&tmem_full[acc]);
+          else umma_commit_pair(&tmem_full[acc]);
         }
       }
     }
@@ -472,6 +502,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     c.smf_s = smem_u32(smf);
     c.lane = lane;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cq * QW;
+    uint32_t tmem_empty_addr[2];  // where this warp reports "accumulator drained": the leader's barriers
+    tmem_empty_addr[0] = CL > 1 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
+    tmem_empty_addr[1] = CL > 1 ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : smem_u32(&tmem_empty[1]);
     uint32_t tile = 0;
     for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step) {
       const int mb = mbase + cta_rank;
@@ -492,7 +525,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (ck == QW / CW - 1) {  // last chunk is in registers: hand the accumulator stage back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+              if constexpr (CL == 1) mbar_arrive(&tmem_empty[acc]);
+              else mbar_arrive_cluster(tmem_empty_addr[acc]);
+            }
           }
           Epi::chunk(ep, c, ts, v, n0w + ck * CW, ck);
         }
@@ -503,10 +539,11 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves (or frees TMEM) while the pair still works
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (CL == 1) tmem_dealloc<kTmemCols>(tmem_base);
+    else tmem_dealloc_pair<kTmemCols>(tmem_base);
   }
 }
 

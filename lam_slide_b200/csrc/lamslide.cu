@@ -229,13 +229,17 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   constexpr int kSmemMax = 232448;  // 227 KB of dynamic shared memory per CTA on sm_100
   const int kblocks = K / kBlockK;
   const int cf = Epi::smem_floats(ep);
+  const int mblocks = cdiv(rows, kBlockM);
+  static const bool no_cluster = env_flag("LAMSLIDE_NO_CLUSTER");
+  const bool use_pair = tb_half && !no_cluster && mblocks >= 2 && num_sms() >= 2 && BN % 16 == 0;
+  const int cl = use_pair ? 2 : 1;
   int a_res = kblocks <= kWsMaxKBlocksResident ? 1 : 0, stages = 0;
   static const int max_stages = getenv("LAMSLIDE_WS_STAGES") ? atoi(getenv("LAMSLIDE_WS_STAGES")) : 8;  // profiling aid
   static const bool no_resident = env_flag("LAMSLIDE_WS_NO_RESIDENT");
   if (no_resident) a_res = 0;
   for (int pass = 0; pass < 2 && !stages; ++pass) {
     for (int s = std::min(8, max_stages); s >= 2; --s)
-      if (ws_smem_plan(BN, kblocks, s, a_res, cf, Epi::kStageBytes).total <= kSmemMax) {
+      if (ws_smem_plan(BN, kblocks, s, a_res, cf, Epi::kStageBytes, cl).total <= kSmemMax) {
         stages = s;
         break;
       }
@@ -245,16 +249,13 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     }
   }
   if (!stages) return 1;
-  const WsSmemPlan plan = ws_smem_plan(BN, kblocks, stages, a_res, cf, Epi::kStageBytes);
-  const int mblocks = cdiv(rows, kBlockM);
-  static const bool no_cluster = env_flag("LAMSLIDE_NO_CLUSTER");
-  const bool use_cluster = tb_half && !no_cluster && mblocks >= 2 && num_sms() >= 2;
+  const WsSmemPlan plan = ws_smem_plan(BN, kblocks, stages, a_res, cf, Epi::kStageBytes, cl);
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kWsThreads);
   cfg.dynamicSmemBytes = plan.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  if (use_cluster) {
+  if (use_pair) {
     auto kern = gemm_ws_kernel<BN, 2, Epi>;
     static bool configured = false;
     if (!configured) {

@@ -262,7 +262,8 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
       configured = true;
     }
-    const int grid = std::min(num_sms() / 2 * 2, cdiv(mblocks, 2) * 2);
+    static const int grid_cap = getenv("LAMSLIDE_WS_GRID") ? atoi(getenv("LAMSLIDE_WS_GRID")) : 1 << 30;  // profiling aid
+    const int grid = std::min(std::min(num_sms(), grid_cap) / 2 * 2, cdiv(mblocks, 2) * 2);
     cfg.gridDim = dim3(grid);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
@@ -275,7 +276,8 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
       configured = true;
     }
-    cfg.gridDim = dim3(std::min(num_sms(), mblocks));
+    static const int grid_cap = getenv("LAMSLIDE_WS_GRID") ? atoi(getenv("LAMSLIDE_WS_GRID")) : 1 << 30;  // profiling aid
+    cfg.gridDim = dim3(std::min(std::min(num_sms(), grid_cap), mblocks));
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, o0, o0, mblocks, N / BN, kblocks, stages, a_res, ep));
   }
   LAUNCH_CHECK();

@@ -409,18 +409,22 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The two control warps run their loops with ALL 32 lanes (warp-uniform control flow and addresses, so descriptors and
+  // barrier addresses live in uniform registers) and elect one lane only around the TMA / tcgen05 instructions themselves.
+  // (Putting the whole loop under `if (lane == 0)` made the compiler wrap every UTCHMMA / UTMALDG in a lane-serialising
+  // R2UR loop: ~130 instructions per k-block on the MMA thread, which capped the tensor pipe at ~50 %.)
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0, mb_iter = 0;
-      for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++mb_iter) {
-        const int mb = mbase + cta_rank;  // may be past the end in the last sweep: the TMA zero-fills, nothing is stored
-        for (int nt = 0; nt < num_n_tiles; ++nt) {
-          const int n0 = Epi::template tile_n0<BN>(ep, nt) + cta_rank * kBRows;
-          for (int kb = 0; kb < num_k_blocks; ++kb) {
-            if (a_resident && nt == 0) {  // refill A k-block kb as soon as the previous m-block's last tile has consumed it
-              mbar_wait(&a_empty[kb], (mb_iter & 1) ^ 1);
+    int s = 0;
+    uint32_t ph = 0, mb_iter = 0;
+    for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++mb_iter) {
+      const int mb = mbase + cta_rank;  // may be past the end in the last sweep: the TMA zero-fills, nothing is stored
+      for (int nt = 0; nt < num_n_tiles; ++nt) {
+        const int n0 = Epi::template tile_n0<BN>(ep, nt) + cta_rank * kBRows;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          if (a_resident && nt == 0) {  // refill A k-block kb as soon as the previous m-block's last tile has consumed it
+            mbar_wait(&a_empty[kb], (mb_iter & 1) ^ 1);
+            if (elect_one()) {
               if constexpr (CL == 1) {
                 mbar_arrive_expect_tx(&a_full[kb], kABytes);
                 tma_load_2d(&tmap_a, &a_full[kb], a_res + kb * kABytes, kb * kBlockK, mb * kBlockM);
@@ -429,7 +433,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tma_load_2d_pair(&tmap_a, mapa_u32(smem_u32(&a_full[kb]), 0), a_res + kb * kABytes, kb * kBlockK, mb * kBlockM);
               }
             }
-            mbar_wait(&empty_bar[s], ph ^ 1);
+            __syncwarp();
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (elect_one()) {
             uint8_t* dst = ring + s * plan.stage_bytes;
             if constexpr (CL == 1) {
               mbar_arrive_expect_tx(&full_bar[s], plan.stage_bytes);
@@ -447,14 +454,15 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
               tma_load_2d_pair(&tmap_b, bar, dst, kb * kBlockK, n0);
             }
-            if (++s == stages) s = 0, ph ^= 1;
           }
+          __syncwarp();
+          if (++s == stages) s = 0, ph ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread; in a CTA pair only the leader's) =====
-    if (lane == 0 && leader) {
+    // ===== MMA issuer (in a CTA pair only the leader's warp) =====
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CL, BN);
       int s = 0;
       uint32_t ph = 0, mb_iter = 0, tile = 0;
@@ -473,22 +481,27 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t b_addr = a_resident ? st_addr : st_addr + kABytes;
             const uint64_t a_desc = umma_desc_sw128(a_addr);
             const uint64_t b_desc = umma_desc_sw128(b_addr);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              if constexpr (CL == 1) umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-              else umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                if constexpr (CL == 1) umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                else umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              }
+              if constexpr (CL == 1) {
+                umma_commit(&empty_bar[s]);
+                if (a_resident && nt == num_n_tiles - 1) umma_commit(&a_empty[kb]);
+              } else {
+                umma_commit_pair(&empty_bar[s]);
+                if (a_resident && nt == num_n_tiles - 1) umma_commit_pair(&a_empty[kb]);
+              }
+              if (kb == num_k_blocks - 1) {
+                if constexpr (CL == 1) umma_commit(&tmem_full[acc]);
+                else umma_commit_pair(&tmem_full[acc]);
+              }
             }
-            if constexpr (CL == 1) {
-              umma_commit(&empty_bar[s]);
-              if (a_resident && nt == num_n_tiles - 1) umma_commit(&a_empty[kb]);
-            } else {
-              umma_commit_pair(&empty_bar[s]);
-              if (a_resident && nt == num_n_tiles - 1) umma_commit_pair(&a_empty[kb]);
-            }
+            __syncwarp();
             if (++s == stages) s = 0, ph ^= 1;
           }
-          if constexpr (CL == 1) umma_commit(&tmem_full[acc]);
-          else umma_commit_pair(&tmem_full[acc]);
         }
       }
     }

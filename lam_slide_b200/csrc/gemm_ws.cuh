@@ -61,7 +61,7 @@ struct EpiLinear1Ws {
     __nv_bfloat16* act;     // [rows, H + M]
     int H, M, rows;
     int pos_div, pos_mod;   // rope position of a row = (row / pos_div) % pos_mod
-    int debug;              // profiling aid (lamslide_debug_linear1): 1 = skip the global stores, 2 = skip the epilogue math
+    int debug;              // profiling aid (lamslide_debug_linear1): bit 0 = skip the global stores, bit 1 = skip the epilogue math
   };
   static constexpr int CW = HD;                                  // chunk width (columns)
   static constexpr int kStageBytes = kWsStageBytesPerWarp;
@@ -73,6 +73,10 @@ struct EpiLinear1Ws {
   static constexpr int UNITS = kPair ? 2 * CH : CH;             // 16-byte units per staged row
   static constexpr int PITCH = (kPair ? UNITS : (UNITS % 2 == 0 ? UNITS + 1 : UNITS)) * 16;  // bytes (pairs: dense, 2-way conflicts on the writes only)
   static_assert(32 * PITCH <= kWsStageBytesPerWarp, "staging box too large");
+  // Paired boxes are dense 32 x (2 HD) bf16 tiles: they go out as ONE TMA tensor store per warp and tile half, so the epilogue
+  // warps never wait on the LSU store path (with st.global the stores and the math did not overlap: +53 us and +56 us on a
+  // 187 us floor gave 295 us).  o0 / o1 = store maps of qkv / act with a {2 HD, 32} box, no swizzle.
+  static constexpr bool kTmaStore = kPair;
   struct Tile {
     int kind;  // 0 q, 1 k, 2 v, 3 mlp
     const float4 *cs, *sn;  // this row's RoPE table entries (L1-resident: re-read per head rather than held in 24 registers)
@@ -102,19 +106,31 @@ struct EpiLinear1Ws {
   // 474 us per 4AA launch against 391 us staged; small-box TMA stores were no better.)
   static __device__ __forceinline__ void emit(const Params& p, const WsCtx& c, const uint32_t* w, __nv_bfloat16* out, int ld, int col, int ck) {
     const int half = kPair ? (ck & 1) : 0;
-    if (half == 0) __syncwarp();  // the previous box has been read out by every lane
+    if (half == 0) {
+      if (kTmaStore && c.lane == 0) bulk_wait_read<0>();  // the TMA unit has read the previous box out of shared memory
+      __syncwarp();                                       // ... / the previous box has been read out by every lane
+    }
 #pragma unroll
     for (int ch = 0; ch < CH; ++ch)
       st_shared_v4(c.stage_s + c.lane * PITCH + (half * CH + ch) * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
     if (kPair && half == 0) return;
-    __syncwarp();
     const int col0 = col - half * HD;  // first column of the staged row
+    if constexpr (kTmaStore) {
+      fence_proxy_async();  // generic-proxy writes of every lane -> visible to the async proxy (TMA)
+      __syncwarp();
+      if (c.lane == 0 && !(p.debug & 1)) {
+        tma_store_2d_s(out == p.qkv ? c.o0 : c.o1, c.stage_s, col0, c.row0);
+        bulk_commit();
+      }
+      return;
+    }
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < UNITS; ++k) {
       const int id = c.lane + 32 * k;
       const int r = id / UNITS, ch = id % UNITS;
       const uint4 val = ld_shared_v4(c.stage_s + r * PITCH + ch * 16);
-      if (c.row0 + r < p.rows && p.debug != 1) *reinterpret_cast<uint4*>(out + (size_t)(c.row0 + r) * ld + col0 + ch * 8) = val;
+      if (c.row0 + r < p.rows && !(p.debug & 1)) *reinterpret_cast<uint4*>(out + (size_t)(c.row0 + r) * ld + col0 + ch * 8) = val;
     }
   }
   // v: HD accumulators of this thread's row, columns col .. col + HD
@@ -122,7 +138,7 @@ struct EpiLinear1Ws {
     const int H3 = 3 * p.H;
     const uint32_t bias_s = c.smf_s + col * 4;
     uint32_t w[HD / 2];
-    if (p.debug == 2) {  // raw accumulators, no math
+    if (p.debug & 2) {  // raw accumulators, no math
 #pragma unroll
       for (int j = 0; j < HD / 2; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
       if (t.kind == 3) emit(p, c, w, p.act, p.H + p.M, p.H + (col - H3), ck);
@@ -188,7 +204,9 @@ struct EpiLinear1Ws {
     }
     emit(p, c, w, p.qkv, H3, col, ck);
   }
-  static __device__ __forceinline__ void finish(const WsCtx&) {}
+  static __device__ __forceinline__ void finish(const WsCtx& c) {
+    if (kTmaStore && c.lane == 0) bulk_wait_read<0>();  // staged boxes must be read out before the CTA's shared memory goes away
+  }
 };
 
 // ------------------------------------------------------------------------------------------------ linear2 epilogue

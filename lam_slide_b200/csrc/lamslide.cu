@@ -224,8 +224,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int rows, i
 // shared-memory plan; the caller then uses the one-tile-per-CTA kernel above.  tb_half: the weight map with a box of BN / 2
 // rows — when given (and the grid is large enough) the kernel runs as 2-CTA clusters that multicast the weight tiles.
 template <int BN, class Epi>
-static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_half, const CUtensorMap& o0, int rows,
-                          int N, int K, const typename Epi::Params& ep, cudaStream_t st) {
+static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tb_half, const CUtensorMap& o0,
+                          const CUtensorMap& o1, int rows, int N, int K, const typename Epi::Params& ep, cudaStream_t st) {
   constexpr int kSmemMax = 232448;  // 227 KB of dynamic shared memory per CTA on sm_100
   const int kblocks = K / kBlockK;
   const int cf = Epi::smem_floats(ep);
@@ -268,7 +268,7 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, *tb_half, o0, o0, mblocks, N / BN, kblocks, stages, a_res, ep));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, *tb_half, o0, o1, mblocks, N / BN, kblocks, stages, a_res, ep));
   } else {
     auto kern = gemm_ws_kernel<BN, 1, Epi>;
     static bool configured = false;
@@ -278,7 +278,7 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     }
     static const int grid_cap = getenv("LAMSLIDE_WS_GRID") ? atoi(getenv("LAMSLIDE_WS_GRID")) : 1 << 30;  // profiling aid
     cfg.gridDim = dim3(std::min(std::min(num_sms(), grid_cap), mblocks));
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, o0, o0, mblocks, N / BN, kblocks, stages, a_res, ep));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, o0, o1, mblocks, N / BN, kblocks, stages, a_res, ep));
   }
   LAUNCH_CHECK();
   return 0;
@@ -565,15 +565,15 @@ static int launch_linear2(const lamslide_backbone* bb, const CUtensorMap& ta, co
 
 // warp-specialised variants; return 1 when the tiling is not covered (caller falls back to the kernels above)
 template <int HD>
-static int launch_linear1_ws(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, int rows,
-                             const typename EpiLinear1Ws<HD>::Params& ep, cudaStream_t st) {
+static int launch_linear1_ws(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, const CUtensorMap& qkv_st,
+                             const CUtensorMap& act_st, int rows, const typename EpiLinear1Ws<HD>::Params& ep, cudaStream_t st) {
   const int N = 3 * bb->H + bb->M, K = bb->H;
   if constexpr (HD == 24) {
-    if (bb->bn1 == 192) return launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, bw.tm_w1, &bw.tm_w1_h, ta, rows, N, K, ep, st);
+    if (bb->bn1 == 192) return launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, bw.tm_w1, &bw.tm_w1_h, qkv_st, act_st, rows, N, K, ep, st);
   } else {
-    if (bb->bn1 == 128) return launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, bw.tm_w1, &bw.tm_w1_h, ta, rows, N, K, ep, st);
+    if (bb->bn1 == 128) return launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, bw.tm_w1, &bw.tm_w1_h, qkv_st, act_st, rows, N, K, ep, st);
     if constexpr (HD == 16) {
-      if (bb->bn1 == 64) return launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, bw.tm_w1, &bw.tm_w1_h, ta, rows, N, K, ep, st);
+      if (bb->bn1 == 64) return launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, bw.tm_w1, &bw.tm_w1_h, qkv_st, act_st, rows, N, K, ep, st);
     }
   }
   return 1;
@@ -583,9 +583,9 @@ static int launch_linear2_ws(const lamslide_backbone* bb, const CUtensorMap& ta,
                              int rows, const EpiLinear2Ws::Params& ep, cudaStream_t st) {
   const int N = bb->H, K = bb->H + bb->M;
   switch (bb->bn2) {
-    case 192: return launch_gemm_ws<192, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, rows, N, K, ep, st);
-    case 128: return launch_gemm_ws<128, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, rows, N, K, ep, st);
-    case 64: return launch_gemm_ws<64, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, rows, N, K, ep, st);
+    case 192: return launch_gemm_ws<192, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, h_red, rows, N, K, ep, st);
+    case 128: return launch_gemm_ws<128, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, h_red, rows, N, K, ep, st);
+    case 64: return launch_gemm_ws<64, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, h_red, rows, N, K, ep, st);
     default: return 1;
   }
 }
@@ -684,6 +684,7 @@ struct ForwardCtx {
   BackboneWorkspace ws;
   CUtensorMap tm_u, tm_act, tm_u3;
   CUtensorMap tm_h_red;                         // f32 reduce-add of the linear2 epilogue (16-column x 32-row boxes)
+  CUtensorMap tm_qkv_st, tm_act_st;             // linear1 epilogue: dense {2 hd, 32} bf16 boxes (hd = 24: paired heads, 96-byte rows)
   CUtensorMap tm_emb_a;                         // [n, 6D] split input-embedding operand (lives in the act buffer)
 };
 
@@ -699,6 +700,9 @@ static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, 
   TRY(make_tmap(&fc.tm_u, fc.ws.u, (uint64_t)n, bb->H, kBlockM));
   TRY(make_tmap(&fc.tm_act, fc.ws.act, (uint64_t)n, bb->H + bb->M, kBlockM));
   TRY(make_tmap(&fc.tm_u3, fc.ws.qkv, (uint64_t)n, 3 * bb->H, kBlockM));  // head input [hi | lo | hi] reuses the qkv buffer
+  TRY(make_tmap_ex(&fc.tm_qkv_st, fc.ws.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, 3 * bb->H, 2 * bb->hd, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  TRY(make_tmap_ex(&fc.tm_act_st, fc.ws.act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, bb->H + bb->M, 2 * bb->hd, 32,
+                   CU_TENSOR_MAP_SWIZZLE_NONE));
   if (bb->w_emb) TRY(make_tmap(&fc.tm_emb_a, fc.ws.act, (uint64_t)n, 6 * bb->D, kBlockM));
   TRY(make_tmap_ex(&fc.tm_h_red, fc.ws.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)n, bb->H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   const int half = bb->hd / 2;
@@ -728,9 +732,9 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
       LAUNCH_CHECK();
       EpiEmbedWs::Params ee{bb->b_in, bb->emask, (const long long*)mask, w.h, H, n};
       switch (bb->bn_emb) {
-        case 192: re = launch_gemm_ws<192, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
-        case 128: re = launch_gemm_ws<128, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
-        case 64: re = launch_gemm_ws<64, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        case 192: re = launch_gemm_ws<192, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        case 128: re = launch_gemm_ws<128, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
+        case 64: re = launch_gemm_ws<64, EpiEmbedWs>(fc.tm_emb_a, bb->tm_wemb, &bb->tm_wemb_h, fc.tm_emb_a, fc.tm_emb_a, n, H, 6 * D, ee, st); break;
         default: break;
       }
       if (re < 0) return re;
@@ -791,7 +795,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   if (!legacy_gemm) {                                                                                                    \
     typename EpiLinear1Ws<HD_>::Params epw{bw.b1, {}, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, 0};                                \
     for (int j = 0; j < HD_; ++j) epw.gam[0][j] = bw.gq_h[j] * q_premul, epw.gam[1][j] = bw.gk_h[j];                                         \
-    r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, n, epw, st);                                \
+    r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_qkv_st, fc.tm_act_st, n, epw, st);                                \
     if (r1 < 0) return r1;                                                                                               \
   }                                                                                                                      \
   if (r1 == 1) {                                                                                                         \
@@ -1497,10 +1501,12 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
     rope_table_kernel<<<cdiv(pos_mod * half, 256), 256, 0, st>>>(cs, sn, pos_mod, half, (double)theta);
     have_pos = pos_mod, have_half = half, have_theta = theta;
   }
-  CUtensorMap ta, tb, tbh_map;
+  CUtensorMap ta, tb, tbh_map, tq, tact;
   TRY(make_tmap(&ta, u, rows, H, kBlockM));
   TRY(make_tmap(&tb, w1, N, H, bn));
   TRY(make_tmap(&tbh_map, w1, N, H, bn / 2));
+  TRY(make_tmap_ex(&tq, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, 3 * H, 2 * HD, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  TRY(make_tmap_ex(&tact, act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, H + M, 2 * HD, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
   const CUtensorMap* tbh = (legacy & 16) ? nullptr : &tbh_map;  // +16: force the one-CTA (no multicast) variant
   const bool flags32 = (legacy & 32) != 0;
   legacy &= 15;
@@ -1508,7 +1514,7 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
   int rc;
   if (legacy != 1) {
     typename EpiLinear1Ws<HD>::Params ep{bias, {}, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod,
-                                         legacy == 2 ? 1 : legacy == 3 ? 2 : 0};
+                                         legacy == 2 ? 1 : legacy == 3 ? 2 : legacy == 4 ? 3 : 0};
     {  // debug hook: the scales arrive as device pointers; fetch them once per distinct pointer pair (not thread-safe)
       static const float *last_q = nullptr, *last_k = nullptr;
       static float hq[32], hk[32];
@@ -1520,10 +1526,10 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
       for (int j = 0; j < HD; ++j) ep.gam[0][j] = hq[j] * q_premul, ep.gam[1][j] = hk[j];
     }
     if constexpr (HD == 24) {
-      rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, tbh, ta, rows, N, H, ep, st) : 1;
+      rc = bn == 192 ? launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, tb, tbh, tq, tact, rows, N, H, ep, st) : 1;
     } else {
-      if (bn == 128) rc = launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, tbh, ta, rows, N, H, ep, st);
-      else if constexpr (HD == 16) rc = launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, tb, tbh, ta, rows, N, H, ep, st);
+      if (bn == 128) rc = launch_gemm_ws<128, EpiLinear1Ws<HD>>(ta, tb, tbh, tq, tact, rows, N, H, ep, st);
+      else if constexpr (HD == 16) rc = launch_gemm_ws<64, EpiLinear1Ws<16>>(ta, tb, tbh, tq, tact, rows, N, H, ep, st);
       else rc = 1;
     }
     if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear1 kernel does not cover H %d M %d hd %d", H, M, HD);
@@ -1569,9 +1575,9 @@ extern "C" int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16,
   if (!legacy) {
     EpiLinear2Ws::Params ep{bias, gate, H, rows_per_sample, H, rows};
     switch (bn) {
-      case 192: rc = launch_gemm_ws<192, EpiLinear2Ws>(ta, tb, tbh, th, rows, H, H + M, ep, st); break;
-      case 128: rc = launch_gemm_ws<128, EpiLinear2Ws>(ta, tb, tbh, th, rows, H, H + M, ep, st); break;
-      case 64: rc = launch_gemm_ws<64, EpiLinear2Ws>(ta, tb, tbh, th, rows, H, H + M, ep, st); break;
+      case 192: rc = launch_gemm_ws<192, EpiLinear2Ws>(ta, tb, tbh, th, th, rows, H, H + M, ep, st); break;
+      case 128: rc = launch_gemm_ws<128, EpiLinear2Ws>(ta, tb, tbh, th, th, rows, H, H + M, ep, st); break;
+      case 64: rc = launch_gemm_ws<64, EpiLinear2Ws>(ta, tb, tbh, th, th, rows, H, H + M, ep, st); break;
       default: rc = 1; break;
     }
     if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "persistent linear2 kernel does not cover H %d M %d", H, M);
@@ -1602,9 +1608,9 @@ extern "C" int lamslide_debug_gemm_mainloop(const void* a_bf16, const void* b_bf
   EpiNullWs::Params ep{0};
   int rc;
   switch (block_n) {
-    case 192: rc = launch_gemm_ws<192, EpiNullWs>(ta, tb, tbh, ta, rows, N, K, ep, (cudaStream_t)stream); break;
-    case 128: rc = launch_gemm_ws<128, EpiNullWs>(ta, tb, tbh, ta, rows, N, K, ep, (cudaStream_t)stream); break;
-    case 64: rc = launch_gemm_ws<64, EpiNullWs>(ta, tb, tbh, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    case 192: rc = launch_gemm_ws<192, EpiNullWs>(ta, tb, tbh, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    case 128: rc = launch_gemm_ws<128, EpiNullWs>(ta, tb, tbh, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
+    case 64: rc = launch_gemm_ws<64, EpiNullWs>(ta, tb, tbh, ta, ta, rows, N, K, ep, (cudaStream_t)stream); break;
     default: return fail(LAMSLIDE_ERR_INVALID, "block_n %d unsupported", block_n);
   }
   if (rc == 1) return fail(LAMSLIDE_ERR_INVALID, "shape does not fit the persistent kernel");

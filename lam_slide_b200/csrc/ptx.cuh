@@ -275,6 +275,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* 
                : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d_s(const void* tmap, uint32_t smem_addr, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_addr), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d_s(const void* tmap, uint32_t smem_addr, int32_t c0, int32_t c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                :

@@ -1,0 +1,288 @@
+// tcgen05 / TMEM attention for long sequences (temporal axis of the second stage, S = T up to 1024 keys per tile pass;
+// mmdit.py:42-55: softmax(q k^T / sqrt(hd)) v, no mask).  q and k arrive RMS-normalised + rotated and q pre-multiplied by
+// hd^-0.5 * log2(e) from the linear1 epilogue, so the logits are bounded (see attn.cuh: attn_seq_kernel) and softmax is evaluated as
+// exp2(s) / sum exp2(s) without a running maximum.
+//
+// One CTA per (sequence, head), one CTA per SM.  All of K and V of the (sequence, head) live in shared memory in the canonical
+// NO-SWIZZLE UMMA layout (8 x 16-byte "core matrices"): element (key, d) at
+//     (key / 8) * GROUP + (d / 8) * 128 + (key % 8) * 16 + (d % 8) * 2          bytes,
+// which serves BOTH MMAs from one image each: K as the K-major B operand of S = Q K^T (N = keys, K = d), V as the MN-major
+// B operand of O = P V (N = d, K = keys).  d is padded to 32 for K and Q (zero chunk), V keeps hd / 8 chunks per key group.
+//
+// Warp roles (384 threads):
+//   warp 0       : TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues)
+//   warp 1       : Q loader (cp.async of two 128-row query tiles into the same core-matrix layout, double buffered)
+//   warps 2, 3   : idle after the K / V load
+//   warps 4..11  : two softmax warpgroups (one query tile each): thread = query row.  Per 128-key chunk: tcgen05.ld S (fp32) ->
+//                  exp2 -> row sum -> bf16 -> tcgen05.st P over the same TMEM columns (P aliases S) -> mbarrier.
+// TMEM (512 columns): S0 | S1 (128 fp32 columns each, P in the first 64), O0 | O1 (32 columns each).
+// Tensor work per (tile, chunk): S = Q K^T as 2 MMAs (M 128, N 128, K 16), O += P V as 8 MMAs (M 128, N 32, K 16, A from TMEM):
+// ~256 tensor cycles against 1024 MUFU cycles for the 16 k exponentials, so the two warpgroups keep the MUFU busy while the
+// other tile's MMAs run.
+#pragma once
+#include "attn.cuh"
+
+namespace lam {
+
+constexpr int kAtcThreads = 384;
+constexpr int kAtcChunk = 128;  // keys per S tile
+
+__host__ __device__ inline int atc_s128(int S) { return (S + 127) & ~127; }
+template <int HD>
+struct AtcCfg {
+  static constexpr int VG = (HD / 8) * 128;  // bytes per 8-key group of the V image
+  static __host__ __device__ size_t k_bytes(int S) { return (size_t)atc_s128(S) * 64; }
+  static __host__ __device__ size_t v_bytes(int S) { return (size_t)atc_s128(S) / 8 * VG + 512; }  // + tail pad (N = 32 reads 4 chunks)
+  static __host__ __device__ size_t q_bytes() { return 4 * 8192; }
+  static __host__ __device__ size_t smem_bytes(int S) { return k_bytes(S) + v_bytes(S) + q_bytes() + 256; }
+};
+
+// no-swizzle UMMA shared-memory descriptor: start address, leading-dimension byte offset, stride-dimension byte offset
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+               "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// variant bits (debug aid, lamslide_debug_attention mode 3 + 4 * variant): 1 = swap LBO / SBO of the Q / K descriptors,
+// 2 = swap LBO / SBO of the V descriptor.  0 is the layout derived from the canonical UMMA layouts.
+template <int HD, int POLY>
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, SeqMap sm, int heads, int variant) {
+  using Cfg = AtcCfg<HD>;
+  constexpr int CH = HD / 8;
+  constexpr int VG = Cfg::VG;
+  extern __shared__ __align__(1024) uint8_t atc_smem[];
+  const int S = sm.S;
+  const int S128 = atc_s128(S);
+  uint8_t* k_img = atc_smem;
+  uint8_t* v_img = k_img + Cfg::k_bytes(S);
+  uint8_t* q_img = v_img + Cfg::v_bytes(S);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(q_img + Cfg::q_bytes());
+  uint64_t* s_full = bars;        // [2] MMA -> softmax warpgroup
+  uint64_t* p_full = bars + 2;    // [2] softmax warpgroup -> MMA
+  uint64_t* o_done = bars + 4;    // [2] MMA -> softmax warpgroup (last P V of a tile)
+  uint64_t* q_full = bars + 6;    // [2] loader -> MMA (a PAIR of query tiles)
+  uint64_t* q_empty = bars + 8;   // [2] MMA -> loader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.x / heads;
+  const int hh = blockIdx.x % heads;
+  const long long base = sm.base(z);
+  const size_t ldq = (size_t)3 * H;
+  const __nv_bfloat16* qptr = qkv + hh * HD;
+  const __nv_bfloat16* kptr = qkv + H + hh * HD;
+  const __nv_bfloat16* vptr = qkv + 2 * H + hh * HD;
+  const int ntiles = (S + 127) / 128;
+  const int npairs = (ntiles + 1) / 2;
+  const int nchunks = S128 / kAtcChunk;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_done[i], 1);
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+
+  // ---- K, V images (whole sequence) + zero padding
+  for (int idx = tid; idx < S128 * 4; idx += kAtcThreads) {  // K: 4 chunks per key (chunk >= CH and keys >= S are zero)
+    const int key = idx >> 2, c = idx & 3;
+    uint8_t* dst = k_img + (key >> 3) * 512 + c * 128 + (key & 7) * 16;
+    if (key < S && c < CH) {
+      cp_async16(dst, kptr + (size_t)(base + (long long)key * sm.seq_stride) * ldq + c * 8, true);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (int idx = tid; idx < S128 * CH; idx += kAtcThreads) {
+    const int key = idx / CH, c = idx % CH;
+    uint8_t* dst = v_img + (key >> 3) * VG + c * 128 + (key & 7) * 16;
+    if (key < S) {
+      cp_async16(dst, vptr + (size_t)(base + (long long)key * sm.seq_stride) * ldq + c * 8, true);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (int idx = tid; idx < 512 / 16; idx += kAtcThreads) *reinterpret_cast<uint4*>(v_img + (size_t)S128 / 8 * VG + idx * 16) = make_uint4(0, 0, 0, 0);
+  for (int idx = tid; idx < 4 * 128; idx += kAtcThreads) {  // zero d-chunk 3.. of the four Q buffers once (never overwritten)
+    const int b = idx >> 7, row = idx & 127;
+    for (int c = CH; c < 4; ++c) *reinterpret_cast<uint4*>(q_img + b * 8192 + (row >> 3) * 512 + c * 128 + (row & 7) * 16) = make_uint4(0, 0, 0, 0);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  fence_proxy_async();  // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t qk_lbo = (variant & 1) ? 512 : 128, qk_sbo = (variant & 1) ? 128 : 512;
+  const uint32_t v_lbo = (variant & 2) ? 128 : VG, v_sbo = (variant & 2) ? VG : 128;
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kAtcChunk);               // A, B K-major
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 32) | (1u << 16);         // B (= V) MN-major
+    const uint32_t k_addr = smem_u32(k_img), v_addr = smem_u32(v_img), q_addr = smem_u32(q_img);
+    uint32_t pcount[2] = {0, 0};  // chunks issued per warpgroup (phase of p_full)
+    for (int p = 0; p < npairs; ++p) {
+      const int qb = p & 1;
+      const bool valid1 = 2 * p + 1 < ntiles;
+      mbar_wait(&q_full[qb], (p >> 1) & 1);
+      tcgen05_fence_after();
+      auto issue_qk = [&](int w, int c) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t a = umma_desc_nosw(q_addr + (qb * 2 + w) * 8192 + j * 256, qk_lbo, qk_sbo);
+            const uint64_t b = umma_desc_nosw(k_addr + c * (kAtcChunk / 8) * 512 + j * 256, qk_lbo, qk_sbo);
+            umma_bf16_ss(tmem_base + w * 128, a, b, idesc_qk, j);
+          }
+          umma_commit(&s_full[w]);
+          if (c == nchunks - 1 && (w == 1 || !valid1)) umma_commit(&q_empty[qb]);  // the pair's query tiles are no longer read
+        }
+        __syncwarp();
+      };
+      issue_qk(0, 0);
+      if (valid1) issue_qk(1, 0);
+      for (int c = 0; c < nchunks; ++c) {
+        for (int w = 0; w < 2; ++w) {
+          if (w == 1 && !valid1) continue;
+          mbar_wait(&p_full[w], pcount[w] & 1);
+          ++pcount[w];
+          tcgen05_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int s = 0; s < kAtcChunk / 16; ++s) {
+              const uint64_t b = umma_desc_nosw(v_addr + (c * (kAtcChunk / 8) + 2 * s) * VG, v_lbo, v_sbo);
+              umma_bf16_ts(tmem_base + 256 + w * 32, tmem_base + w * 128 + s * 8, b, idesc_pv, (c | s) != 0);
+            }
+            if (c == nchunks - 1) umma_commit(&o_done[w]);
+          }
+          __syncwarp();
+          if (c + 1 < nchunks) issue_qk(w, c + 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== Q loader: pair p -> buffers (p & 1) * 2 + {0, 1} =====
+    for (int p = 0; p < npairs; ++p) {
+      const int qb = p & 1;
+      mbar_wait(&q_empty[qb], ((p >> 1) & 1) ^ 1);
+      for (int idx = lane; idx < 2 * 128 * CH; idx += 32) {
+        const int w = idx / (128 * CH), rem = idx % (128 * CH);
+        const int row = rem / CH, c = rem % CH;
+        const int qrow = (2 * p + w) * 128 + row;
+        const bool ok = qrow < S;
+        uint8_t* dst = q_img + (qb * 2 + w) * 8192 + (row >> 3) * 512 + c * 128 + (row & 7) * 16;
+        cp_async16(dst, qptr + (size_t)(base + (long long)(ok ? qrow : 0) * sm.seq_stride) * ldq + c * 8, ok);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full[qb]);
+    }
+  } else if (warp >= 4) {
+    // ===== softmax warpgroups: w = 0 / 1 handles query tile 2 p + w; thread = query row =====
+    const int w = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t s_col = lane_base + w * 128;
+    const uint32_t o_col = lane_base + 256 + w * 32;
+    uint32_t chunk_count = 0, tile_count = 0;
+    for (int p = 0; p < npairs; ++p) {
+      const int tile = 2 * p + w;
+      if (tile >= ntiles) break;
+      const int qrow = tile * 128 + quarter * 32 + lane;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++chunk_count) {
+        mbar_wait(&s_full[w], chunk_count & 1);
+        tcgen05_fence_after();
+        const int key_lim = S - c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count
+        uint32_t sv[2][32];
+        tmem_ld32(s_col, sv[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j + 1 < 4) tmem_ld32(s_col + 32 * (j + 1), sv[(j + 1) & 1]);  // in flight while sub-chunk j is processed
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float x0 = __uint_as_float(sv[j & 1][i]), x1 = __uint_as_float(sv[j & 1][i + 1]);
+            float e0 = ((i / 2) % 8 < POLY) ? poly_exp2(x0) : fast_exp2(x0);
+            float e1 = ((i / 2) % 8 < POLY) ? poly_exp2(x1) : fast_exp2(x1);
+            if (key_lim < kAtcChunk) {
+              if (32 * j + i >= key_lim) e0 = 0.f;
+              if (32 * j + i + 1 >= key_lim) e1 = 0.f;
+            }
+            if ((i & 4) == 0) l0 += e0, l1 += e1;
+            else l2 += e0, l3 += e1;
+            pk[i >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st16(s_col + 16 * j, pk);  // P over S: columns [16 j, 16 j + 16) only cover sub-chunks already in registers
+          if (j + 1 < 4) tmem_ld_wait();
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[w]);
+      }
+      // ---- O of this tile: normalise, store bf16
+      mbar_wait(&o_done[w], tile_count & 1);
+      ++tile_count;
+      tcgen05_fence_after();
+      uint32_t ov[32];
+      tmem_ld32(o_col, ov);
+      tmem_ld_wait();
+      const float inv = 1.f / ((l0 + l1) + (l2 + l3));
+      if (qrow < S) {
+        __nv_bfloat16* op = out + (size_t)(base + (long long)qrow * sm.seq_stride) * ldo + hh * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 8) {
+          uint4 o4;
+          o4.x = pack_bf16x2(__uint_as_float(ov[d + 0]) * inv, __uint_as_float(ov[d + 1]) * inv);
+          o4.y = pack_bf16x2(__uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv);
+          o4.z = pack_bf16x2(__uint_as_float(ov[d + 4]) * inv, __uint_as_float(ov[d + 5]) * inv);
+          o4.w = pack_bf16x2(__uint_as_float(ov[d + 6]) * inv, __uint_as_float(ov[d + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + d) = o4;
+        }
+      }
+      tcgen05_fence_before();  // the O columns are read: the next tile's first P V (ordered behind this warpgroup's next P) may overwrite them
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace lam

@@ -21,6 +21,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
 #include "attn.cuh"
+#include "attn_tc.cuh"
 #include "elementwise.cuh"
 #include "first_stage.cuh"
 
@@ -616,7 +617,24 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
   static const bool legacy_attn = env_flag("LAMSLIDE_LEGACY_ATTN");
   const bool seq_ok = seq_smem <= 232448 - 1024 && (mode == 2 || (!legacy_attn && logit_bound > 0.f && logit_bound <= kSeqKernelMaxLogit));
   if (mode == 2 && !seq_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the whole-sequence attention kernel", sm.S);
-  if ((sm.S > 32 && seq_ok && !force_flash) || mode == 2) {
+  // tcgen05 kernel (attn_tc.cuh): long sequences with bounded logits; mode 3 + 4 * variant forces it (tests / layout probes)
+  const size_t tc_smem = AtcCfg<HD>::smem_bytes(sm.S);
+  static const bool no_tc = env_flag("LAMSLIDE_NO_ATTN_TC");
+  const bool tc_forced = (mode & 3) == 3;
+  const bool tc_ok = tc_smem <= 232448 && (tc_forced || (mode == 0 && !no_tc && !legacy_attn && sm.S >= 384 && logit_bound > 0.f &&
+                                                          logit_bound <= kSeqKernelMaxLogit));
+  if (tc_forced && !tc_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the tcgen05 attention kernel", sm.S);
+  if (tc_ok) {
+    static const int poly = getenv("LAMSLIDE_ATTN_TC_POLY") ? atoi(getenv("LAMSLIDE_ATTN_TC_POLY")) : 0;
+    void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int, int) =
+        poly == 1 ? attn_tc_kernel<HD, 1> : poly == 2 ? attn_tc_kernel<HD, 2> : poly == 3 ? attn_tc_kernel<HD, 3> : attn_tc_kernel<HD, 0>;
+    static const void* configured = nullptr;
+    if (configured != (const void*)kern) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      configured = (const void*)kern;
+    }
+    kern<<<(unsigned)(n_seq * heads), kAtcThreads, tc_smem, st>>>(qkv, out, H, ldo, sm, heads, tc_forced ? (mode >> 2) : 0);
+  } else if ((sm.S > 32 && seq_ok && !force_flash) || mode == 2) {
     // share of the exponentials evaluated on the FMA pipe (poly_exp2) instead of MUFU (of 16 per thread and key block).
     // Measured on B200 (4AA temporal attention): 0 -> 677 us, 2 -> 706, 4 -> 742, 8 -> 820: the kernel is issue-bound, so the
     // extra FMA-pipe instructions cost more than the MUFU slots they free.  Default 0.

@@ -37,6 +37,36 @@ def attn():
     print(f"attn_seq LAMSLIDE_ATTN_POLY={os.environ.get('LAMSLIDE_ATTN_POLY', 'default')}: {us:8.1f} us  {flops / us * 1e-6:7.1f} TFLOP/s", flush=True)
 
 
+def attn_tc_probe():
+    """numerics of the tcgen05 attention kernel for the four descriptor variants (prints, does not assert) + timing"""
+    from tests.test_gpu_kernels import _attention_reference
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    for (B, T, Lx, H, heads) in [(1, 300, 2, 384, 16), (1, 512, 1, 256, 16), (2, 130, 3, 128, 4)]:
+        n = B * T * Lx
+        g = torch.Generator().manual_seed(n)
+        qkv = torch.randn(n, 3 * H, generator=g).to(torch.bfloat16).cuda()
+        ref = _attention_reference(qkv, B, T, Lx, H, heads, True)
+        for variant in range(4):
+            out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
+            rc = lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, 3 + 4 * variant, st)
+            try:
+                torch.cuda.synchronize()
+                err = float((out.float() - ref).abs().max() / ref.abs().max())
+                mean = float((out.float() - ref).abs().mean() / ref.abs().mean())
+                print(f"attn_tc B={B} T={T} L={Lx} H={H} heads={heads} variant={variant}: rc={rc} max_rel={err:.3e} mean_rel={mean:.3e}", flush=True)
+            except Exception as e:  # a trapped launch poisons the context: stop
+                print(f"attn_tc variant={variant}: CUDA error {e}", flush=True)
+                return
+    B, T, Lx, H, heads = 64, 1000, 2, 384, 16
+    n = B * T * Lx
+    qkv = (torch.randn(n, 3 * H, device="cuda") * 0.6).to(torch.bfloat16)
+    out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
+    for mode, name in [(3, "tcgen05"), (2, "mma.sync whole-sequence")]:
+        us = time_fn(lambda: L.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, mode, st)), iters=10)
+        print(f"attention 4AA temporal [{name}] poly={os.environ.get('LAMSLIDE_ATTN_TC_POLY', '0')}: {us:8.1f} us  {4.0 * 24 * T * T * heads * B * Lx / us * 1e-6:7.1f} TFLOP/s", flush=True)
+
+
 def linear1():
     """linear1 of the 4AA config at B = 64 (128000 rows): full kernel, math without stores, stores without math"""
     import math
@@ -60,6 +90,8 @@ def linear1():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "attn":
         return attn()
+    if len(sys.argv) > 1 and sys.argv[1] == "attn_tc":
+        return attn_tc_probe()
     if len(sys.argv) > 1 and sys.argv[1] == "linear1":
         return linear1()
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 128000

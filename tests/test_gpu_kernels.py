@@ -179,3 +179,27 @@ def test_linear2_gated_residual(rows, H, M, rps, legacy):
     ref = h0.double() + gate.double()[b_of_row] * (act.double() @ w2.double().t() + bias.double())
     assert torch.isfinite(h).all()
     assert max_rel(h, ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,L,H,heads,temporal", [
+    (2, 1000, 2, 384, 16, 1), (1, 300, 2, 384, 16, 1), (1, 129, 2, 384, 16, 1), (1, 1040, 1, 384, 16, 1), (2, 130, 3, 128, 4, 1),
+    (1, 512, 1, 256, 16, 1), (2, 7, 192, 256, 16, 0), (1, 64, 1, 256, 16, 1),
+])
+def test_tcgen05_attention_matches_softmax_reference(B, T, L, H, heads, temporal):
+    """mode 3: S = Q K^T and O = P V on tcgen05 (accumulators and P in TMEM), K / V images in the no-swizzle UMMA layout."""
+    L_ = _lib()
+    lib = L_.load()
+    n = B * T * L
+    g = torch.Generator(device="cpu").manual_seed(n + H + 2)
+    qkv = (torch.randn(n, 3 * H, generator=g)).to(torch.bfloat16).cuda()
+    ldo = H + 64
+    out = torch.zeros(n, ldo, dtype=torch.bfloat16, device="cuda")
+    L_.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, L, H, heads, ldo, temporal, 3,
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = _attention_reference(qkv, B, T, L, H, heads, bool(temporal))
+    got = out[:, :H].float()
+    assert torch.isfinite(got).all()
+    assert float(out[:, H:].float().abs().max()) == 0.0
+    assert max_rel(got, ref) < 2e-2
+    assert float((got - ref).abs().mean() / ref.abs().mean()) < 5e-3

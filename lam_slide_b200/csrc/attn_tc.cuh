@@ -1,40 +1,41 @@
-// tcgen05 / TMEM attention for long sequences (temporal axis of the second stage, S = T up to 1024 keys per tile pass;
-// mmdit.py:42-55: softmax(q k^T / sqrt(hd)) v, no mask).  q and k arrive RMS-normalised + rotated and q pre-multiplied by
-// hd^-0.5 * log2(e) from the linear1 epilogue, so the logits are bounded (see attn.cuh: attn_seq_kernel) and softmax is evaluated as
-// exp2(s) / sum exp2(s) without a running maximum.
+// tcgen05 / TMEM attention for long sequences (temporal axis of the second stage; mmdit.py:42-55: softmax(q k^T / sqrt(hd)) v,
+// no mask).  q and k arrive RMS-normalised + rotated and q pre-multiplied by hd^-0.5 * log2(e) from the linear1 epilogue, so the
+// logits are bounded (see attn.cuh: attn_seq_kernel) and softmax is evaluated as exp2(s) / sum exp2(s) without a running maximum.
 //
-// One CTA per (sequence, head), one CTA per SM.  All of K and V of the (sequence, head) live in shared memory in the canonical
-// NO-SWIZZLE UMMA layout (8 x 16-byte "core matrices"): element (key, d) at
-//     (key / 8) * GROUP + (d / 8) * 128 + (key % 8) * 16 + (d % 8) * 2          bytes,
+// One CTA per (sequence, head); TWO CTAs per SM (each ~112 KB of shared memory and 256 TMEM columns at S = 1000), so one CTA's
+// K / V load phase and MMA round trips hide behind the other's exponentials.  All of K and V of the (sequence, head) live in
+// shared memory in the canonical NO-SWIZZLE UMMA layout (8 x 16-byte "core matrices"): element (key, d) at
+//     (key / 8) * (hd / 8) * 128 + (d / 8) * 128 + (key % 8) * 16 + (d % 8) * 2          bytes,
 // which serves BOTH MMAs from one image each: K as the K-major B operand of S = Q K^T (N = keys, K = d), V as the MN-major
-// B operand of O = P V (N = d, K = keys).  d is padded to 32 for K and Q (zero chunk), V keeps hd / 8 chunks per key group.
+// B operand of O = P V (N = d, K = keys).  The contraction of S runs over d padded to a multiple of 16: the Q tile carries zero
+// chunks there, so whatever (finite) bytes the K image has at those offsets do not matter.
 //
-// Warp roles (384 threads):
-//   warp 0       : TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues)
-//   warp 1       : Q loader (cp.async of two 128-row query tiles into the same core-matrix layout, double buffered)
-//   warps 2, 3   : idle after the K / V load
-//   warps 4..11  : two softmax warpgroups (one query tile each): thread = query row.  Per 128-key chunk: tcgen05.ld S (fp32) ->
-//                  exp2 -> row sum -> bf16 -> tcgen05.st P over the same TMEM columns (P aliases S) -> mbarrier.
-// TMEM (512 columns): S0 | S1 (128 fp32 columns each, P in the first 64), O0 | O1 (32 columns each).
-// Tensor work per (tile, chunk): S = Q K^T as 2 MMAs (M 128, N 128, K 16), O += P V as 8 MMAs (M 128, N 32, K 16, A from TMEM):
-// ~256 tensor cycles against 1024 MUFU cycles for the 16 k exponentials, so the two warpgroups keep the MUFU busy while the
-// other tile's MMAs run.
+// Warp roles (256 threads):
+//   warp 0      : TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues)
+//   warp 1      : Q loader (cp.async of a 128-row query tile into the same core-matrix layout, double buffered)
+//   warps 2, 3  : idle after the K / V load
+//   warps 4..7  : softmax: thread = query row.  Per 128-key chunk: tcgen05.ld S (fp32) -> exp2 -> row sum -> bf16 ->
+//                 tcgen05.st P over the same TMEM columns (P aliases S) -> mbarrier.
+// TMEM (256 columns): S (128 fp32 columns, P in the first 64) | O (32 columns).
+// Tensor work per chunk: S = Q K^T as 1-2 MMAs (M 128, N 128, K 16), O += P V as 8 MMAs (M 128, N 32, K 16, A from TMEM):
+// ~256 tensor cycles against 1024 MUFU cycles for the 16 k exponentials — the kernel is bound by the exponentials.
 #pragma once
 #include "attn.cuh"
 
 namespace lam {
 
-constexpr int kAtcThreads = 384;
+constexpr int kAtcThreads = 256;
 constexpr int kAtcChunk = 128;  // keys per S tile
 
 __host__ __device__ inline int atc_s128(int S) { return (S + 127) & ~127; }
 template <int HD>
 struct AtcCfg {
-  static constexpr int VG = (HD / 8) * 128;  // bytes per 8-key group of the V image
-  static __host__ __device__ size_t k_bytes(int S) { return (size_t)atc_s128(S) * 64; }
-  static __host__ __device__ size_t v_bytes(int S) { return (size_t)atc_s128(S) / 8 * VG + 512; }  // + tail pad (N = 32 reads 4 chunks)
-  static __host__ __device__ size_t q_bytes() { return 4 * 8192; }
-  static __host__ __device__ size_t smem_bytes(int S) { return k_bytes(S) + v_bytes(S) + q_bytes() + 256; }
+  static constexpr int KG = (HD / 8) * 128;      // bytes per 8-key group of the K / V images
+  static constexpr int KSTEPS = (HD + 15) / 16;  // k16 steps of S = Q K^T
+  static __host__ __device__ size_t kv_bytes(int S) { return (size_t)atc_s128(S) / 8 * KG; }
+  static __host__ __device__ size_t q_bytes() { return 2 * 8192; }
+  // K image | V image | 128-byte zero tail (the N = 32 P V MMA reads 4 d-chunks per key group) | 2 Q tiles | barriers
+  static __host__ __device__ size_t smem_bytes(int S) { return 2 * kv_bytes(S) + 128 + q_bytes() + 128; }
 };
 
 // no-swizzle UMMA shared-memory descriptor: start address, leading-dimension byte offset, stride-dimension byte offset
@@ -64,27 +65,29 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// POLY: of every 8 exponentials, POLY are evaluated on the FMA pipe (poly_exp2) instead of MUFU.EX2.
 // variant bits (debug aid, lamslide_debug_attention mode 3 + 4 * variant): 1 = swap LBO / SBO of the Q / K descriptors,
-// 2 = swap LBO / SBO of the V descriptor.  0 is the layout derived from the canonical UMMA layouts.
+// 2 = swap LBO / SBO of the V descriptor.  0 is the layout derived from the canonical UMMA layouts (verified on B200).
 template <int HD, int POLY>
-__global__ void __launch_bounds__(kAtcThreads, 1)
+__global__ void __launch_bounds__(kAtcThreads, 2)
 attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, SeqMap sm, int heads, int variant) {
   using Cfg = AtcCfg<HD>;
   constexpr int CH = HD / 8;
-  constexpr int VG = Cfg::VG;
+  constexpr int KG = Cfg::KG;
+  constexpr int KSTEPS = Cfg::KSTEPS;
   extern __shared__ __align__(1024) uint8_t atc_smem[];
   const int S = sm.S;
   const int S128 = atc_s128(S);
   uint8_t* k_img = atc_smem;
-  uint8_t* v_img = k_img + Cfg::k_bytes(S);
-  uint8_t* q_img = v_img + Cfg::v_bytes(S);
+  uint8_t* v_img = k_img + Cfg::kv_bytes(S);
+  uint8_t* q_img = v_img + Cfg::kv_bytes(S) + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(q_img + Cfg::q_bytes());
-  uint64_t* s_full = bars;        // [2] MMA -> softmax warpgroup
-  uint64_t* p_full = bars + 2;    // [2] softmax warpgroup -> MMA
-  uint64_t* o_done = bars + 4;    // [2] MMA -> softmax warpgroup (last P V of a tile)
-  uint64_t* q_full = bars + 6;    // [2] loader -> MMA (a PAIR of query tiles)
-  uint64_t* q_empty = bars + 8;   // [2] MMA -> loader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* s_full = bars;        // MMA -> softmax
+  uint64_t* p_full = bars + 1;    // softmax -> MMA
+  uint64_t* o_done = bars + 2;    // MMA -> softmax (last P V of a tile)
+  uint64_t* q_full = bars + 3;    // [2] loader -> MMA
+  uint64_t* q_empty = bars + 5;   // [2] MMA -> loader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.x / heads;
@@ -95,44 +98,37 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
   const __nv_bfloat16* kptr = qkv + H + hh * HD;
   const __nv_bfloat16* vptr = qkv + 2 * H + hh * HD;
   const int ntiles = (S + 127) / 128;
-  const int npairs = (ntiles + 1) / 2;
   const int nchunks = S128 / kAtcChunk;
 
   if (tid == 0) {
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_done, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&o_done[i], 1);
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
 
-  // ---- K, V images (whole sequence) + zero padding
-  for (int idx = tid; idx < S128 * 4; idx += kAtcThreads) {  // K: 4 chunks per key (chunk >= CH and keys >= S are zero)
-    const int key = idx >> 2, c = idx & 3;
-    uint8_t* dst = k_img + (key >> 3) * 512 + c * 128 + (key & 7) * 16;
-    if (key < S && c < CH) {
-      cp_async16(dst, kptr + (size_t)(base + (long long)key * sm.seq_stride) * ldq + c * 8, true);
-    } else {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-    }
-  }
+  // ---- K, V images (whole sequence); keys >= S are zero rows
   for (int idx = tid; idx < S128 * CH; idx += kAtcThreads) {
     const int key = idx / CH, c = idx % CH;
-    uint8_t* dst = v_img + (key >> 3) * VG + c * 128 + (key & 7) * 16;
+    const uint32_t off = (key >> 3) * KG + c * 128 + (key & 7) * 16;
     if (key < S) {
-      cp_async16(dst, vptr + (size_t)(base + (long long)key * sm.seq_stride) * ldq + c * 8, true);
+      const size_t tok = (size_t)(base + (long long)key * sm.seq_stride) * ldq + c * 8;
+      cp_async16(k_img + off, kptr + tok, true);
+      cp_async16(v_img + off, vptr + tok, true);
     } else {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(k_img + off) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(v_img + off) = make_uint4(0, 0, 0, 0);
     }
   }
-  for (int idx = tid; idx < 512 / 16; idx += kAtcThreads) *reinterpret_cast<uint4*>(v_img + (size_t)S128 / 8 * VG + idx * 16) = make_uint4(0, 0, 0, 0);
-  for (int idx = tid; idx < 4 * 128; idx += kAtcThreads) {  // zero d-chunk 3.. of the four Q buffers once (never overwritten)
+  if (tid < 8) *reinterpret_cast<uint4*>(v_img + Cfg::kv_bytes(S) + tid * 16) = make_uint4(0, 0, 0, 0);
+  for (int idx = tid; idx < 2 * 128; idx += kAtcThreads) {  // zero d-chunks CH .. 2 KSTEPS of the two Q buffers once (never overwritten)
     const int b = idx >> 7, row = idx & 127;
-    for (int c = CH; c < 4; ++c) *reinterpret_cast<uint4*>(q_img + b * 8192 + (row >> 3) * 512 + c * 128 + (row & 7) * 16) = make_uint4(0, 0, 0, 0);
+    for (int c = CH; c < 2 * KSTEPS; ++c) *reinterpret_cast<uint4*>(q_img + b * 8192 + (row >> 3) * 512 + c * 128 + (row & 7) * 16) = make_uint4(0, 0, 0, 0);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -141,88 +137,79 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t qk_lbo = (variant & 1) ? 512 : 128, qk_sbo = (variant & 1) ? 128 : 512;
-  const uint32_t v_lbo = (variant & 2) ? 128 : VG, v_sbo = (variant & 2) ? VG : 128;
+  const uint32_t q_lbo = (variant & 1) ? 512 : 128, q_sbo = (variant & 1) ? 128 : 512;
+  const uint32_t k_lbo = (variant & 1) ? KG : 128, k_sbo = (variant & 1) ? 128 : KG;
+  const uint32_t v_lbo = (variant & 2) ? 128 : KG, v_sbo = (variant & 2) ? KG : 128;
 
   if (warp == 0) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: S(t, c) = Q_t K_c^T;  O_t += P(t, c) V_c.  The next S is issued right behind each P V (in-order pipe). =====
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kAtcChunk);               // A, B K-major
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 32) | (1u << 16);         // B (= V) MN-major
     const uint32_t k_addr = smem_u32(k_img), v_addr = smem_u32(v_img), q_addr = smem_u32(q_img);
-    uint32_t pcount[2] = {0, 0};  // chunks issued per warpgroup (phase of p_full)
-    for (int p = 0; p < npairs; ++p) {
-      const int qb = p & 1;
-      const bool valid1 = 2 * p + 1 < ntiles;
-      mbar_wait(&q_full[qb], (p >> 1) & 1);
-      tcgen05_fence_after();
-      auto issue_qk = [&](int w, int c) {
+    auto issue_qk = [&](int t, int c) {
+      if (c == 0) {
+        mbar_wait(&q_full[t & 1], (t >> 1) & 1);
+        tcgen05_fence_after();
+      }
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < KSTEPS; ++j) {
+          const uint64_t a = umma_desc_nosw(q_addr + (t & 1) * 8192 + j * 256, q_lbo, q_sbo);
+          const uint64_t b = umma_desc_nosw(k_addr + c * (kAtcChunk / 8) * KG + j * 256, k_lbo, k_sbo);
+          umma_bf16_ss(tmem_base, a, b, idesc_qk, j);
+        }
+        umma_commit(s_full);
+        if (c == nchunks - 1) umma_commit(&q_empty[t & 1]);  // the query tile is no longer read
+      }
+      __syncwarp();
+    };
+    issue_qk(0, 0);
+    uint32_t n = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      for (int c = 0; c < nchunks; ++c, ++n) {
+        mbar_wait(p_full, n & 1);
+        tcgen05_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t a = umma_desc_nosw(q_addr + (qb * 2 + w) * 8192 + j * 256, qk_lbo, qk_sbo);
-            const uint64_t b = umma_desc_nosw(k_addr + c * (kAtcChunk / 8) * 512 + j * 256, qk_lbo, qk_sbo);
-            umma_bf16_ss(tmem_base + w * 128, a, b, idesc_qk, j);
+          for (int s = 0; s < kAtcChunk / 16; ++s) {
+            const uint64_t b = umma_desc_nosw(v_addr + (c * (kAtcChunk / 8) + 2 * s) * KG, v_lbo, v_sbo);
+            umma_bf16_ts(tmem_base + 128, tmem_base + s * 8, b, idesc_pv, (c | s) != 0);
           }
-          umma_commit(&s_full[w]);
-          if (c == nchunks - 1 && (w == 1 || !valid1)) umma_commit(&q_empty[qb]);  // the pair's query tiles are no longer read
+          if (c == nchunks - 1) umma_commit(o_done);
         }
         __syncwarp();
-      };
-      issue_qk(0, 0);
-      if (valid1) issue_qk(1, 0);
-      for (int c = 0; c < nchunks; ++c) {
-        for (int w = 0; w < 2; ++w) {
-          if (w == 1 && !valid1) continue;
-          mbar_wait(&p_full[w], pcount[w] & 1);
-          ++pcount[w];
-          tcgen05_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int s = 0; s < kAtcChunk / 16; ++s) {
-              const uint64_t b = umma_desc_nosw(v_addr + (c * (kAtcChunk / 8) + 2 * s) * VG, v_lbo, v_sbo);
-              umma_bf16_ts(tmem_base + 256 + w * 32, tmem_base + w * 128 + s * 8, b, idesc_pv, (c | s) != 0);
-            }
-            if (c == nchunks - 1) umma_commit(&o_done[w]);
-          }
-          __syncwarp();
-          if (c + 1 < nchunks) issue_qk(w, c + 1);
-        }
+        if (c + 1 < nchunks) issue_qk(t, c + 1);
+        else if (t + 1 < ntiles) issue_qk(t + 1, 0);
       }
     }
   } else if (warp == 1) {
-    // ===== Q loader: pair p -> buffers (p & 1) * 2 + {0, 1} =====
-    for (int p = 0; p < npairs; ++p) {
-      const int qb = p & 1;
-      mbar_wait(&q_empty[qb], ((p >> 1) & 1) ^ 1);
-      for (int idx = lane; idx < 2 * 128 * CH; idx += 32) {
-        const int w = idx / (128 * CH), rem = idx % (128 * CH);
-        const int row = rem / CH, c = rem % CH;
-        const int qrow = (2 * p + w) * 128 + row;
+    // ===== Q loader: tile t -> buffer t & 1 =====
+    for (int t = 0; t < ntiles; ++t) {
+      mbar_wait(&q_empty[t & 1], ((t >> 1) & 1) ^ 1);
+      for (int idx = lane; idx < 128 * CH; idx += 32) {
+        const int row = idx / CH, c = idx % CH;
+        const int qrow = t * 128 + row;
         const bool ok = qrow < S;
-        uint8_t* dst = q_img + (qb * 2 + w) * 8192 + (row >> 3) * 512 + c * 128 + (row & 7) * 16;
+        uint8_t* dst = q_img + (t & 1) * 8192 + (row >> 3) * 512 + c * 128 + (row & 7) * 16;
         cp_async16(dst, qptr + (size_t)(base + (long long)(ok ? qrow : 0) * sm.seq_stride) * ldq + c * 8, ok);
       }
       cp_async_commit();
       cp_async_wait<0>();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&q_full[qb]);
+      if (lane == 0) mbar_arrive(&q_full[t & 1]);
     }
   } else if (warp >= 4) {
-    // ===== softmax warpgroups: w = 0 / 1 handles query tile 2 p + w; thread = query row =====
-    const int w = (warp - 4) >> 2;
+    // ===== softmax: thread = query row =====
     const int quarter = warp & 3;
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t s_col = lane_base + w * 128;
-    const uint32_t o_col = lane_base + 256 + w * 32;
-    uint32_t chunk_count = 0, tile_count = 0;
-    for (int p = 0; p < npairs; ++p) {
-      const int tile = 2 * p + w;
-      if (tile >= ntiles) break;
-      const int qrow = tile * 128 + quarter * 32 + lane;
+    const uint32_t s_col = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t o_col = s_col + 128;
+    uint32_t n = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int qrow = t * 128 + quarter * 32 + lane;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      for (int c = 0; c < nchunks; ++c, ++chunk_count) {
-        mbar_wait(&s_full[w], chunk_count & 1);
+      for (int c = 0; c < nchunks; ++c, ++n) {
+        mbar_wait(s_full, n & 1);
         tcgen05_fence_after();
         const int key_lim = S - c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count
         uint32_t sv[2][32];
@@ -251,11 +238,10 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[w]);
+        if (lane == 0) mbar_arrive(p_full);
       }
       // ---- O of this tile: normalise, store bf16
-      mbar_wait(&o_done[w], tile_count & 1);
-      ++tile_count;
+      mbar_wait(o_done, t & 1);
       tcgen05_fence_after();
       uint32_t ov[32];
       tmem_ld32(o_col, ov);
@@ -273,7 +259,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
           *reinterpret_cast<uint4*>(op + d) = o4;
         }
       }
-      tcgen05_fence_before();  // the O columns are read: the next tile's first P V (ordered behind this warpgroup's next P) may overwrite them
+      tcgen05_fence_before();  // O is read: the next tile's first P V (ordered behind this thread's next P) may overwrite it
     }
   }
 
@@ -281,7 +267,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 

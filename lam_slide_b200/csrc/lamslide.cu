@@ -631,6 +631,7 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
     static const void* configured = nullptr;
     if (configured != (const void*)kern) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       configured = (const void*)kern;
     }
     kern<<<(unsigned)(n_seq * heads), kAtcThreads, tc_smem, st>>>(qkv, out, H, ldo, sm, heads, tc_forced ? (mode >> 2) : 0);

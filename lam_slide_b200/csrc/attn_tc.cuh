@@ -63,7 +63,51 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
                "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One 128-key chunk of one query row: S (fp32, TMEM) -> exp2 -> row-sum partials -> bf16 P written over the same columns.
+// MASKED: keys >= key_lim get probability 0 (instantiated for the last chunk of a sequence only).
+template <int POLY, bool MASKED>
+__device__ __forceinline__ void atc_softmax_sub(const uint32_t* sv, uint32_t p_col, int key0, int key_lim, float& l0, float& l1, float& l2,
+                                                float& l3) {
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float x0 = __uint_as_float(sv[i]), x1 = __uint_as_float(sv[i + 1]);
+    float e0 = ((i / 2) % 8 < POLY) ? poly_exp2(x0) : fast_exp2(x0);
+    float e1 = ((i / 2) % 8 < POLY) ? poly_exp2(x1) : fast_exp2(x1);
+    if (MASKED) {
+      if (key0 + i >= key_lim) e0 = 0.f;
+      if (key0 + i + 1 >= key_lim) e1 = 0.f;
+    }
+    if ((i & 4) == 0) l0 += e0, l1 += e1;
+    else l2 += e0, l3 += e1;
+    pk[i >> 1] = pack_bf16x2(e0, e1);
+  }
+  tmem_st8(p_col, pk);  // P over S: these columns only cover sub-chunks that are already in registers
+}
+template <int POLY, bool MASKED>
+__device__ __forceinline__ void atc_softmax_chunk(uint32_t s_col, int key_lim, float& l0, float& l1, float& l2, float& l3) {
+  // 16 columns per TMEM load, two loads in flight; the loop is unrolled by two only (static register indices, bounded live
+  // ranges: the kernel runs at 128 registers per thread for two CTAs per SM)
+  uint32_t sa[16], sb[16];
+  tmem_ld16(s_col, sa);
+  tmem_ld_wait();
+#pragma unroll 1
+  for (int jj = 0; jj < kAtcChunk / 32; ++jj) {
+    tmem_ld16(s_col + 32 * jj + 16, sb);  // in flight while sub-chunk 2 jj is processed
+    atc_softmax_sub<POLY, MASKED>(sa, s_col + 16 * jj, 32 * jj, key_lim, l0, l1, l2, l3);
+    tmem_ld_wait();
+    if (jj + 1 < kAtcChunk / 32) tmem_ld16(s_col + 32 * jj + 32, sa);
+    atc_softmax_sub<POLY, MASKED>(sb, s_col + 16 * jj + 8, 32 * jj + 16, key_lim, l0, l1, l2, l3);
+    tmem_ld_wait();
+  }
+}
 
 // POLY: of every 8 exponentials, POLY are evaluated on the FMA pipe (poly_exp2) instead of MUFU.EX2.
 // variant bits (debug aid, lamslide_debug_attention mode 3 + 4 * variant): 1 = swap LBO / SBO of the Q / K descriptors,
@@ -211,30 +255,9 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
       for (int c = 0; c < nchunks; ++c, ++n) {
         mbar_wait(s_full, n & 1);
         tcgen05_fence_after();
-        const int key_lim = S - c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count
-        uint32_t sv[2][32];
-        tmem_ld32(s_col, sv[0]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j + 1 < 4) tmem_ld32(s_col + 32 * (j + 1), sv[(j + 1) & 1]);  // in flight while sub-chunk j is processed
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float x0 = __uint_as_float(sv[j & 1][i]), x1 = __uint_as_float(sv[j & 1][i + 1]);
-            float e0 = ((i / 2) % 8 < POLY) ? poly_exp2(x0) : fast_exp2(x0);
-            float e1 = ((i / 2) % 8 < POLY) ? poly_exp2(x1) : fast_exp2(x1);
-            if (key_lim < kAtcChunk) {
-              if (32 * j + i >= key_lim) e0 = 0.f;
-              if (32 * j + i + 1 >= key_lim) e1 = 0.f;
-            }
-            if ((i & 4) == 0) l0 += e0, l1 += e1;
-            else l2 += e0, l3 += e1;
-            pk[i >> 1] = pack_bf16x2(e0, e1);
-          }
-          tmem_st16(s_col + 16 * j, pk);  // P over S: columns [16 j, 16 j + 16) only cover sub-chunks already in registers
-          if (j + 1 < 4) tmem_ld_wait();
-        }
+        const int key_lim = S - c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count: last chunk only
+        if (key_lim >= kAtcChunk) atc_softmax_chunk<POLY, false>(s_col, key_lim, l0, l1, l2, l3);
+        else atc_softmax_chunk<POLY, true>(s_col, key_lim, l0, l1, l2, l3);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();

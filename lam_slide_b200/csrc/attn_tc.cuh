@@ -14,18 +14,19 @@
 //   warp 0      : TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues)
 //   warp 1      : Q loader (cp.async of a 128-row query tile into the same core-matrix layout, double buffered)
 //   warps 2, 3  : idle after the K / V load
-//   warps 4..7  : softmax: thread = query row.  Per 128-key chunk: tcgen05.ld S (fp32) -> exp2 -> row sum -> bf16 ->
+//   warps 4..7  : softmax: thread = query row.  Per 64-key chunk: tcgen05.ld S (fp32) -> exp2 -> row sum -> bf16 ->
 //                 tcgen05.st P over the same TMEM columns (P aliases S) -> mbarrier.
-// TMEM (256 columns): S (128 fp32 columns, P in the first 64) | O (32 columns).
-// Tensor work per chunk: S = Q K^T as 1-2 MMAs (M 128, N 128, K 16), O += P V as 8 MMAs (M 128, N 32, K 16, A from TMEM):
-// ~256 tensor cycles against 1024 MUFU cycles for the 16 k exponentials — the kernel is bound by the exponentials.
+// TMEM (256 columns): S0 | S1 (64 fp32 columns each, P in the first 32: DOUBLE BUFFERED so S of chunk n + 1 is computed while the
+// softmax warps work on chunk n and the MMA round trip is off their critical path) | O (32 columns).
+// Tensor work per chunk: S = Q K^T as 1-2 MMAs (M 128, N 64, K 16), O += P V as 4 MMAs (M 128, N 32, K 16, A from TMEM):
+// ~250 tensor cycles against 512 MUFU cycles for the 8 k exponentials — the kernel is bound by the exponentials.
 #pragma once
 #include "attn.cuh"
 
 namespace lam {
 
 constexpr int kAtcThreads = 256;
-constexpr int kAtcChunk = 128;  // keys per S tile
+constexpr int kAtcChunk = 64;   // keys per S tile
 
 __host__ __device__ inline int atc_s128(int S) { return (S + 127) & ~127; }
 template <int HD>
@@ -126,12 +127,12 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
   uint8_t* v_img = k_img + Cfg::kv_bytes(S);
   uint8_t* q_img = v_img + Cfg::kv_bytes(S) + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(q_img + Cfg::q_bytes());
-  uint64_t* s_full = bars;        // MMA -> softmax
-  uint64_t* p_full = bars + 1;    // softmax -> MMA
-  uint64_t* o_done = bars + 2;    // MMA -> softmax (last P V of a tile)
-  uint64_t* q_full = bars + 3;    // [2] loader -> MMA
-  uint64_t* q_empty = bars + 5;   // [2] MMA -> loader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* s_full = bars;        // [2] MMA -> softmax (S buffer n & 1)
+  uint64_t* p_full = bars + 2;    // [2] softmax -> MMA
+  uint64_t* o_done = bars + 4;    // MMA -> softmax (last P V of a tile)
+  uint64_t* q_full = bars + 5;    // [2] loader -> MMA
+  uint64_t* q_empty = bars + 7;   // [2] MMA -> loader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int z = blockIdx.x / heads;
@@ -142,13 +143,13 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
   const __nv_bfloat16* kptr = qkv + H + hh * HD;
   const __nv_bfloat16* vptr = qkv + 2 * H + hh * HD;
   const int ntiles = (S + 127) / 128;
-  const int nchunks = S128 / kAtcChunk;
+  const int nchunks = (S + kAtcChunk - 1) / kAtcChunk;
 
   if (tid == 0) {
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
     mbar_init(o_done, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
     }
@@ -186,11 +187,14 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
   const uint32_t v_lbo = (variant & 2) ? 128 : KG, v_sbo = (variant & 2) ? KG : 128;
 
   if (warp == 0) {
-    // ===== MMA issuer: S(t, c) = Q_t K_c^T;  O_t += P(t, c) V_c.  The next S is issued right behind each P V (in-order pipe). =====
+    // ===== MMA issuer.  Chunk n = (tile t, chunk c) uses S buffer n & 1: S(n) = Q_t K_c^T;  O_t += P(n) V_c.  S(n + 2) is issued
+    // right behind P V(n) (in-order tensor pipe: the P it overwrites has been consumed), so two S tiles are always ahead. =====
     constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kAtcChunk);               // A, B K-major
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 32) | (1u << 16);         // B (= V) MN-major
     const uint32_t k_addr = smem_u32(k_img), v_addr = smem_u32(v_img), q_addr = smem_u32(q_img);
-    auto issue_qk = [&](int t, int c) {
+    const int total = ntiles * nchunks;
+    auto issue_qk = [&](int n) {
+      const int t = n / nchunks, c = n % nchunks;
       if (c == 0) {
         mbar_wait(&q_full[t & 1], (t >> 1) & 1);
         tcgen05_fence_after();
@@ -200,31 +204,29 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
         for (int j = 0; j < KSTEPS; ++j) {
           const uint64_t a = umma_desc_nosw(q_addr + (t & 1) * 8192 + j * 256, q_lbo, q_sbo);
           const uint64_t b = umma_desc_nosw(k_addr + c * (kAtcChunk / 8) * KG + j * 256, k_lbo, k_sbo);
-          umma_bf16_ss(tmem_base, a, b, idesc_qk, j);
+          umma_bf16_ss(tmem_base + (n & 1) * kAtcChunk, a, b, idesc_qk, j);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[n & 1]);
         if (c == nchunks - 1) umma_commit(&q_empty[t & 1]);  // the query tile is no longer read
       }
       __syncwarp();
     };
-    issue_qk(0, 0);
-    uint32_t n = 0;
-    for (int t = 0; t < ntiles; ++t) {
-      for (int c = 0; c < nchunks; ++c, ++n) {
-        mbar_wait(p_full, n & 1);
-        tcgen05_fence_after();
-        if (elect_one()) {
+    issue_qk(0);
+    if (total > 1) issue_qk(1);
+    for (int n = 0; n < total; ++n) {
+      const int c = n % nchunks;
+      mbar_wait(&p_full[n & 1], (n >> 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int s = 0; s < kAtcChunk / 16; ++s) {
-            const uint64_t b = umma_desc_nosw(v_addr + (c * (kAtcChunk / 8) + 2 * s) * KG, v_lbo, v_sbo);
-            umma_bf16_ts(tmem_base + 128, tmem_base + s * 8, b, idesc_pv, (c | s) != 0);
-          }
-          if (c == nchunks - 1) umma_commit(o_done);
+        for (int s = 0; s < kAtcChunk / 16; ++s) {
+          const uint64_t b = umma_desc_nosw(v_addr + (c * (kAtcChunk / 8) + 2 * s) * KG, v_lbo, v_sbo);
+          umma_bf16_ts(tmem_base + 2 * kAtcChunk, tmem_base + (n & 1) * kAtcChunk + s * 8, b, idesc_pv, (c | s) != 0);
         }
-        __syncwarp();
-        if (c + 1 < nchunks) issue_qk(t, c + 1);
-        else if (t + 1 < ntiles) issue_qk(t + 1, 0);
+        if (c == nchunks - 1) umma_commit(o_done);
       }
+      __syncwarp();
+      if (n + 2 < total) issue_qk(n + 2);
     }
   } else if (warp == 1) {
     // ===== Q loader: tile t -> buffer t & 1 =====
@@ -246,22 +248,23 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
   } else if (warp >= 4) {
     // ===== softmax: thread = query row =====
     const int quarter = warp & 3;
-    const uint32_t s_col = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t o_col = s_col + 128;
+    const uint32_t s_col0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t o_col = s_col0 + 2 * kAtcChunk;
     uint32_t n = 0;
     for (int t = 0; t < ntiles; ++t) {
       const int qrow = t * 128 + quarter * 32 + lane;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       for (int c = 0; c < nchunks; ++c, ++n) {
-        mbar_wait(s_full, n & 1);
+        mbar_wait(&s_full[n & 1], (n >> 1) & 1);
         tcgen05_fence_after();
+        const uint32_t s_col = s_col0 + (n & 1) * kAtcChunk;
         const int key_lim = S - c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count: last chunk only
         if (key_lim >= kAtcChunk) atc_softmax_chunk<POLY, false>(s_col, key_lim, l0, l1, l2, l3);
         else atc_softmax_chunk<POLY, true>(s_col, key_lim, l0, l1, l2, l3);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(&p_full[n & 1]);
       }
       // ---- O of this tile: normalise, store bf16
       mbar_wait(o_done, t & 1);

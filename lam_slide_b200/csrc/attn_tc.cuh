@@ -10,14 +10,15 @@
 // B operand of O = P V (N = d, K = keys).  The contraction of S runs over d padded to a multiple of 16: the Q tile carries zero
 // chunks there, so whatever (finite) bytes the K image has at those offsets do not matter.
 //
-// Warp roles (256 threads):
+// Warp roles (384 threads):
 //   warp 0      : TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues)
 //   warp 1      : Q loader (cp.async of a 128-row query tile into the same core-matrix layout, double buffered)
 //   warps 2, 3  : idle after the K / V load
-//   warps 4..7  : softmax: thread = query row.  Per 64-key chunk: tcgen05.ld S (fp32) -> exp2 -> row sum -> bf16 ->
-//                 tcgen05.st P over the same TMEM columns (P aliases S) -> mbarrier.
-// TMEM (256 columns): S0 | S1 (64 fp32 columns each, P in the first 32: DOUBLE BUFFERED so S of chunk n + 1 is computed while the
-// softmax warps work on chunk n and the MMA round trip is off their critical path) | O (32 columns).
+//   warps 4..11 : softmax: thread = (query row, half of the chunk's keys) — 8 warps per CTA, 4 per scheduler with two CTAs per SM,
+//                 which is what it takes to keep the 16-lane MUFU unit busy.  Per 64-key chunk: tcgen05.ld S (fp32) -> exp2 ->
+//                 partial row sum -> bf16 -> tcgen05.st P over the same TMEM columns (P aliases S) -> mbarrier.
+// TMEM (256 columns): S0 | S1 (64 fp32 columns each, P over columns [0,16) and [32,48): DOUBLE BUFFERED so S of chunk n + 1 is computed while the
+// softmax warps work on chunk n and the MMA round trip is off their critical path) | O (32 columns) | 2 columns for the row-sum exchange.
 // Tensor work per chunk: S = Q K^T as 1-2 MMAs (M 128, N 64, K 16), O += P V as 4 MMAs (M 128, N 32, K 16, A from TMEM):
 // ~250 tensor cycles against 512 MUFU cycles for the 8 k exponentials — the kernel is bound by the exponentials.
 #pragma once
@@ -25,7 +26,7 @@
 
 namespace lam {
 
-constexpr int kAtcThreads = 256;
+constexpr int kAtcThreads = 384;
 constexpr int kAtcChunk = 64;   // keys per S tile
 
 __host__ __device__ inline int atc_s128(int S) { return (S + 127) & ~127; }
@@ -69,6 +70,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  return v;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // One 128-key chunk of one query row: S (fp32, TMEM) -> exp2 -> row-sum partials -> bf16 P written over the same columns.
@@ -92,22 +101,17 @@ __device__ __forceinline__ void atc_softmax_sub(const uint32_t* sv, uint32_t p_c
   }
   tmem_st8(p_col, pk);  // P over S: these columns only cover sub-chunks that are already in registers
 }
+// this thread's 32 keys of the chunk: s_col / p_col point at its S columns (fp32) and P columns (bf16 pairs); key0 = index of its
+// first key inside the chunk
 template <int POLY, bool MASKED>
-__device__ __forceinline__ void atc_softmax_chunk(uint32_t s_col, int key_lim, float& l0, float& l1, float& l2, float& l3) {
-  // 16 columns per TMEM load, two loads in flight; the loop is unrolled by two only (static register indices, bounded live
-  // ranges: the kernel runs at 128 registers per thread for two CTAs per SM)
+__device__ __forceinline__ void atc_softmax_chunk(uint32_t s_col, uint32_t p_col, int key0, int key_lim, float& l0, float& l1, float& l2,
+                                                  float& l3) {
   uint32_t sa[16], sb[16];
   tmem_ld16(s_col, sa);
+  tmem_ld16(s_col + 16, sb);
   tmem_ld_wait();
-#pragma unroll 1
-  for (int jj = 0; jj < kAtcChunk / 32; ++jj) {
-    tmem_ld16(s_col + 32 * jj + 16, sb);  // in flight while sub-chunk 2 jj is processed
-    atc_softmax_sub<POLY, MASKED>(sa, s_col + 16 * jj, 32 * jj, key_lim, l0, l1, l2, l3);
-    tmem_ld_wait();
-    if (jj + 1 < kAtcChunk / 32) tmem_ld16(s_col + 32 * jj + 32, sa);
-    atc_softmax_sub<POLY, MASKED>(sb, s_col + 16 * jj + 8, 32 * jj + 16, key_lim, l0, l1, l2, l3);
-    tmem_ld_wait();
-  }
+  atc_softmax_sub<POLY, MASKED>(sa, p_col, key0, key_lim, l0, l1, l2, l3);
+  atc_softmax_sub<POLY, MASKED>(sb, p_col + 8, key0 + 16, key_lim, l0, l1, l2, l3);
 }
 
 // POLY: of every 8 exponentials, POLY are evaluated on the FMA pipe (poly_exp2) instead of MUFU.EX2.
@@ -149,7 +153,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
     mbar_init(o_done, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 8);
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
     }
@@ -221,7 +225,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
 #pragma unroll
         for (int s = 0; s < kAtcChunk / 16; ++s) {
           const uint64_t b = umma_desc_nosw(v_addr + (c * (kAtcChunk / 8) + 2 * s) * KG, v_lbo, v_sbo);
-          umma_bf16_ts(tmem_base + 2 * kAtcChunk, tmem_base + (n & 1) * kAtcChunk + s * 8, b, idesc_pv, (c | s) != 0);
+          umma_bf16_ts(tmem_base + 2 * kAtcChunk, tmem_base + (n & 1) * kAtcChunk + (s >> 1) * 32 + (s & 1) * 8, b, idesc_pv, (c | s) != 0);
         }
         if (c == nchunks - 1) umma_commit(o_done);
       }
@@ -246,46 +250,61 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
       if (lane == 0) mbar_arrive(&q_full[t & 1]);
     }
   } else if (warp >= 4) {
-    // ===== softmax: thread = query row =====
+    // ===== softmax: thread = (query row, half of the chunk's keys) =====
     const int quarter = warp & 3;
-    const uint32_t s_col0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t o_col = s_col0 + 2 * kAtcChunk;
+    const int half = (warp - 4) >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_col = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t n = 0;
     for (int t = 0; t < ntiles; ++t) {
-      const int qrow = t * 128 + quarter * 32 + lane;
+      const int qrow = t * 128 + row;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       for (int c = 0; c < nchunks; ++c, ++n) {
         mbar_wait(&s_full[n & 1], (n >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t s_col = s_col0 + (n & 1) * kAtcChunk;
+        const uint32_t buf = lane_col + (n & 1) * kAtcChunk;
         const int key_lim = S - c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count: last chunk only
-        if (key_lim >= kAtcChunk) atc_softmax_chunk<POLY, false>(s_col, key_lim, l0, l1, l2, l3);
-        else atc_softmax_chunk<POLY, true>(s_col, key_lim, l0, l1, l2, l3);
+        // each half overwrites only ITS OWN S columns with P (columns [32 h, 32 h + 16)), so the two warps that share a TMEM lane
+        // quarter never touch each other's data and need no synchronisation inside a chunk
+        if (key_lim >= kAtcChunk) atc_softmax_chunk<POLY, false>(buf + 32 * half, buf + 32 * half, 32 * half, key_lim, l0, l1, l2, l3);
+        else atc_softmax_chunk<POLY, true>(buf + 32 * half, buf + 32 * half, 32 * half, key_lim, l0, l1, l2, l3);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[n & 1]);
       }
-      // ---- O of this tile: normalise, store bf16
+      // ---- O of this tile: exchange the partial row sums, normalise, store bf16 (half h writes d in [16 h, 16 h + 16))
+      // (through two spare TMEM columns of this lane: the two halves of a row are the same lane of two different warps)
+      const float l_mine = (l0 + l1) + (l2 + l3);
+      const uint32_t l_col = lane_col + 2 * kAtcChunk + 32;
+      tmem_st1(l_col + half, __float_as_uint(l_mine));
+      tmem_st_wait();
+      tcgen05_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tcgen05_fence_after();
+      const float l_other = __uint_as_float(tmem_ld1(l_col + (half ^ 1)));
       mbar_wait(o_done, t & 1);
       tcgen05_fence_after();
-      uint32_t ov[32];
-      tmem_ld32(o_col, ov);
+      uint32_t ov[16];
+      tmem_ld16(lane_col + 2 * kAtcChunk + 16 * half, ov);
       tmem_ld_wait();
-      const float inv = 1.f / ((l0 + l1) + (l2 + l3));
+      const float inv = 1.f / (l_mine + l_other);
       if (qrow < S) {
-        __nv_bfloat16* op = out + (size_t)(base + (long long)qrow * sm.seq_stride) * ldo + hh * HD;
+        __nv_bfloat16* op = out + (size_t)(base + (long long)qrow * sm.seq_stride) * ldo + hh * HD + 16 * half;
 #pragma unroll
-        for (int d = 0; d < HD; d += 8) {
-          uint4 o4;
-          o4.x = pack_bf16x2(__uint_as_float(ov[d + 0]) * inv, __uint_as_float(ov[d + 1]) * inv);
-          o4.y = pack_bf16x2(__uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv);
-          o4.z = pack_bf16x2(__uint_as_float(ov[d + 4]) * inv, __uint_as_float(ov[d + 5]) * inv);
-          o4.w = pack_bf16x2(__uint_as_float(ov[d + 6]) * inv, __uint_as_float(ov[d + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + d) = o4;
+        for (int d = 0; d < 16; d += 8) {
+          if (16 * half + d < HD) {
+            uint4 o4;
+            o4.x = pack_bf16x2(__uint_as_float(ov[d + 0]) * inv, __uint_as_float(ov[d + 1]) * inv);
+            o4.y = pack_bf16x2(__uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv);
+            o4.z = pack_bf16x2(__uint_as_float(ov[d + 4]) * inv, __uint_as_float(ov[d + 5]) * inv);
+            o4.w = pack_bf16x2(__uint_as_float(ov[d + 6]) * inv, __uint_as_float(ov[d + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + d) = o4;
+          }
         }
       }
       tcgen05_fence_before();  // O is read: the next tile's first P V (ordered behind this thread's next P) may overwrite it
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // both halves have read the exchanged sums before they are rewritten
     }
   }
 

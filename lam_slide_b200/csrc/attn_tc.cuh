@@ -101,19 +101,6 @@ __device__ __forceinline__ void atc_softmax_sub(const uint32_t* sv, uint32_t p_c
   }
   tmem_st8(p_col, pk);  // P over S: these columns only cover sub-chunks that are already in registers
 }
-// this thread's 32 keys of the chunk: s_col / p_col point at its S columns (fp32) and P columns (bf16 pairs); key0 = index of its
-// first key inside the chunk
-template <int POLY, bool MASKED>
-__device__ __forceinline__ void atc_softmax_chunk(uint32_t s_col, uint32_t p_col, int key0, int key_lim, float& l0, float& l1, float& l2,
-                                                  float& l3) {
-  uint32_t sa[16], sb[16];
-  tmem_ld16(s_col, sa);
-  tmem_ld16(s_col + 16, sb);
-  tmem_ld_wait();
-  atc_softmax_sub<POLY, MASKED>(sa, p_col, key0, key_lim, l0, l1, l2, l3);
-  atc_softmax_sub<POLY, MASKED>(sb, p_col + 8, key0 + 16, key_lim, l0, l1, l2, l3);
-}
-
 // POLY: of every 8 exponentials, POLY are evaluated on the FMA pipe (poly_exp2) instead of MUFU.EX2.
 // variant bits (debug aid, lamslide_debug_attention mode 3 + 4 * variant): 1 = swap LBO / SBO of the Q / K descriptors,
 // 2 = swap LBO / SBO of the V descriptor.  0 is the layout derived from the canonical UMMA layouts (verified on B200).
@@ -262,17 +249,32 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
       for (int c = 0; c < nchunks; ++c, ++n) {
         mbar_wait(&s_full[n & 1], (n >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t buf = lane_col + (n & 1) * kAtcChunk;
-        const int key_lim = S - c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count: last chunk only
         // each half overwrites only ITS OWN S columns with P (columns [32 h, 32 h + 16)), so the two warps that share a TMEM lane
         // quarter never touch each other's data and need no synchronisation inside a chunk
-        if (key_lim >= kAtcChunk) atc_softmax_chunk<POLY, false>(buf + 32 * half, buf + 32 * half, 32 * half, key_lim, l0, l1, l2, l3);
-        else atc_softmax_chunk<POLY, true>(buf + 32 * half, buf + 32 * half, 32 * half, key_lim, l0, l1, l2, l3);
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[n & 1]);
+        const uint32_t buf = lane_col + (n & 1) * kAtcChunk + 32 * half;
+        uint32_t sa[16], sb[16];
+        tmem_ld16(buf, sa);
+        tmem_ld16(buf + 16, sb);
+        if (c > 0) {  // hand chunk n - 1's P to the MMA warp now: its stores have long drained, so nothing stalls here
+          tmem_st_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[(n - 1) & 1]);
+        }
+        tmem_ld_wait();
+        const int key_lim = S - c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count: last chunk only
+        if (key_lim >= kAtcChunk) {
+          atc_softmax_sub<POLY, false>(sa, buf, 32 * half, key_lim, l0, l1, l2, l3);
+          atc_softmax_sub<POLY, false>(sb, buf + 8, 32 * half + 16, key_lim, l0, l1, l2, l3);
+        } else {
+          atc_softmax_sub<POLY, true>(sa, buf, 32 * half, key_lim, l0, l1, l2, l3);
+          atc_softmax_sub<POLY, true>(sb, buf + 8, 32 * half + 16, key_lim, l0, l1, l2, l3);
+        }
       }
+      tmem_st_wait();  // last chunk of the tile
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[(n - 1) & 1]);
       // ---- O of this tile: exchange the partial row sums, normalise, store bf16 (half h writes d in [16 h, 16 h + 16))
       // (through two spare TMEM columns of this lane: the two halves of a row are the same lane of two different warps)
       const float l_mine = (l0 + l1) + (l2 + l3);

@@ -619,9 +619,13 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
   if (mode == 2 && !seq_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the whole-sequence attention kernel", sm.S);
   // tcgen05 kernel (attn_tc.cuh): long sequences with bounded logits; mode 3 + 4 * variant forces it (tests / layout probes)
   const size_t tc_smem = AtcCfg<HD>::smem_bytes(sm.S);
-  static const bool no_tc = env_flag("LAMSLIDE_NO_ATTN_TC");
+  // Measured on B200 (4AA temporal attention, 128 sequences x 16 heads, S = 1000, hd = 24): 755 us against 677 us for the mma.sync
+  // whole-sequence kernel — S has to come back from TMEM through tcgen05.ld (measured 100 B/clk/SM, scripts/ldtm_bench.cu), which
+  // costs 0.31 ms on top of the 0.48 ms of MUFU exponentials, and the two did not overlap in any of the variants tried.  The
+  // tcgen05 kernel is therefore opt-in (LAMSLIDE_ATTN_TC=1); tests exercise it through mode 3.
+  static const bool use_tc = env_flag("LAMSLIDE_ATTN_TC");
   const bool tc_forced = (mode & 3) == 3;
-  const bool tc_ok = tc_smem <= 232448 && (tc_forced || (mode == 0 && !no_tc && !legacy_attn && sm.S >= 384 && logit_bound > 0.f &&
+  const bool tc_ok = tc_smem <= 232448 && (tc_forced || (mode == 0 && use_tc && !legacy_attn && sm.S >= 384 && logit_bound > 0.f &&
                                                           logit_bound <= kSeqKernelMaxLogit));
   if (tc_forced && !tc_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the tcgen05 attention kernel", sm.S);
   if (tc_ok) {

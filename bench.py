@@ -268,8 +268,13 @@ def main():
         ms_per_launch = prof[dom]["ms"] / n_launch
         achieved = flops[dom] / (ms_per_launch * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same config only)
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and args.config == "peptide" and B == DEFAULT_BATCH["peptide"] and T == 1000:
+            traffic = json.load(open(tpath)).get("kernels", {}).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": f"{peaks_src} bf16_tflops_sustained (kernel timed inside a long step)",
+                    "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)",
+                    "peak_source": f"{peaks_src} bf16_tflops_sustained (kernel timed inside a long step)",
                     "ms_per_launch": ms_per_launch, "launches_per_step": n_launch / pr_steps,
                     "share_of_step": shares.get(dom)}
         ftraj = flops_per_trajectory(cfg, args.num_steps)

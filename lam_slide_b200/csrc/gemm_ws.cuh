@@ -119,7 +119,8 @@ struct EpiLinear1Ws {
       fence_proxy_async();  // generic-proxy writes of every lane -> visible to the async proxy (TMA)
       __syncwarp();
       if (c.lane == 0 && !(p.debug & 1)) {
-        tma_store_2d_s(out == p.qkv ? c.o0 : c.o1, c.stage_s, col0, c.row0);
+        if (p.debug & 4) tma_store_2d_s_hint(out == p.qkv ? c.o0 : c.o1, c.stage_s, col0, c.row0, l2_policy_evict_first());
+        else tma_store_2d_s(out == p.qkv ? c.o0 : c.o1, c.stage_s, col0, c.row0);
         bulk_commit();
       }
       return;

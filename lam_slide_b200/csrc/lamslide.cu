@@ -1537,7 +1537,7 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
   int rc;
   if (legacy != 1) {
     typename EpiLinear1Ws<HD>::Params ep{bias, {}, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod,
-                                         legacy == 2 ? 1 : legacy == 3 ? 2 : legacy == 4 ? 3 : 0};
+                                         legacy == 2 ? 1 : legacy == 3 ? 2 : legacy == 4 ? 3 : legacy == 5 ? 4 : 0};
     {  // debug hook: the scales arrive as device pointers; fetch them once per distinct pointer pair (not thread-safe)
       static const float *last_q = nullptr, *last_k = nullptr;
       static float hq[32], hk[32];

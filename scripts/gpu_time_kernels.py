@@ -81,7 +81,7 @@ def linear1():
     gk = torch.ones(24, device="cuda")
     qkv = torch.empty(rows, 3 * H, device="cuda", dtype=torch.bfloat16)
     act = torch.empty(rows, H + M, device="cuda", dtype=torch.bfloat16)
-    for mode, name in [(32, "full, 2-CTA multicast"), (48, "full, 1 CTA"), (34, "math, no stores"), (35, "stores, no math"), (36, "no math, no stores"), (1, "legacy kernel")]:
+    for mode, name in [(32, "full, 2-CTA multicast"), (48, "full, 1 CTA"), (34, "math, no stores"), (35, "stores, no math"), (36, "no math, no stores"), (37, "full, evict-first stores"), (1, "legacy kernel")]:
         us = time_fn(lambda: L.check(lib.lamslide_debug_linear1(u.data_ptr(), w1.data_ptr(), bias.data_ptr(), gq.data_ptr(), gk.data_ptr(),
                                                                 qkv.data_ptr(), act.data_ptr(), rows, H, M, heads, 2, 1000, 10000.0, mode, st)))
         print(f"linear1 rows={rows} [{name}]: {us:8.1f} us  {2.0 * rows * (3 * H + M) * H / us * 1e-6:7.1f} TFLOP/s", flush=True)

@@ -73,6 +73,78 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs a) {
   }
 }
 
+// Same contract, 128 x 64 tile, 8 x 4 outputs per thread, 16-byte global loads (K fastest), register-staged double buffering of the
+// shared-memory k-slices.  Needs K % 4 == 0, ldx % 4 == 0 and 16-byte aligned X / W rows; the launcher falls back to the kernel
+// above otherwise (e.g. the 106-wide peptide feature rows).
+__global__ void __launch_bounds__(256) linear_f32_v2_kernel(LinearArgs a) {
+  constexpr int BM = 128, BN = 64, BK = 16;
+  __shared__ __align__(16) float Xs[2][BK][BM + 4];
+  __shared__ __align__(16) float Ws[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int ty = tid >> 4, tx = tid & 15;  // rows ty*8..+7, cols tx*4..+3
+  // global -> register staging: X tile 128 x 16 = 512 float4 (2 per thread), W tile 64 x 16 = 256 float4 (1 per thread)
+  const int xr0 = tid >> 2, xk = (tid & 3) * 4;  // X rows xr0 and xr0 + 64
+  const int wn = tid >> 2;
+  float4 xa, xb, wv;
+  auto gload = [&](int k0) {
+    const int k = k0 + xk;
+    const bool kin = k < a.K;  // K % 4 == 0: a float4 is all-in or all-out
+    const int ra = r0 + xr0, rb = ra + 64, n = n0 + wn;
+    xa = (kin && ra < a.rows) ? *reinterpret_cast<const float4*>(a.X + (size_t)ra * a.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xb = (kin && rb < a.rows) ? *reinterpret_cast<const float4*>(a.X + (size_t)rb * a.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    wv = (kin && n < a.N) ? __ldg(reinterpret_cast<const float4*>(a.W + (size_t)n * a.K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto sstore = [&](int buf) {
+    Xs[buf][xk + 0][xr0] = xa.x, Xs[buf][xk + 1][xr0] = xa.y, Xs[buf][xk + 2][xr0] = xa.z, Xs[buf][xk + 3][xr0] = xa.w;
+    Xs[buf][xk + 0][xr0 + 64] = xb.x, Xs[buf][xk + 1][xr0 + 64] = xb.y, Xs[buf][xk + 2][xr0 + 64] = xb.z, Xs[buf][xk + 3][xr0 + 64] = xb.w;
+    Ws[buf][xk + 0][wn] = wv.x, Ws[buf][xk + 1][wn] = wv.y, Ws[buf][xk + 2][wn] = wv.z, Ws[buf][xk + 3][wn] = wv.w;
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int nk = (a.K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * BK);  // in flight during the FMAs below
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&Xs[buf][kk][ty * 8]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&Xs[buf][kk][ty * 8 + 4]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&Ws[buf][kk][tx * 4]);
+      const float xr[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w}, wr[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], wr[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);  // the other buffer was last read in iteration kt - 1 (barrier at its end)
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty * 8 + i;
+    if (r >= a.rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.N) continue;
+      float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
+      if (a.gelu) v = gelu_exact(v);
+      if (a.rowadd) v += a.rowadd[(size_t)(r % a.rowadd_period) * a.ldra + n];
+      if (a.res) v += a.res[(size_t)r * a.ldr + n];
+      a.Y[(size_t)r * a.ldy + n] = v;
+    }
+  }
+}
+
 // ---- LayerNorm over rows (nn.LayerNorm semantics, eps given, optional affine), out-of-place with pitches; warp per row.
 // x_bcast_period > 0: the input row is x[r % period] (used to normalise the learned latents once per frame without
 // materialising the broadcast — encoder.py:39).

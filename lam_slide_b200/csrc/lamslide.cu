@@ -1218,8 +1218,15 @@ static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, 
   a.X = X, a.ldx = ldx, a.W = L.w, a.bias = L.b, a.Y = Y, a.ldy = ldy, a.res = res, a.ldr = ldr;
   a.rowadd = rowadd, a.rowadd_period = period > 0 ? period : 1, a.ldra = ldra;
   a.rows = (int)rows, a.N = L.out, a.K = L.in, a.gelu = gelu ? 1 : 0;
-  dim3 grid(cdiv(L.out, 64), cdiv(rows, 64));
-  linear_f32_kernel<<<grid, 256, 0, st>>>(a);
+  static const bool legacy_fs = env_flag("LAMSLIDE_LEGACY_FS_LINEAR");
+  const bool vec_ok = !legacy_fs && L.in % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)L.w & 15) == 0;
+  if (vec_ok) {
+    dim3 grid(cdiv(L.out, 64), cdiv(rows, 128));
+    linear_f32_v2_kernel<<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid(cdiv(L.out, 64), cdiv(rows, 64));
+    linear_f32_kernel<<<grid, 256, 0, st>>>(a);
+  }
   LAUNCH_CHECK();
   return 0;
 }

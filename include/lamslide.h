@@ -181,6 +181,13 @@ int lamslide_debug_linear2(const void* act_bf16, const void* w2_bf16, const floa
 int lamslide_debug_gemm_mainloop(const void* a_bf16, const void* b_bf16, int32_t rows, int32_t N, int32_t K, int32_t block_n,
                                  void* stream);
 
+/* the fused "MLP half of linear1 + GELU + linear2 + gated residual" kernel in isolation (mmdit.py:241-248, latent_si_v31.py:54):
+ * h [rows,H] fp32 += gate[row / rows_per_sample] * ([act[:, :H] | gelu(u w1[3H:]^T + b1[3H:])] w2^T + b2);
+ * u [rows,H], act [rows,H+M], w1 [3H+M,H], w2 [H,H+M] device bf16; b1 [3H+M], b2 [H], gate [n_samples,H] device fp32. */
+int lamslide_debug_fused_mlp(const void* u_bf16, const void* act_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1,
+                             const float* b2, const float* gate, float* h, int32_t rows, int32_t H, int32_t M,
+                             int32_t rows_per_sample, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ SYMBOLS = [
     "lamslide_backbone_forward", "lamslide_ode_sample", "lamslide_euler_step", "lamslide_setup_conditioning",
     "lamslide_first_stage_create", "lamslide_first_stage_destroy", "lamslide_first_stage_workspace_bytes",
     "lamslide_encode", "lamslide_decode", "lamslide_debug_gemm", "lamslide_debug_attention",
-    "lamslide_debug_linear1", "lamslide_debug_linear2", "lamslide_debug_gemm_mainloop",
+    "lamslide_debug_linear1", "lamslide_debug_linear2", "lamslide_debug_gemm_mainloop", "lamslide_debug_fused_mlp",
     "lamslide_profile_begin", "lamslide_profile_end",
 ]
 
@@ -101,6 +101,7 @@ def load() -> C.CDLL:
     lib.lamslide_debug_linear1.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.c_float, i32, vp]
     lib.lamslide_debug_linear2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.lamslide_debug_gemm_mainloop.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.lamslide_debug_fused_mlp.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.lamslide_profile_end.argtypes = [C.c_char_p, sz]
     if lib.lamslide_abi_version() != 1:
         raise LamSlideError("liblamslide.so ABI version mismatch")

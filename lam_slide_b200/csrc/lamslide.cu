@@ -20,6 +20,7 @@
 #include "../../include/lamslide.h"
 #include "gemm_tc.cuh"
 #include "gemm_ws.cuh"
+#include "mlp_fused.cuh"
 #include "attn.cuh"
 #include "attn_tc.cuh"
 #include "elementwise.cuh"
@@ -293,7 +294,8 @@ struct BlockWeights {
   float gq_h[32] = {0}, gk_h[32] = {0};  // host copies of the QK-norm scales (passed by value to the persistent linear1 kernel)
   float logit_bound = 0.f;  // max |q.k| * hd^-0.5 * log2(e) after QK-RMSNorm: hd^0.5 * log2(e) * max|gq| * max|gk|
   CUtensorMap tm_w1, tm_w2;
-  CUtensorMap tm_w1_h, tm_w2_h;  // boxes of half a tile: 2-CTA clusters fetch half a weight tile each and multicast it
+  CUtensorMap tm_w1_h, tm_w2_h;  // boxes of half a tile: in a CTA pair each CTA stages half of every weight tile
+  CUtensorMap tm_w1_u, tm_w2_u;  // 128-row x 64-column units of the fused MLP kernel (mlp_fused.cuh)
 };
 
 struct lamslide_backbone {
@@ -499,6 +501,8 @@ extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, con
       TRY(make_tmap(&bw.tm_w2, bw.w2, H, H + M, bn2));
       TRY(make_tmap(&bw.tm_w1_h, bw.w1, 3 * H + M, H, bn1 / 2));
       TRY(make_tmap(&bw.tm_w2_h, bw.w2, H, H + M, bn2 / 2));
+      TRY(make_tmap(&bw.tm_w1_u, bw.w1, 3 * H + M, H, 128));
+      TRY(make_tmap(&bw.tm_w2_u, bw.w2, H, H + M, 128));
     }
   }
   {
@@ -568,7 +572,7 @@ static int launch_linear2(const lamslide_backbone* bb, const CUtensorMap& ta, co
 template <int HD>
 static int launch_linear1_ws(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, const CUtensorMap& qkv_st,
                              const CUtensorMap& act_st, int rows, const typename EpiLinear1Ws<HD>::Params& ep, cudaStream_t st) {
-  const int N = 3 * bb->H + bb->M, K = bb->H;
+  const int N = 3 * bb->H + ep.M, K = bb->H;  // ep.M = 0: q | k | v only (the MLP half runs in the fused kernel)
   if constexpr (HD == 24) {
     if (bb->bn1 == 192) return launch_gemm_ws<192, EpiLinear1Ws<24>>(ta, bw.tm_w1, &bw.tm_w1_h, qkv_st, act_st, rows, N, K, ep, st);
   } else {
@@ -589,6 +593,29 @@ static int launch_linear2_ws(const lamslide_backbone* bb, const CUtensorMap& ta,
     case 64: return launch_gemm_ws<64, EpiLinear2Ws>(ta, bw.tm_w2, &bw.tm_w2_h, h_red, h_red, rows, N, K, ep, st);
     default: return 1;
   }
+}
+
+// fused MLP half of linear1 + GELU + linear2 + gated residual (mlp_fused.cuh).  Returns 1 when the shape is not covered.
+static int fused_mlp_stages(int H, int M) {
+  if (H % 128 != 0 || H > 384 || M % 128 != 0 || M <= 0) return 0;
+  for (int s = 8; s >= 3; --s)
+    if (fused_mlp_smem(H, M, s).total <= 232448) return s;
+  return 0;
+}
+static int launch_fused_mlp(const CUtensorMap& tm_u, const CUtensorMap& tm_attn, const CUtensorMap& tm_w1u, const CUtensorMap& tm_w2u,
+                            const CUtensorMap& tm_h, int rows, const FusedMlpParams& p, cudaStream_t st) {
+  const int stages = fused_mlp_stages(p.H, p.M);
+  if (!stages) return 1;
+  const FusedMlpSmem plan = fused_mlp_smem(p.H, p.M, stages);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  const int mblocks = cdiv(rows, kBlockM);
+  mlp_fused_kernel<<<std::min(num_sms(), mblocks), kWsThreads, plan.total, st>>>(tm_u, tm_attn, tm_w1u, tm_w2u, tm_h, mblocks, stages, p);
+  LAUNCH_CHECK();
+  return 0;
 }
 
 static int launch_plain(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int rows, int N, int K, const EpiPlain::Params& ep,
@@ -790,6 +817,10 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   }
   // 3. layers
   static const bool legacy_gemm = env_flag("LAMSLIDE_LEGACY_GEMM");  // A/B switch: one-tile-per-CTA GEMM kernels
+  static const bool no_fused = env_flag("LAMSLIDE_NO_FUSED_MLP");    // A/B switch: separate linear1 (full) + linear2 kernels
+  // fused MLP path: linear1 computes q | k | v only; the MLP half, the GELU and linear2 run in mlp_fused_kernel
+  const bool fused = !legacy_gemm && !no_fused && fused_mlp_stages(H, M) > 0 && (3 * H) % bb->bn1 == 0 &&
+                     (bb->bn1 == 192 || bb->bn1 == 128 || (bb->bn1 == 64 && hd == 16));
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)hd));
   for (int i = 0; i < bb->depth; ++i) {
     for (int s = 0; s < 2; ++s) {
@@ -816,7 +847,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   ProfScope ps(PC_LINEAR1, st);                                                                                          \
   int r1 = 1;                                                                                                            \
   if (!legacy_gemm) {                                                                                                    \
-    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, {}, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, 0};                                \
+    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, {}, cs, sn, w.qkv, w.act, H, fused ? 0 : M, n, pos_div, pos_mod, 0};                    \
     for (int j = 0; j < HD_; ++j) epw.gam[0][j] = bw.gq_h[j] * q_premul, epw.gam[1][j] = bw.gk_h[j];                                         \
     r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_qkv_st, fc.tm_act_st, n, epw, st);                                \
     if (r1 < 0) return r1;                                                                                               \
@@ -840,7 +871,11 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
       {
         ProfScope ps(PC_LINEAR2, st);
         int r2 = 1;
-        if (!legacy_gemm) {
+        if (fused) {
+          FusedMlpParams fp{bw.b1 + 3 * H, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, M, n};
+          r2 = launch_fused_mlp(fc.tm_u, fc.tm_act, bw.tm_w1_u, bw.tm_w2_u, fc.tm_h_red, n, fp, st);
+          if (r2 < 0) return r2;
+        } else if (!legacy_gemm) {
           EpiLinear2Ws::Params e2w{bw.b2, modl + 2 * H, bb->mod_width, T * L, H, n};
           r2 = launch_linear2_ws(bb, fc.tm_act, bw, fc.tm_h_red, n, e2w, st);
           if (r2 < 0) return r2;
@@ -1644,5 +1679,23 @@ extern "C" int lamslide_debug_gemm_mainloop(const void* a_bf16, const void* b_bf
     default: return fail(LAMSLIDE_ERR_INVALID, "block_n %d unsupported", block_n);
   }
   if (rc == 1) return fail(LAMSLIDE_ERR_INVALID, "shape does not fit the persistent kernel");
+  return rc;
+}
+
+// fused MLP half + linear2 + gated residual in isolation (tests/test_gpu_kernels.py):  h += gate[b] * ([attn | gelu(u W1m^T + b1m)] W2^T + b2)
+// u [rows,H] bf16, act [rows,H+M] bf16 (only the attention half [:, :H] is read), w1 [3H+M,H] bf16, w2 [H,H+M] bf16, b1 [3H+M], b2 [H].
+extern "C" int lamslide_debug_fused_mlp(const void* u_bf16, const void* act_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1,
+                                        const float* b2, const float* gate, float* h, int32_t rows, int32_t H, int32_t M,
+                                        int32_t rows_per_sample, void* stream) {
+  if (!u_bf16 || !act_bf16 || !w1_bf16 || !w2_bf16 || !b1 || !b2 || !gate || !h) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  CUtensorMap tu, ta, tw1, tw2, th;
+  TRY(make_tmap(&tu, u_bf16, rows, H, kBlockM));
+  TRY(make_tmap(&ta, act_bf16, rows, H + M, kBlockM));
+  TRY(make_tmap(&tw1, w1_bf16, 3 * H + M, H, 128));
+  TRY(make_tmap(&tw2, w2_bf16, H, H + M, 128));
+  TRY(make_tmap_ex(&th, h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  FusedMlpParams fp{b1 + 3 * H, b2, gate, H, rows_per_sample, H, M, rows};
+  int rc = launch_fused_mlp(tu, ta, tw1, tw2, th, rows, fp, (cudaStream_t)stream);
+  if (rc == 1) return fail(LAMSLIDE_ERR_INVALID, "fused MLP kernel does not cover H %d M %d", H, M);
   return rc;
 }

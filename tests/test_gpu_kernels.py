@@ -203,3 +203,36 @@ def test_tcgen05_attention_matches_softmax_reference(B, T, L, H, heads, temporal
     assert float(out[:, H:].float().abs().max()) == 0.0
     assert max_rel(got, ref) < 2e-2
     assert float((got - ref).abs().mean() / ref.abs().mean()) < 5e-3
+
+
+@pytest.mark.parametrize("rows,H,M,rps", [
+    (1000, 384, 1536, 250), (20000 + 37, 384, 1536, 2000), (128 * 150, 384, 1536, 2000), (333, 256, 1024, 160), (777, 128, 256, 40),
+    (4096, 256, 512, 5760), (100, 384, 1536, 50),
+])
+def test_fused_mlp_linear2(rows, H, M, rps):
+    """h += gate[b] * ([attn | gelu(u W1m^T + b1m)] W2^T + b2): the MLP half of linear1, GELU and linear2 in one kernel
+    (mmdit.py:241-248, latent_si_v31.py:54) vs fp64 (with the hidden activation rounded to bf16 as the A operand)."""
+    L_ = _lib()
+    lib = L_.load()
+    g = torch.Generator(device="cpu").manual_seed(rows + M + 5)
+    nb = (rows + rps - 1) // rps
+    u = torch.randn(rows, H, generator=g).to(torch.bfloat16).cuda()
+    act = torch.randn(rows, H + M, generator=g).to(torch.bfloat16).cuda()  # only [:, :H] (attention output) is read
+    w1 = (torch.randn(3 * H + M, H, generator=g) / math.sqrt(H)).to(torch.bfloat16).cuda()
+    w2 = (torch.randn(H, H + M, generator=g) / math.sqrt(H + M)).to(torch.bfloat16).cuda()
+    b1 = (0.1 * torch.randn(3 * H + M, generator=g)).cuda()
+    b2 = (0.1 * torch.randn(H, generator=g)).cuda()
+    gate = torch.randn(nb, H, generator=g).cuda()
+    h0 = torch.randn(rows, H, generator=g).cuda()
+    h = h0.clone()
+    L_.check(lib.lamslide_debug_fused_mlp(u.data_ptr(), act.data_ptr(), w1.data_ptr(), w2.data_ptr(), b1.data_ptr(), b2.data_ptr(),
+                                          gate.data_ptr(), h.data_ptr(), rows, H, M, rps, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    pre = u.double() @ w1[3 * H:].double().t() + b1[3 * H:].double()
+    hid = (0.5 * pre * (1.0 + torch.erf(pre / math.sqrt(2.0)))).to(torch.bfloat16).double()
+    cat = torch.cat([act[:, :H].double(), hid], dim=1)
+    b_of_row = torch.arange(rows, device="cuda") // rps
+    ref = h0.double() + gate.double()[b_of_row] * (cat @ w2.double().t() + b2.double())
+    assert torch.isfinite(h).all()
+    assert max_rel(h, ref) < 2e-3  # bf16 rounding flips of the hidden activation (GELU fit 2.6e-5) only
+    assert float((h.double() - ref).abs().mean() / ref.abs().mean()) < 2e-4

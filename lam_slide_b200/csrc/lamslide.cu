@@ -295,7 +295,7 @@ struct BlockWeights {
   float logit_bound = 0.f;  // max |q.k| * hd^-0.5 * log2(e) after QK-RMSNorm: hd^0.5 * log2(e) * max|gq| * max|gk|
   CUtensorMap tm_w1, tm_w2;
   CUtensorMap tm_w1_h, tm_w2_h;  // boxes of half a tile: in a CTA pair each CTA stages half of every weight tile
-  CUtensorMap tm_w1_u, tm_w2_u;  // 128-row x 64-column units of the fused MLP kernel (mlp_fused.cuh)
+  CUtensorMap tm_w1_u, tm_w2_u;  // half-unit boxes of the fused MLP kernel (mlp_fused.cuh): 64 / NU/2 rows x 64 columns
 };
 
 struct lamslide_backbone {
@@ -501,8 +501,8 @@ extern "C" int lamslide_backbone_create(const lamslide_backbone_config* cfg, con
       TRY(make_tmap(&bw.tm_w2, bw.w2, H, H + M, bn2));
       TRY(make_tmap(&bw.tm_w1_h, bw.w1, 3 * H + M, H, bn1 / 2));
       TRY(make_tmap(&bw.tm_w2_h, bw.w2, H, H + M, bn2 / 2));
-      TRY(make_tmap(&bw.tm_w1_u, bw.w1, 3 * H + M, H, 128));
-      TRY(make_tmap(&bw.tm_w2_u, bw.w2, H, H + M, 128));
+      TRY(make_tmap(&bw.tm_w1_u, bw.w1, 3 * H + M, H, 64));
+      TRY(make_tmap(&bw.tm_w2_u, bw.w2, H, H + M, fused_mlp_out_unit(H) / 2));
     }
   }
   {
@@ -596,24 +596,45 @@ static int launch_linear2_ws(const lamslide_backbone* bb, const CUtensorMap& ta,
 }
 
 // fused MLP half of linear1 + GELU + linear2 + gated residual (mlp_fused.cuh).  Returns 1 when the shape is not covered.
-static int fused_mlp_stages(int H, int M) {
-  if (H % 128 != 0 || H > 384 || M % 128 != 0 || M <= 0) return 0;
-  for (int s = 8; s >= 3; --s)
-    if (fused_mlp_smem(H, M, s).total <= 232448) return s;
-  return 0;
+// ring depths of the fused MLP kernel (mlp_fused.cuh): stream 2 gets 4 stages (3 if tight), stream 1 what is left (3..6)
+static bool fused_mlp_stages(int H, int M, int* s1, int* s2) {
+  if (H % 128 != 0 || H > 384 || M % 128 != 0 || M <= 0) return false;
+  for (int b = 4; b >= 3; --b)
+    for (int a = 6; a >= 3; --a)
+      if (fused_mlp_smem(H, M, a, b).total <= 232448) {
+        *s1 = a, *s2 = b;
+        return true;
+      }
+  return false;
+}
+static bool fused_mlp_ok(int H, int M) {
+  int a, b;
+  return fused_mlp_stages(H, M, &a, &b);
 }
 static int launch_fused_mlp(const CUtensorMap& tm_u, const CUtensorMap& tm_attn, const CUtensorMap& tm_w1u, const CUtensorMap& tm_w2u,
-                            const CUtensorMap& tm_h, int rows, const FusedMlpParams& p, cudaStream_t st) {
-  const int stages = fused_mlp_stages(p.H, p.M);
-  if (!stages) return 1;
-  const FusedMlpSmem plan = fused_mlp_smem(p.H, p.M, stages);
+                            const CUtensorMap& tm_h, int rows, const FusedMlpParams& p_in, cudaStream_t st) {
+  int s1 = 0, s2 = 0;
+  if (!fused_mlp_stages(p_in.H, p_in.M, &s1, &s2)) return 1;
+  FusedMlpParams p = p_in;
+  if (const char* e = getenv("LAMSLIDE_FUSED_DEBUG")) p.debug = atoi(e);  // profiling aids (mlp_fused.cuh)
+  if (const char* e = getenv("LAMSLIDE_FUSED_STAGES")) s1 = std::max(2, std::min(s1, atoi(e))), s2 = std::max(2, std::min(s2, atoi(e)));
+  const FusedMlpSmem plan = fused_mlp_smem(p.H, p.M, s1, s2);
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     configured = true;
   }
   const int mblocks = cdiv(rows, kBlockM);
-  mlp_fused_kernel<<<std::min(num_sms(), mblocks), kWsThreads, plan.total, st>>>(tm_u, tm_attn, tm_w1u, tm_w2u, tm_h, mblocks, stages, p);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(std::min(num_sms() / 2 * 2, cdiv(mblocks, 2) * 2));
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = plan.total;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mlp_fused_kernel, tm_u, tm_attn, tm_w1u, tm_w2u, tm_h, mblocks, s1, s2, p));
   LAUNCH_CHECK();
   return 0;
 }
@@ -819,7 +840,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   static const bool legacy_gemm = env_flag("LAMSLIDE_LEGACY_GEMM");  // A/B switch: one-tile-per-CTA GEMM kernels
   static const bool no_fused = env_flag("LAMSLIDE_NO_FUSED_MLP");    // A/B switch: separate linear1 (full) + linear2 kernels
   // fused MLP path: linear1 computes q | k | v only; the MLP half, the GELU and linear2 run in mlp_fused_kernel
-  const bool fused = !legacy_gemm && !no_fused && fused_mlp_stages(H, M) > 0 && (3 * H) % bb->bn1 == 0 &&
+  const bool fused = !legacy_gemm && !no_fused && fused_mlp_ok(H, M) && (3 * H) % bb->bn1 == 0 &&
                      (bb->bn1 == 192 || bb->bn1 == 128 || (bb->bn1 == 64 && hd == 16));
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)hd));
   for (int i = 0; i < bb->depth; ++i) {
@@ -872,7 +893,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
         ProfScope ps(PC_LINEAR2, st);
         int r2 = 1;
         if (fused) {
-          FusedMlpParams fp{bw.b1 + 3 * H, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, M, n};
+          FusedMlpParams fp{bw.b1 + 3 * H, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, M, n, 0};
           r2 = launch_fused_mlp(fc.tm_u, fc.tm_act, bw.tm_w1_u, bw.tm_w2_u, fc.tm_h_red, n, fp, st);
           if (r2 < 0) return r2;
         } else if (!legacy_gemm) {
@@ -1691,10 +1712,10 @@ extern "C" int lamslide_debug_fused_mlp(const void* u_bf16, const void* act_bf16
   CUtensorMap tu, ta, tw1, tw2, th;
   TRY(make_tmap(&tu, u_bf16, rows, H, kBlockM));
   TRY(make_tmap(&ta, act_bf16, rows, H + M, kBlockM));
-  TRY(make_tmap(&tw1, w1_bf16, 3 * H + M, H, 128));
-  TRY(make_tmap(&tw2, w2_bf16, H, H + M, 128));
+  TRY(make_tmap(&tw1, w1_bf16, 3 * H + M, H, 64));
+  TRY(make_tmap(&tw2, w2_bf16, H, H + M, fused_mlp_out_unit(H) / 2));
   TRY(make_tmap_ex(&th, h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-  FusedMlpParams fp{b1 + 3 * H, b2, gate, H, rows_per_sample, H, M, rows};
+  FusedMlpParams fp{b1 + 3 * H, b2, gate, H, rows_per_sample, H, M, rows, 0};
   int rc = launch_fused_mlp(tu, ta, tw1, tw2, th, rows, fp, (cudaStream_t)stream);
   if (rc == 1) return fail(LAMSLIDE_ERR_INVALID, "fused MLP kernel does not cover H %d M %d", H, M);
   return rc;

@@ -149,6 +149,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// default semantics (release at CTA scope): orders this thread's earlier shared-memory writes / proxy fences before the arrival
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA tile load into THIS CTA's shared memory whose complete_tx goes to an mbarrier given by shared::cluster address — in a
 // CTA pair both producers signal the leader's barrier, which the (single) MMA issuer waits on.
 __device__ __forceinline__ void tma_load_2d_pair(const void* tmap, uint32_t bar_cluster_addr, void* smem_dst, int32_t c0, int32_t c1) {

@@ -87,7 +87,33 @@ def linear1():
         print(f"linear1 rows={rows} [{name}]: {us:8.1f} us  {2.0 * rows * (3 * H + M) * H / us * 1e-6:7.1f} TFLOP/s", flush=True)
 
 
+def fused():
+    """fused MLP + linear2 kernel of the 4AA config at B = 64, with the profiling knobs of mlp_fused.cuh"""
+    import math
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rows = int(sys.argv[2]) if len(sys.argv) > 2 else 128000
+    H, M = 384, 1536
+    u = torch.randn(rows, H, device="cuda").to(torch.bfloat16)
+    act = torch.randn(rows, H + M, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn(3 * H + M, H, device="cuda") / math.sqrt(H)).to(torch.bfloat16)
+    w2 = (torch.randn(H, H + M, device="cuda") / math.sqrt(H + M)).to(torch.bfloat16)
+    b1 = torch.randn(3 * H + M, device="cuda") * 0.1
+    b2 = torch.randn(H, device="cuda") * 0.1
+    gate = torch.randn(rows // 2000 + 1, H, device="cuda")
+    h = torch.zeros(rows, H, device="cuda")
+    flops = 2.0 * rows * (H * M + (H + M) * H)
+    for dbg, stages in [(0, 8), (0, 4), (0, 3), (1, 8), (2, 8), (4, 8), (5, 8), (8, 8), (15, 8), (9, 8)]:
+        os.environ["LAMSLIDE_FUSED_DEBUG"] = str(dbg)
+        os.environ["LAMSLIDE_FUSED_STAGES"] = str(stages)
+        us = time_fn(lambda: L.check(lib.lamslide_debug_fused_mlp(u.data_ptr(), act.data_ptr(), w1.data_ptr(), w2.data_ptr(), b1.data_ptr(),
+                                                                  b2.data_ptr(), gate.data_ptr(), h.data_ptr(), rows, H, M, 2000, st)), iters=10)
+        print(f"fused mlp rows={rows} debug={dbg} max_stages={stages}: {us:8.1f} us  {flops / us * 1e-6:7.1f} TFLOP/s", flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "fused":
+        return fused()
     if len(sys.argv) > 1 and sys.argv[1] == "attn":
         return attn()
     if len(sys.argv) > 1 and sys.argv[1] == "attn_tc":

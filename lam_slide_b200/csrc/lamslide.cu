@@ -596,15 +596,17 @@ static int launch_linear2_ws(const lamslide_backbone* bb, const CUtensorMap& ta,
 }
 
 // fused MLP half of linear1 + GELU + linear2 + gated residual (mlp_fused.cuh).  Returns 1 when the shape is not covered.
-// ring depths of the fused MLP kernel (mlp_fused.cuh): stream 2 gets 4 stages (3 if tight), stream 1 what is left (3..6)
+// ring depths of the fused MLP kernel (mlp_fused.cuh): ring 1 (16 KB stages) up to 4 deep, ring 2 what is left (3..6)
 static bool fused_mlp_stages(int H, int M, int* s1, int* s2) {
   if (H % 128 != 0 || H > 384 || M % 128 != 0 || M <= 0) return false;
-  for (int b = 4; b >= 3; --b)
-    for (int a = 6; a >= 3; --a)
-      if (fused_mlp_smem(H, M, a, b).total <= 232448) {
+  for (int a = 4; a >= 2; --a)
+    for (int b = 6; b >= 3; --b) {
+      const FusedMlpSmem plan = fused_mlp_smem(H, M, a, b);
+      if (plan.total <= 232448) {
         *s1 = a, *s2 = b;
         return true;
       }
+    }
   return false;
 }
 static bool fused_mlp_ok(int H, int M) {
@@ -617,6 +619,7 @@ static int launch_fused_mlp(const CUtensorMap& tm_u, const CUtensorMap& tm_attn,
   if (!fused_mlp_stages(p_in.H, p_in.M, &s1, &s2)) return 1;
   FusedMlpParams p = p_in;
   if (const char* e = getenv("LAMSLIDE_FUSED_DEBUG")) p.debug = atoi(e);  // profiling aids (mlp_fused.cuh)
+  if (const char* e = getenv("LAMSLIDE_FUSED_TRACE")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));  // device buffer, 3 x 4096 x 8 B
   if (const char* e = getenv("LAMSLIDE_FUSED_STAGES")) s1 = std::max(2, std::min(s1, atoi(e))), s2 = std::max(2, std::min(s2, atoi(e)));
   const FusedMlpSmem plan = fused_mlp_smem(p.H, p.M, s1, s2);
   static bool configured = false;
@@ -627,7 +630,9 @@ static int launch_fused_mlp(const CUtensorMap& tm_u, const CUtensorMap& tm_attn,
   const int mblocks = cdiv(rows, kBlockM);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
-  cfg.gridDim = dim3(std::min(num_sms() / 2 * 2, cdiv(mblocks, 2) * 2));
+  int grid_cap = num_sms();
+  if (const char* e = getenv("LAMSLIDE_FUSED_GRID")) grid_cap = std::max(2, std::min(grid_cap, atoi(e)));  // profiling aid
+  cfg.gridDim = dim3(std::min(grid_cap / 2 * 2, cdiv(mblocks, 2) * 2));
   cfg.blockDim = dim3(kFusedThreads);
   cfg.dynamicSmemBytes = plan.total;
   cfg.stream = st;
@@ -893,7 +898,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
         ProfScope ps(PC_LINEAR2, st);
         int r2 = 1;
         if (fused) {
-          FusedMlpParams fp{bw.b1 + 3 * H, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, M, n, 0};
+          FusedMlpParams fp{bw.b1 + 3 * H, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, M, n, nullptr, 0};
           r2 = launch_fused_mlp(fc.tm_u, fc.tm_act, bw.tm_w1_u, bw.tm_w2_u, fc.tm_h_red, n, fp, st);
           if (r2 < 0) return r2;
         } else if (!legacy_gemm) {
@@ -1715,7 +1720,7 @@ extern "C" int lamslide_debug_fused_mlp(const void* u_bf16, const void* act_bf16
   TRY(make_tmap(&tw1, w1_bf16, 3 * H + M, H, 64));
   TRY(make_tmap(&tw2, w2_bf16, H, H + M, fused_mlp_out_unit(H) / 2));
   TRY(make_tmap_ex(&th, h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-  FusedMlpParams fp{b1 + 3 * H, b2, gate, H, rows_per_sample, H, M, rows, 0};
+  FusedMlpParams fp{b1 + 3 * H, b2, gate, H, rows_per_sample, H, M, rows, nullptr, 0};
   int rc = launch_fused_mlp(tu, ta, tw1, tw2, th, rows, fp, (cudaStream_t)stream);
   if (rc == 1) return fail(LAMSLIDE_ERR_INVALID, "fused MLP kernel does not cover H %d M %d", H, M);
   return rc;

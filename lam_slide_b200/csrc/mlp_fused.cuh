@@ -11,21 +11,27 @@
 // and stages HALF of every weight unit, so per SM the weight bytes crossing the L2 -> SM port are halved (one CTA per m-block
 // needs 64 B/clk/SM of weights at full tensor rate; the L2 delivers ~42).
 // TMEM (512 columns): OUT accumulator 128 x H fp32 (H <= 384 columns) | ACC1 128 x 128 at column 384.
-// Shared memory: u tile resident (H/64 k-blocks of 16 KB), G = two 128 x 64 bf16 tiles (A operand of the second GEMM: first the
-// attention tile k-blocks by TMA, then the GELU output of each hidden chunk written by the epilogue warps in the 128-byte
-// swizzled layout), ring 1 of W1m half-units [64 rows x 64 k], ring 2 of W2 half-units [NU/2 rows x 64 k], constants, barriers.
+// Shared memory: u tile resident (H/64 k-blocks of 16 KB) | G = two 128 x 64 bf16 tiles (A operand of the second GEMM: the GELU
+// output of a hidden chunk, written by the epilogue warps in the 128-byte swizzled layout; also the staging area of the output
+// boxes) | ring 1 (16 KB stages: W1m half-units [64 rows x 128 k], and the attention tile k-blocks [128 x 64]) | ring 2 (W2
+// half-units [NU/2 rows x 64 k]) | constants (b1m, b2, the gate rows of this m-block) | barriers.
 //
 // Two independent MMA streams, each with its own producer warp, ring and issuing warp (measured, scripts/issue_bench.cu: the
-// wait / elect / 4 x UTCHMMA / commit sequence costs ~350 cycles of the issuing warp per unit, more than the 256 cycles an
-// N = 128 unit occupies the tensor pipe — one issuer for both streams left the pipe at 40 %):
-//     stream 1 (warps 0,1):  for each hidden chunk j (128 columns):  ACC1 = u W1m_j^T                (H/64 units, N = 128)
+// wait / elect / 4 x UTCHMMA / commit sequence costs ~350 cycles of the issuing warp per unit, more than the 256 cycles four
+// N = 128 MMAs occupy the tensor pipe — one issuer for both streams left the pipe at 40 %):
+//     stream 1 (warps 0,1):  for each hidden chunk j (128 columns):  ACC1 = u W1m_j^T     (units of 2 k-blocks = 8 MMAs, N = 128)
 //     stream 2 (warps 2,3):  OUT = attn W2[:, :H]^T ;  then per chunk j:  OUT += gelu(ACC1 + b1m_j) W2[:, H+128j ..]^T
-//                            (units of NU = 192 output columns for H = 384, else min(H, 256))
+//                            (units of NU = 192 output columns for H = 384, else min(H, 256); 4 MMAs each)
+// The attention tiles travel through ring 1 (between the W1m units of chunk 0 and chunk 1 of the same m-block), so they are
+// prefetched while the previous m-block drains and G stays free for the first GELU chunk.
 // Warps 4..19: epilogue (TMEM lane quarter = warp % 4, column quarter = (warp - 4) / 4): ACC1 -> + bias -> GELU -> bf16 -> G;
-// at the end of the m-block OUT -> gate * (acc + b2) -> TMA f32 reduce-add into h (staged in G).
+// at the end of the m-block OUT -> gate * (acc + b2) -> TMA f32 reduce-add into h (16-column x 32-row boxes staged in G; measured,
+// scripts/drain_bench.cu: 4.8 us per m-block alone, 12 us when all CTAs drain at once (HBM read-modify-write), against 6.4 / 16 us
+// for 8-column boxes and worse for red.global or ld+st from registers).
 // Barrier protocol in the pair (same offsets in both CTAs): "full" barriers live on the leader (both producers' TMA loads
 // complete_tx there, the leader arms 2x the bytes; both CTAs' epilogue warps arrive there), "empty" barriers are per CTA (the
-// leader's issuing threads commit to both CTAs).
+// leader's issuing threads commit to both CTAs).  Every waiter follows its barrier phase by phase (a parity wait cannot tell
+// phases two apart).
 #pragma once
 #include "gemm_ws.cuh"
 
@@ -40,6 +46,7 @@ struct FusedMlpParams {
   int gate_stride;
   int rows_per_sample;  // T * L
   int H, M, rows;
+  long long* trace;  // profiling aid: when set, CTA 0 records (tag << 48 | clock) events, 4096 slots per role (see TRACE below)
   int debug;  // profiling aid: 1 skip the GELU math, 2 skip the output reduce-add, 4 skip the G tile writes, 8 skip the weight TMA loads
 };
 
@@ -53,20 +60,23 @@ static inline __host__ __device__ FusedMlpSmem fused_mlp_smem(int H, int M, int 
   FusedMlpSmem s;
   s.u_bytes = (H / 64) * 16384;
   s.g_bytes = 2 * 16384;
-  s.ring1_bytes = stages1 * 8192;
+  s.ring1_bytes = stages1 * 16384;
   s.ring2_bytes = (stages2 * fused_mlp_out_unit(H) * 64 + 1023) / 1024 * 1024;
-  s.const_bytes = ((M + H) * 4 + 15) / 16 * 16;
+  s.const_bytes = ((M + 3 * H) * 4 + 15) / 16 * 16;  // b1m | b2 | gate rows of two samples
   s.bar_bytes = 512;
   s.total = s.u_bytes + s.g_bytes + s.ring1_bytes + s.ring2_bytes + s.const_bytes + s.bar_bytes;
   return s;
 }
 
+// byte offset of (row r, 16-byte chunk c) inside a TMA-staged box with 32-byte rows (SWIZZLE_32B on the host side)
+__device__ __forceinline__ uint32_t stage_off32(int r, int c) { return r * 32 + ((c ^ ((r >> 2) & 1)) << 4); }
+
 __global__ void __launch_bounds__(kFusedThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_attn,
                  const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
                  const __grid_constant__ CUtensorMap tmap_h, int num_m_blocks, int stages1, int stages2, FusedMlpParams p) {
-  constexpr int kTile = 16384;   // one [128 x 64] bf16 tile (u k-block, G tile)
-  constexpr int kUnit1 = 8192;   // this CTA's half of a W1m unit: [64 rows x 64 k]
+  constexpr int kTile = 16384;   // one [128 x 64] bf16 tile (u k-block, G tile, attention tile) = one ring-1 stage
+  constexpr int kUnit1 = 16384;  // this CTA's half of a W1m unit: [64 rows x 128 k] as two 128-byte-swizzled [64 x 64] boxes
   const int H = p.H, M = p.M;
   const int KB = H / 64;               // k-blocks of u / attn
   const int NU = fused_mlp_out_unit(H);
@@ -79,10 +89,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const FusedMlpSmem plan = fused_mlp_smem(H, M, stages1, stages2);
   uint8_t* u_res = smem;
-  uint8_t* g_buf = u_res + plan.u_bytes;   // two 16 KB tiles (also the staging area of the final epilogue)
+  uint8_t* g_buf = u_res + plan.u_bytes;
   uint8_t* ring1 = g_buf + plan.g_bytes;
   uint8_t* ring2 = ring1 + plan.ring1_bytes;
-  float* smf = reinterpret_cast<float*>(ring2 + plan.ring2_bytes);  // [M] b1m | [H] b2
+  float* smf = reinterpret_cast<float*>(ring2 + plan.ring2_bytes);  // [M] b1m | [H] b2 | [2][H] gate
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smf) + plan.const_bytes);
   uint64_t* full1 = bars;            // [8] ring 1                      (leader)
   uint64_t* empty1 = bars + 8;       // [8]                             (per CTA)
@@ -90,18 +100,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
   uint64_t* empty2 = bars + 24;      // [8]                             (per CTA)
   uint64_t* a_full = bars + 32;      // [8] u k-blocks                  (leader)
   uint64_t* a_empty = bars + 40;     // [8]                             (per CTA)
-  uint64_t* ga_full = bars + 48;     // [2] attention tile in G slot    (leader; TMA of both CTAs)
-  uint64_t* gg_full = bars + 50;     // [2] GELU output in G slot       (leader; 8 warps of each CTA)
-  uint64_t* g_empty = bars + 52;     // [2] G slot consumed by the MMAs (per CTA)
-  uint64_t* acc1_full = bars + 54;   //                                 (per CTA)
-  uint64_t* acc1_empty = bars + 55;  //                                 (leader; 16 warps of each CTA)
-  uint64_t* out_full = bars + 56;    //                                 (per CTA)
-  uint64_t* out_free = bars + 57;    //                                 (leader; 16 warps of each CTA)
-  uint64_t* stage_free = bars + 58;  // G no longer used as staging     (per CTA; its 16 epilogue warps)
-  uint64_t* attn_done = bars + 59;   // OUT = attn W2a^T has consumed the last attention tile: G belongs to the GELU chunks (per CTA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 60);
+  uint64_t* gg_full = bars + 48;     // [2] GELU output in G tile       (leader; 8 warps of each CTA)
+  uint64_t* g_empty = bars + 50;     // [2] G tile consumed by the MMAs (per CTA)
+  uint64_t* acc1_full = bars + 52;   //                                 (per CTA)
+  uint64_t* acc1_empty = bars + 53;  //                                 (leader; 16 warps of each CTA)
+  uint64_t* out_full = bars + 54;    //                                 (per CTA)
+  uint64_t* out_free = bars + 55;    //                                 (leader; 16 warps of each CTA)
+  uint64_t* attn_done = bars + 56;   // the attention tiles of this m-block have left ring 1 (per CTA; issuer 1 waits on the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 57);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: TMA / MMA operands stay in uniform registers
   const int lane = threadIdx.x & 31;
   const int cta_rank = (int)cluster_ctarank();
   const bool leader = cta_rank == 0;
@@ -122,7 +130,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&ga_full[s], 1);
       mbar_init(&gg_full[s], 2 * (kWsEpiWarps / 2));  // the 8 warps of each CTA whose hidden columns fall into this 64-column tile
       mbar_init(&g_empty[s], 1);
     }
@@ -130,7 +137,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
     mbar_init(acc1_empty, 2 * kWsEpiWarps);
     mbar_init(out_full, 1);
     mbar_init(out_free, 2 * kWsEpiWarps);
-    mbar_init(stage_free, kWsEpiWarps);
     mbar_init(attn_done, 1);
     fence_barrier_init();
   }
@@ -146,59 +152,62 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_out = tmem_base;            // H columns
   const uint32_t tmem_acc1 = tmem_base + 384;     // 128 columns
+  // event trace of CTA 0 (roles: 0 epilogue warp 4, 1 issuer 1, 2 issuer 2)
+  int trace_n = 0;
+  auto TRACE = [&](int role, int tag) {
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 4095) {
+      p.trace[role * 4096 + 1 + trace_n] = (static_cast<long long>(tag) << 48) | (clock64() & 0xffffffffffffll);
+      p.trace[role * 4096] = ++trace_n;
+    }
+  };
+
+  // Ring 1 carries, per m-block and in this order: the W1m units of chunk 0 (KB/2 stages, consumed by issuer 1), the attention
+  // tile k-blocks (KB stages, consumed by issuer 2), the W1m units of chunks 1.. (consumed by issuer 1).  Each consumer skips
+  // the other's stages — but a parity wait cannot tell phases two apart, so neither may wait on a stage whose previous use (by
+  // the other consumer) is still outstanding: issuer 2 first waits for chunk 0's ACC1 (its units have then left the ring),
+  // issuer 1 waits for attn_done before it goes on to chunk 1.
+  auto ring1_skip = [&](int& s, uint32_t& ph, int n) {
+    s += n;
+    while (s >= stages1) s -= stages1, ph ^= 1;
+  };
 
   if (warp == 0) {
-    // ===== producer 1: u k-blocks (once per m-block) and W1m half-units, in the order stream 1 consumes them =====
+    // ===== producer 1: u k-blocks, W1m half-units and attention tiles, in ring-1 order =====
     int s = 0;
     uint32_t ph = 0, it = 0;
     for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++it) {
       const int m0 = (mbase + cta_rank) * kBlockM;  // may be past the end in the last sweep: the TMA zero-fills, nothing is stored
+      for (int kb = 0; kb < KB; ++kb) {  // u: its buffers are released by the last chunk of the previous m-block
+        mbar_wait(&a_empty[kb], (it & 1) ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&a_full[kb], 2 * kTile);
+          tma_load_2d_pair(&tmap_u, mapa_u32(smem_u32(&a_full[kb]), 0), u_res + kb * kTile, kb * 64, m0);
+        }
+        __syncwarp();
+      }
       for (int j = 0; j < NJ; ++j) {
-        for (int kb = 0; kb < KB; ++kb) {
-          if (j == 0) {  // u k-block kb: its buffer is released by the last chunk of the previous m-block
-            mbar_wait(&a_empty[kb], (it & 1) ^ 1);
-            if (elect_one()) {
-              if (leader) mbar_arrive_expect_tx(&a_full[kb], 2 * kTile);
-              tma_load_2d_pair(&tmap_u, mapa_u32(smem_u32(&a_full[kb]), 0), u_res + kb * kTile, kb * 64, m0);
-            }
-            __syncwarp();
-          }
+        for (int kb = 0; kb < KB; kb += 2) {
           mbar_wait(&empty1[s], ph ^ 1);
           if (elect_one()) {
             if (p.debug & 8) {
               if (leader) mbar_arrive(&full1[s]);
             } else {
               if (leader) mbar_arrive_expect_tx(&full1[s], 2 * kUnit1);
-              tma_load_2d_pair(&tmap_w1, mapa_u32(smem_u32(&full1[s]), 0), ring1 + s * kUnit1, kb * 64, 3 * H + j * 128 + cta_rank * 64);
+              const uint32_t bar = mapa_u32(smem_u32(&full1[s]), 0);
+              const int w_row = 3 * H + j * 128 + cta_rank * 64;
+              tma_load_2d_pair(&tmap_w1, bar, ring1 + s * kUnit1, kb * 64, w_row);
+              tma_load_2d_pair(&tmap_w1, bar, ring1 + s * kUnit1 + kUnit1 / 2, kb * 64 + 64, w_row);
             }
           }
           __syncwarp();
           if (++s == stages1) s = 0, ph ^= 1;
         }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== issuer 1 (leader): ACC1 = u W1m_j^T for every hidden chunk =====
-    if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, 128);
-      int s = 0;
-      uint32_t ph = 0, it = 0, n_acc1 = 0;
-      for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++it) {
-        for (int j = 0; j < NJ; ++j, ++n_acc1) {
-          mbar_wait(acc1_empty, (n_acc1 & 1) ^ 1);  // the epilogue warps of both CTAs have read the previous chunk
-          tcgen05_fence_after();
-          for (int kb = 0; kb < KB; ++kb) {
-            if (j == 0) mbar_wait(&a_full[kb], it & 1);
-            mbar_wait(&full1[s], ph);
-            tcgen05_fence_after();
-            const uint64_t a_desc = umma_desc_sw128(smem_u32(u_res + kb * kTile));
-            const uint64_t b_desc = umma_desc_sw128(smem_u32(ring1 + s * kUnit1));
+        if (j == 0) {
+          for (int kk = 0; kk < KB; ++kk) {
+            mbar_wait(&empty1[s], ph ^ 1);
             if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16_ss_pair(tmem_acc1, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-              umma_commit_pair(&empty1[s]);
-              if (j == NJ - 1) umma_commit_pair(&a_empty[kb]);
-              if (kb == KB - 1) umma_commit_pair(acc1_full);
+              if (leader) mbar_arrive_expect_tx(&full1[s], 2 * kTile);
+              tma_load_2d_pair(&tmap_attn, mapa_u32(smem_u32(&full1[s]), 0), ring1 + s * kTile, kk * 64, m0);
             }
             __syncwarp();
             if (++s == stages1) s = 0, ph ^= 1;
@@ -206,10 +215,56 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
         }
       }
     }
+  } else if (warp == 1) {
+    // ===== issuer 1 (leader): ACC1 = u W1m_j^T for every hidden chunk =====
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 128);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(u_res));  // the 14-bit address field (bytes >> 4) cannot carry: smem < 256 KB
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(ring1));
+      int s = 0;
+      uint32_t ph = 0, it = 0, n_acc1 = 0;
+      for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++it) {
+        for (int j = 0; j < NJ; ++j, ++n_acc1) {
+          mbar_wait(acc1_empty, (n_acc1 & 1) ^ 1);  // the epilogue warps of both CTAs have read the previous chunk
+          tcgen05_fence_after();
+          TRACE(1, 1);
+          for (int kb = 0; kb < KB; kb += 2) {  // one unit = two k-blocks = 8 MMAs (N = 128: 512 tensor-pipe cycles per wait/commit)
+            if (j == 0) {
+              mbar_wait(&a_full[kb], it & 1);
+              mbar_wait(&a_full[kb + 1], it & 1);
+            }
+            mbar_wait(&full1[s], ph);
+            tcgen05_fence_after();
+            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(kb * (kTile >> 4));
+            const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(s * (kUnit1 >> 4));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_bf16_ss_pair(tmem_acc1, a_desc + (k >> 2) * (kTile >> 4) + 2 * (k & 3), b_desc + (k >> 2) * (kUnit1 >> 5) + 2 * (k & 3),
+                                  idesc, (kb | k) != 0);
+              umma_commit_pair(&empty1[s]);
+              if (j == NJ - 1) {
+                umma_commit_pair(&a_empty[kb]);
+                umma_commit_pair(&a_empty[kb + 1]);
+              }
+              if (kb == KB - 2) umma_commit_pair(acc1_full);
+            }
+            __syncwarp();
+            if (++s == stages1) s = 0, ph ^= 1;
+          }
+          TRACE(1, 2);
+          if (j == 0) {  // the attention tiles (issuer 2)
+            mbar_wait(attn_done, it & 1);
+            TRACE(1, 3);
+            ring1_skip(s, ph, KB);
+          }
+        }
+      }
+    }
   } else if (warp == 2) {
-    // ===== producer 2: attention tiles into G and W2 half-units, in the order stream 2 consumes them =====
+    // ===== producer 2: W2 half-units, in the order stream 2 consumes them =====
     int s = 0;
-    uint32_t ph = 0, it = 0, g_use0 = 0, g_use1 = 0;  // writes into G slot 0 / 1 so far (TMA + epilogue)
+    uint32_t ph = 0;
     auto unit = [&](int row, int col) {
       mbar_wait(&empty2[s], ph ^ 1);
       if (elect_one()) {
@@ -223,39 +278,26 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
       __syncwarp();
       if (++s == stages2) s = 0, ph ^= 1;
     };
-    for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++it) {
-      const int m0 = (mbase + cta_rank) * kBlockM;
-      // the final epilogue of the previous m-block stages its output boxes in G: wait until it is done with them
-      mbar_wait(stage_free, (it & 1) ^ 1);
-      for (int kk = 0; kk < KB; ++kk) {  // attention tile k-block kk -> G slot kk & 1, then its NI weight units
-        const int slot = kk & 1;
-        mbar_wait(&g_empty[slot], ((slot ? g_use1 : g_use0) & 1) ^ 1);
-        if (slot) ++g_use1;
-        else ++g_use0;
-        if (elect_one()) {
-          if (leader) mbar_arrive_expect_tx(&ga_full[slot], 2 * kTile);
-          tma_load_2d_pair(&tmap_attn, mapa_u32(smem_u32(&ga_full[slot]), 0), g_buf + slot * kTile, kk * 64, m0);
-        }
-        __syncwarp();
+    for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step) {
+      for (int kk = 0; kk < KB; ++kk)
         for (int i = 0; i < NI; ++i) unit(i * NU, kk * 64);
-      }
-      for (int j = 0; j < NJ; ++j) {
+      for (int j = 0; j < NJ; ++j)
         for (int kk = 0; kk < 2; ++kk)
           for (int i = 0; i < NI; ++i) unit(i * NU, H + j * 128 + kk * 64);
-        ++g_use0, ++g_use1;  // the epilogue warps' writes of chunk j
-      }
     }
   } else if (warp == 3) {
     // ===== issuer 2 (leader): OUT = attn W2a^T, then OUT += gelu chunk j W2[:, H + 128 j ..]^T =====
     if (leader) {
       const uint32_t idesc = umma_idesc_bf16(256, NU);
-      int s = 0;
-      uint32_t ph = 0, it = 0, ga_use0 = 0, ga_use1 = 0, gg_use0 = 0, gg_use1 = 0;
-      auto mma_unit = [&](uint32_t d_tmem, uint32_t a_addr, bool first_zero) {
+      const uint64_t g_desc0 = umma_desc_sw128(smem_u32(g_buf));
+      const uint64_t t_desc0 = umma_desc_sw128(smem_u32(ring1));
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(ring2));
+      int s = 0, s1 = 0;
+      uint32_t ph = 0, ph1 = 0, it = 0, n_chunk = 0;
+      auto mma_unit = [&](uint32_t d_tmem, uint64_t a_desc, bool first_zero) {
         mbar_wait(&full2[s], ph);
         tcgen05_fence_after();
-        const uint64_t a_desc = umma_desc_sw128(a_addr);
-        const uint64_t b_desc = umma_desc_sw128(smem_u32(ring2 + s * kUnit2));
+        const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(s * (kUnit2 >> 4));
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (first_zero && k == 0) ? 0u : 1u);
@@ -265,32 +307,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
         if (++s == stages2) s = 0, ph ^= 1;
       };
       for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++it) {
+        TRACE(2, 1);
         mbar_wait(out_free, (it & 1) ^ 1);  // the previous m-block's OUT has been drained (both CTAs)
         tcgen05_fence_after();
+        TRACE(2, 2);
+        mbar_wait(acc1_full, n_chunk & 1);  // chunk 0 of this m-block is complete: its W1m units (issuer 1) have left ring 1
+        ring1_skip(s1, ph1, KB / 2);
         for (int kk = 0; kk < KB; ++kk) {
-          const int slot = kk & 1;
-          mbar_wait(&ga_full[slot], (slot ? ga_use1 : ga_use0) & 1);
-          if (slot) ++ga_use1;
-          else ++ga_use0;
+          mbar_wait(&full1[s1], ph1);
           tcgen05_fence_after();
-          for (int i = 0; i < NI; ++i) mma_unit(tmem_out + i * NU, smem_u32(g_buf + slot * kTile), kk == 0);
+          const uint64_t a_desc = t_desc0 + static_cast<uint64_t>(s1 * (kTile >> 4));
+          for (int i = 0; i < NI; ++i) mma_unit(tmem_out + i * NU, a_desc, kk == 0);
           if (elect_one()) {
-            umma_commit_pair(&g_empty[slot]);
+            umma_commit_pair(&empty1[s1]);
             if (kk == KB - 1) umma_commit_pair(attn_done);
           }
           __syncwarp();
+          if (++s1 == stages1) s1 = 0, ph1 ^= 1;
         }
-        for (int j = 0; j < NJ; ++j) {
+        TRACE(2, 3);
+        ring1_skip(s1, ph1, (NJ - 1) * (KB / 2));  // the W1m units of chunks 1.. (issuer 1)
+        for (int j = 0; j < NJ; ++j, ++n_chunk) {
           for (int kk = 0; kk < 2; ++kk) {
-            mbar_wait(&gg_full[kk], (kk ? gg_use1 : gg_use0) & 1);
-            if (kk) ++gg_use1;
-            else ++gg_use0;
+            mbar_wait(&gg_full[kk], n_chunk & 1);
             tcgen05_fence_after();
-            for (int i = 0; i < NI; ++i) mma_unit(tmem_out + i * NU, smem_u32(g_buf + kk * kTile), false);
+            TRACE(2, 4 + kk);
+            const uint64_t a_desc = g_desc0 + static_cast<uint64_t>(kk * (kTile >> 4));
+            for (int i = 0; i < NI; ++i) mma_unit(tmem_out + i * NU, a_desc, false);
             if (elect_one()) umma_commit_pair(&g_empty[kk]);
             __syncwarp();
           }
         }
+        TRACE(2, 6);
         if (elect_one()) umma_commit_pair(out_full);
         __syncwarp();
       }
@@ -307,15 +355,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
     const uint32_t acc1_empty_l = mapa_u32(smem_u32(acc1_empty), 0);  // the leader's barriers
     const uint32_t out_free_l = mapa_u32(smem_u32(out_free), 0);
     const uint32_t gg_full_l = mapa_u32(smem_u32(&gg_full[kk]), 0);
-    uint32_t it = 0, n_acc1 = 0, g_use_mine = 0;  // writes so far into the G tile this warp writes (TMA + epilogue)
+    const int etid = threadIdx.x - 128;
+    const int b_max = (p.rows - 1) / p.rows_per_sample;
+    uint32_t it = 0, n_chunk = 0;
     for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++it) {
-      const int row0 = (mbase + cta_rank) * kBlockM + q * 32;
+      const int m0 = (mbase + cta_rank) * kBlockM;
+      const int row0 = m0 + q * 32;
       const int row = row0 + lane;
+      // gate rows of the (at most two, unless rows_per_sample < 128) samples this m-block touches -> shared memory.  The named
+      // barrier also orders the previous m-block's staging boxes (each warp has waited for its own TMA reads) before G is rewritten.
+      const int b0 = (m0 < p.rows ? m0 : p.rows - 1) / p.rows_per_sample;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kWsEpiWarps) : "memory");
+      for (int i = etid; i < 2 * H; i += 32 * kWsEpiWarps) {
+        const int bb = b0 + (i >= H ? 1 : 0);
+        smf[M + H + i] = p.gate[(size_t)(bb < b_max ? bb : b_max) * p.gate_stride + (i >= H ? i - H : i)];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kWsEpiWarps) : "memory");
       // ---- hidden chunks: ACC1 -> +bias -> GELU -> bf16 -> G (A operand layout: 128-byte swizzle, K-major)
-      g_use_mine += kk ? KB / 2 : (KB + 1) / 2;  // the attention tiles (TMA) written into that G tile first
-      for (int j = 0; j < NJ; ++j, ++n_acc1) {
-        mbar_wait(acc1_full, n_acc1 & 1);
+      for (int j = 0; j < NJ; ++j, ++n_chunk) {
+        if (warp == 4) TRACE(0, 1);
+        mbar_wait(acc1_full, n_chunk & 1);
         tcgen05_fence_after();
+        if (warp == 4) TRACE(0, 2);
         uint32_t v[32];
         tmem_ld32(lane_t + 384 + cq * 32, v);
         tmem_ld_wait();
@@ -338,11 +399,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
           w[2 * i] = pack_bf16x2(y0, y1);
           w[2 * i + 1] = pack_bf16x2(y2, y3);
         }
-        // Stream 1 runs ahead of stream 2: chunk 0 may be ready while the attention tiles still cycle through G.  A parity wait
-        // only tells adjacent phases apart, so first wait for the end of the attention phase as such ...
-        if (j == 0) mbar_wait(attn_done, it & 1);
-        mbar_wait(&g_empty[kk], (g_use_mine & 1) ^ 1);  // ... then: the MMAs that read the previous content of this tile are done
-        ++g_use_mine;
+        if (warp == 4) TRACE(0, 3);
+        mbar_wait(&g_empty[kk], (n_chunk & 1) ^ 1);  // the MMAs that read the previous chunk out of this tile are done
+        if (warp == 4) TRACE(0, 4);
         const uint32_t tile = g_s + kk * kTile + r_in_tile * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -354,34 +413,43 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(gg_full_l);
       }
-      // ---- OUT: h += gate * (acc + b2) as TMA f32 reduce-add boxes of 16 columns, staged in G (free once out_full fired)
+      // ---- OUT: h += gate * (acc + b2) as TMA f32 reduce-add boxes of 16 columns x 32 rows, one staging box per warp in G
+      // (free once out_full fired: every MMA that reads G has completed)
+      if (warp == 4) TRACE(0, 5);
       mbar_wait(out_full, it & 1);
       tcgen05_fence_after();
+      if (warp == 4) TRACE(0, 6);
       const int b = (row < p.rows ? row : p.rows - 1) / p.rows_per_sample;
-      const float* gate = p.gate + (size_t)b * p.gate_stride;
+      const bool gate_in_smem = b - b0 <= 1;
+      const uint32_t gate_s = smf_s + (M + H + (b - b0) * H) * 4;
+      const float* gate_g = p.gate + (size_t)b * p.gate_stride;
       const int wcols = H / 4;  // this warp's output columns
       const uint32_t stage_s = g_s + (warp - 4) * 2048;
+      const int col0 = cq * wcols;
+      const bool issuer = elect_one();  // TMA issue, commit and wait all by the same (elected) lane
+      uint32_t v[16];
+      tmem_ld16(lane_t + col0, v);
       for (int bx = 0; bx < wcols / 16; ++bx) {
-        const int col = cq * wcols + bx * 16;
-        uint32_t v[16];
-        tmem_ld16(lane_t + col, v);
+        const int col = col0 + bx * 16;
         tmem_ld_wait();
-        if (bx == wcols / 16 - 1) {  // OUT is in registers: the next m-block's first MMAs may overwrite it
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(out_free_l);
-        }
         float4 o[4];
 #pragma unroll
         for (int jx = 0; jx < 4; ++jx) {
-          const float4 gv = __ldg(reinterpret_cast<const float4*>(gate + col) + jx);
+          const float4 gv = gate_in_smem ? ld_shared_f4(gate_s + col * 4 + jx * 16) : __ldg(reinterpret_cast<const float4*>(gate_g + col) + jx);
           const float4 bv = ld_shared_f4(smf_s + (M + col) * 4 + jx * 16);
           o[jx].x = gv.x * (__uint_as_float(v[4 * jx + 0]) + bv.x);
           o[jx].y = gv.y * (__uint_as_float(v[4 * jx + 1]) + bv.y);
           o[jx].z = gv.z * (__uint_as_float(v[4 * jx + 2]) + bv.z);
           o[jx].w = gv.w * (__uint_as_float(v[4 * jx + 3]) + bv.w);
         }
-        if (lane == 0) bulk_wait_read<0>();
+        if (bx + 1 < wcols / 16) {  // next 16 columns: TMEM load in flight while these are staged and stored
+          tmem_ld16(lane_t + col + 16, v);
+        } else {  // OUT is in registers: the next m-block's first MMAs may overwrite it
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(out_free_l);
+        }
+        if (issuer) bulk_wait_read<0>();  // the previous reduce-add has read the staging box
         __syncwarp();
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)
@@ -389,16 +457,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
                        __float_as_uint(o[ch].w));
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && !(p.debug & 2)) {
+        if (issuer && !(p.debug & 2)) {
           tma_reduce_add_2d_s(&tmap_h, stage_s, col, row0);
           bulk_commit();
         }
       }
-      if (lane == 0) {
-        bulk_wait_read<0>();
-        mbar_arrive(stage_free);  // G is free for the next m-block's attention tiles
-      }
+      if (issuer) bulk_wait_read<0>();  // before the named barrier at the top of the next m-block lets G be rewritten
       __syncwarp();
+      if (warp == 4) TRACE(0, 7);
     }
   }
 

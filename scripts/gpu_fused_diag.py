@@ -44,6 +44,52 @@ def run(rows, H, M, mode):
         print(f"  m-block {mb}: by 64-col group [{cols}]   by 32-row group [{rws}]")
 
 
+def trace(rows=128000, H=384, M=1536):
+    """event timeline of CTA 0 (LAMSLIDE_FUSED_TRACE): cycles between the events of the epilogue warp and the two issuers"""
+    lib = L.load()
+    u = torch.randn(rows, H, device="cuda").to(torch.bfloat16)
+    act = torch.randn(rows, H + M, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn(3 * H + M, H, device="cuda") / math.sqrt(H)).to(torch.bfloat16)
+    w2 = (torch.randn(H, H + M, device="cuda") / math.sqrt(H + M)).to(torch.bfloat16)
+    b1 = torch.randn(3 * H + M, device="cuda") * 0.1
+    b2 = torch.randn(H, device="cuda") * 0.1
+    gate = torch.randn(rows // 2000 + 1, H, device="cuda")
+    h = torch.zeros(rows, H, device="cuda")
+    buf = torch.zeros(3 * 4096, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    call = lambda: L.check(lib.lamslide_debug_fused_mlp(u.data_ptr(), act.data_ptr(), w1.data_ptr(), w2.data_ptr(), b1.data_ptr(), b2.data_ptr(),
+                                                        gate.data_ptr(), h.data_ptr(), rows, H, M, 2000, st))
+    call()
+    torch.cuda.synchronize()
+    os.environ["LAMSLIDE_FUSED_TRACE"] = str(buf.data_ptr())
+    call()
+    torch.cuda.synchronize()
+    del os.environ["LAMSLIDE_FUSED_TRACE"]
+    t = buf.cpu().view(3, 4096)
+    names = {0: {1: "wait acc1_full", 2: "got acc1_full", 3: "gelu done, wait g_empty", 4: "got g_empty", 5: "wait out_full", 6: "got out_full", 7: "drain done"},
+             1: {1: "acc1_empty ok -> issue G1", 2: "G1 issued", 3: "attn_done ok"},
+             2: {1: "wait out_free", 2: "out_free ok", 3: "attn phase issued", 4: "gg_full[0] ok", 5: "gg_full[1] ok", 6: "all issued"}}
+    ev = []
+    for r in range(3):
+        n = int(t[r, 0])
+        for i in range(n):
+            x = int(t[r, 1 + i])
+            ev.append((x & ((1 << 48) - 1), r, x >> 48))
+    ev.sort()
+    t0 = ev[0][0]
+    role = ["EPI ", "ISS1", "ISS2"]
+    last = {0: t0, 1: t0, 2: t0}
+    lim = int(sys.argv[2]) if len(sys.argv) > 2 else 260
+    for (c, r, tag) in ev[:lim]:
+        print(f"{c - t0:9d}  (+{c - last[r]:6d})  {'          ' * r}{role[r]} {names[r].get(tag, tag)}")
+        last[r] = c
+    print("total cycles", ev[-1][0] - t0, "events", len(ev))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "trace":
+    trace()
+    sys.exit(0)
+
 if __name__ == "__main__":
     rows, H, M = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (512, 384, 1536)
     for mode in ("attn_only", "mlp_only", "both"):

@@ -393,7 +393,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_empty = bars + 34;                            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: TMA / MMA operands stay in uniform registers
   const int lane = threadIdx.x & 31;
   const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;

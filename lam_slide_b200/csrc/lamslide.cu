@@ -696,6 +696,10 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
     // share of the exponentials evaluated on the FMA pipe (poly_exp2) instead of MUFU (of 16 per thread and key block).
     // Measured on B200 (4AA temporal attention): 0 -> 677 us, 2 -> 706, 4 -> 742, 8 -> 820: the kernel is issue-bound, so the
     // extra FMA-pipe instructions cost more than the MUFU slots they free.  Default 0.
+    // Also tried (B200, same shape): exponentials on packed f16x2 with f16 P.V and row sums from an extra "ones column" MMA — 677 us
+    // again with all-MUFU (ex2.approx.f16x2 compiles to TWO MUFU.EX2.F16, there is no packed MUFU), 729-855 us with 1/4 .. 4/4 of the
+    // pairs on an HFMA2 polynomial.  Legacy mma.sync peaks at 8.3 cycles per m16n8k16 and SM sub-partition (550 TFLOP/s,
+    // scripts/hmma_bench.cu): 14 HMMA + 16 MUFU per warp and 16-key block = 116 + 128 pipe cycles against 189 measured.
     static const int poly = getenv("LAMSLIDE_ATTN_POLY") ? atoi(getenv("LAMSLIDE_ATTN_POLY")) : 0;
     void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int) =
         poly == 0 ? attn_seq_kernel<HD, 0x0000u> : poly == 2 ? attn_seq_kernel<HD, 0x0808u> : poly == 6 ? attn_seq_kernel<HD, 0xA8A8u>

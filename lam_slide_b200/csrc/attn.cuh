@@ -214,8 +214,9 @@ struct AttnSeqCfg {
 
 // POLY_MASK: bit (mt * 8 + nt * 4 + e) set => that one of the 16 exponentials a thread evaluates per 16-key block is
 // computed with poly_exp2 on the FMA pipe instead of MUFU.EX2 (both pipes then run side by side).
-template <int HD, uint32_t POLY_MASK>
-__global__ void __launch_bounds__(256, 2)
+// MT: m16 tiles (16 query rows) per warp; the CTA has 16 / MT warps, i.e. always covers 256 query rows per pass.
+template <int HD, uint32_t POLY_MASK, int MT = 2>
+__global__ void __launch_bounds__(512 / MT, 2)
 attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, SeqMap sm, int heads) {
   using Cfg = AttnSeqCfg<HD>;
   constexpr int PITCH = Cfg::PITCH;
@@ -240,7 +241,7 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const __nv_bfloat16* vptr = qkv + 2 * H + hh * HD;
 
   // ---- K, V -> shared memory (rows >= S zero-filled)
-  for (int idx = tid; idx < S16 * CH; idx += 256) {
+  for (int idx = tid; idx < S16 * CH; idx += 512 / MT) {
     const int r = idx / CH, c = idx % CH;
     const bool ok = r < S;
     const size_t tok = (size_t)(base + (long long)(ok ? r : 0) * sm.seq_stride);
@@ -260,12 +261,12 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
   const uint32_t ks_base = smem_u32(Ks), vs_base = smem_u32(Vs);
   const int nkb = S16 / 16;
 
-  for (int q_base = warp * 32; q_base < S; q_base += 256) {
+  for (int q_base = warp * 16 * MT; q_base < S; q_base += 256) {
     // ---- Q fragments (two m16 tiles) straight from global memory
-    uint32_t aq[2][K16 > 0 ? K16 : 1][4];
-    uint32_t aq8[2][2];
+    uint32_t aq[MT][K16 > 0 ? K16 : 1][4];
+    uint32_t aq8[MT][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
       for (int hr = 0; hr < 2; ++hr) {
         const int row = q_base + mt * 16 + g + hr * 8;
@@ -279,10 +280,10 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         if constexpr (K8) aq8[mt][hr] = ok ? *reinterpret_cast<const uint32_t*>(qp + K16 * 16 + t * 2) : 0u;
       }
     }
-    float o[2][NT][4];
-    float l[2][2];
+    float o[MT][NT][4];
+    float l[MT][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       l[mt][0] = l[mt][1] = 0.f;
 #pragma unroll
       for (int d = 0; d < NT; ++d) o[mt][d][0] = o[mt][d][1] = o[mt][d][2] = o[mt][d][3] = 0.f;
@@ -297,9 +298,9 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 #pragma unroll
       for (int ks = 0; ks < K16; ++ks) ldmatrix_x4(kf[ks], ks_base + krow + k_lane_off + ks * 32);
       if constexpr (K8) ldmatrix_x2(kf8, ks_base + krow + k_lane_off8 + (K16 - 1) * 32);
-      float s[2][2][4];
+      float s[MT][2][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           mma_bf16_16816_z(s[mt][nt], aq[mt][0], kf[0][2 * nt], kf[0][2 * nt + 1]);
@@ -318,7 +319,7 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         vf[2 * (NT - 1)] = r0, vf[2 * (NT - 1) + 1] = r1;
       }
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
@@ -328,7 +329,7 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
       }
       if (kb == nkb - 1 && S16 != S) {  // zero the probabilities of the padding keys (zero-filled K rows give exp2(0) = 1)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -336,7 +337,7 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
               if (kb * 16 + nt * 8 + t * 2 + (e & 1) >= S) s[mt][nt][e] = 0.f;
       }
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         l[mt][0] += (s[mt][0][0] + s[mt][0][1]) + (s[mt][1][0] + s[mt][1][1]);
         l[mt][1] += (s[mt][0][2] + s[mt][0][3]) + (s[mt][1][2] + s[mt][1][3]);
         uint32_t ap[4];
@@ -351,7 +352,7 @@ attn_seq_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 
     // ---- finalize: row sums across the quad, normalise, store bf16
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
       for (int hr = 0; hr < 2; ++hr) {
         float lv = l[mt][hr];

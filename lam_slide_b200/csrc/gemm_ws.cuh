@@ -170,7 +170,14 @@ struct EpiLinear1Ws {
       emit(p, c, w, p.qkv, H3, col, ck);
       return;
     }
-    // ---- q or k: RMSNorm + RoPE over the head
+    // ---- q or k: RMSNorm + RoPE over the head.  Two instantiations so that the scales are compile-time-indexed constant-bank
+    // operands of the FMULs (a run-time q / k select made them 24 indexed LDC per chunk: 18 % of the kernel's stall samples).
+    if (t.kind == 0) rms_rope<0>(p, t, v, bias_s, w);
+    else rms_rope<1>(p, t, v, bias_s, w);
+    emit(p, c, w, p.qkv, H3, col, ck);
+  }
+  template <int IS_K>
+  static __device__ __forceinline__ void rms_rope(const Params& p, const Tile& t, const uint32_t* v, uint32_t bias_s, uint32_t* w) {
     float x[HD];
     float ss = 0.f;
 #pragma unroll
@@ -194,16 +201,13 @@ struct EpiLinear1Ws {
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
         const int j = 2 * j2 + h2;
-        const float4 gv = t.kind == 0 ? make_float4(p.gam[0][4 * j], p.gam[0][4 * j + 1], p.gam[0][4 * j + 2], p.gam[0][4 * j + 3])
-                                      : make_float4(p.gam[1][4 * j], p.gam[1][4 * j + 1], p.gam[1][4 * j + 2], p.gam[1][4 * j + 3]);
-        const float e0 = x[4 * j + 0] * gv.x, d0 = x[4 * j + 1] * gv.y;
-        const float e1 = x[4 * j + 2] * gv.z, d1 = x[4 * j + 3] * gv.w;
+        const float e0 = x[4 * j + 0] * p.gam[IS_K][4 * j], d0 = x[4 * j + 1] * p.gam[IS_K][4 * j + 1];
+        const float e1 = x[4 * j + 2] * p.gam[IS_K][4 * j + 2], d1 = x[4 * j + 3] * p.gam[IS_K][4 * j + 3];
         const float c0 = cc[2 * h2], s0 = sc[2 * h2], c1 = cc[2 * h2 + 1], s1 = sc[2 * h2 + 1];
         w[2 * j] = pack_bf16x2(fmaf(c0, e0, -s0 * d0), fmaf(s0, e0, c0 * d0));
         w[2 * j + 1] = pack_bf16x2(fmaf(c1, e1, -s1 * d1), fmaf(s1, e1, c1 * d1));
       }
     }
-    emit(p, c, w, p.qkv, H3, col, ck);
   }
   static __device__ __forceinline__ void finish(const WsCtx& c) {
     if (kTmaStore && c.lane == 0) bulk_wait_read<0>();  // staged boxes must be read out before the CTA's shared memory goes away
@@ -534,9 +538,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     c.smf_s = smem_u32(smf);
     c.lane = lane;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cq * QW;
-    uint32_t tmem_empty_addr[2];  // where this warp reports "accumulator drained": the leader's barriers
-    tmem_empty_addr[0] = CL > 1 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
-    tmem_empty_addr[1] = CL > 1 ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : smem_u32(&tmem_empty[1]);
+    // where this warp reports "accumulator drained": the leader's barriers (stage acc at + 8 * acc)
+    const uint32_t tmem_empty_addr = CL > 1 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
     uint32_t tile = 0;
     for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step) {
       const int mb = mbase + cta_rank;
@@ -559,7 +562,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) {
               if constexpr (CL == 1) mbar_arrive(&tmem_empty[acc]);
-              else mbar_arrive_cluster(tmem_empty_addr[acc]);
+              else mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
             }
           }
           Epi::chunk(ep, c, ts, v, n0w + ck * CW, ck);

@@ -701,15 +701,17 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
     // pairs on an HFMA2 polynomial.  Legacy mma.sync peaks at 8.3 cycles per m16n8k16 and SM sub-partition (550 TFLOP/s,
     // scripts/hmma_bench.cu): 14 HMMA + 16 MUFU per warp and 16-key block = 116 + 128 pipe cycles against 189 measured.
     static const int poly = getenv("LAMSLIDE_ATTN_POLY") ? atoi(getenv("LAMSLIDE_ATTN_POLY")) : 0;
+    // 16 query rows per warp and 16 warps per CTA (63 registers) instead of 32 rows x 8 warps: 661 us against 677 us (B200, 4AA)
+    static const int mt1 = getenv("LAMSLIDE_ATTN_MT1") ? atoi(getenv("LAMSLIDE_ATTN_MT1")) : 1;
     void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int) =
-        poly == 0 ? attn_seq_kernel<HD, 0x0000u> : poly == 2 ? attn_seq_kernel<HD, 0x0808u> : poly == 6 ? attn_seq_kernel<HD, 0xA8A8u>
+        mt1 ? attn_seq_kernel<HD, 0x0000u, 1> : poly == 0 ? attn_seq_kernel<HD, 0x0000u> : poly == 2 ? attn_seq_kernel<HD, 0x0808u> : poly == 6 ? attn_seq_kernel<HD, 0xA8A8u>
         : poly == 8 ? attn_seq_kernel<HD, 0xAAAAu> : attn_seq_kernel<HD, 0x8888u>;
     static const void* configured = nullptr;
     if (configured != (const void*)kern) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
       configured = (const void*)kern;
     }
-    kern<<<(unsigned)(n_seq * heads), 256, seq_smem, st>>>(qkv, out, H, ldo, sm, heads);
+    kern<<<(unsigned)(n_seq * heads), mt1 ? 512 : 256, seq_smem, st>>>(qkv, out, H, ldo, sm, heads);
   } else if (sm.S <= 32 && !force_flash) {
     long long items = (long long)n_seq * sm.S * heads;
     attn_small_kernel<HD><<<cdiv(items, 256), 256, 0, st>>>(qkv, out, H, ldo, heads, sm, items);

@@ -713,8 +713,16 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
     }
     kern<<<(unsigned)(n_seq * heads), mt1 ? 512 : 256, seq_smem, st>>>(qkv, out, H, ldo, sm, heads);
   } else if (sm.S <= 32 && !force_flash) {
-    long long items = (long long)n_seq * sm.S * heads;
-    attn_small_kernel<HD><<<cdiv(items, 256), 256, 0, st>>>(qkv, out, H, ldo, heads, sm, items);
+    // contiguous sequences whose q|k|v rows fit 8 warps x 6 KB of shared memory: warp per sequence (attn_rows_kernel)
+    static const bool legacy_small = env_flag("LAMSLIDE_LEGACY_SMALL_ATTN");
+    const bool contiguous = sm.seq_stride == 1 && sm.inner == 1 && sm.outer_stride == sm.S;
+    const size_t rows_smem = (size_t)8 * sm.S * 3 * H * 2;
+    if (!legacy_small && contiguous && rows_smem <= 48 * 1024 && ldo % 8 == 0 && H % 8 == 0) {
+      attn_rows_kernel<HD><<<(unsigned)cdiv((long long)n_seq, 8), 256, rows_smem, st>>>(qkv, out, H, ldo, heads, sm.S, n_seq);
+    } else {
+      long long items = (long long)n_seq * sm.S * heads;
+      attn_small_kernel<HD><<<cdiv(items, 256), 256, 0, st>>>(qkv, out, H, ldo, heads, sm, items);
+    }
   } else {
     int nqt = cdiv(sm.S, 128);
     dim3 grid((unsigned)(n_seq * nqt), heads);

@@ -7,6 +7,8 @@
 //   4  red.global.add.v4.f32 straight from registers (thread = row, 64 contiguous bytes per thread and box)
 //   5  ld.global.v4 + add + st.global.v4 straight from registers (rows are owned by the CTA: no atomicity needed)
 //   6  as 5 with all loads of the warp's 96 columns issued before the first store (6 x 16 registers)
+//   7  as 1 with two staging boxes per warp (reduce-adds of two boxes in flight)
+//   8  as 1 with all 16 warps' boxes of one column group issued by ONE thread after a CTA barrier (fewer, back-to-back TMA ops)
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I lam_slide_b200/csrc scripts/drain_bench.cu -lcuda -o /tmp/drain && /tmp/drain
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -56,6 +58,20 @@ __global__ void __launch_bounds__(512, 1) drain_kernel(const __grid_constant__ C
         if (issuer) {
           if (V == 1) tma_reduce_add_2d_s(&tm, s, col0 + bx * 16, row0);
           else tma_store_2d_s(&tm, s, col0 + bx * 16, row0);
+          bulk_commit();
+        }
+      }
+    } else if (V == 7) {
+      const uint32_t st = smem_u32(smem) + warp * 4096;
+      for (int bx = 0; bx < 6; ++bx) {
+        if (issuer) bulk_wait_read<1>();
+        __syncwarp();
+        const uint32_t s = st + (bx & 1) * 2048;
+        for (int ch = 0; ch < 4; ++ch) st_shared_v4(s + lane * 64 + ((ch ^ ((lane >> 1) & 3)) << 4), 1, 2, 3, 4);
+        fence_proxy_async();
+        __syncwarp();
+        if (issuer) {
+          tma_reduce_add_2d_s(&tm, s, col0 + bx * 16, row0);
           bulk_commit();
         }
       }
@@ -109,7 +125,7 @@ static CUtensorMap make_map(float* h, int rows, int box_cols, CUtensorMapSwizzle
 
 template <int V>
 void run(float* h, int rows, int grid, const char* name) {
-  const int box_cols = V == 0 ? 8 : (V == 2 ? 32 : 16);
+  const int box_cols = V == 0 ? 8 : (V == 2 ? 32 : 16);  // V == 7: 16
   const CUtensorMapSwizzle sw = V == 0 ? CU_TENSOR_MAP_SWIZZLE_32B : (V == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   CUtensorMap tm = make_map(h, rows, box_cols, sw);
   const int smem = 65536 + 1024;
@@ -146,6 +162,7 @@ int main() {
     run<4>(h, r, grid, "4 red.global.add.v4.f32 from registers");
     run<5>(h, r, grid, "5 ld + add + st from registers");
     run<6>(h, r, grid, "6 ld x24, then st x24");
+    run<7>(h, r, grid, "7 TMA reduce 16-col boxes x2");
   }
   return 0;
 }

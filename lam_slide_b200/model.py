@@ -127,3 +127,68 @@ class SecondStageSampler(nn.Module):
         x0 = torch.randn_like(model_kwargs["x_cond"]) if noise is None else noise.to(dev, non_blocking=True)
         latents = sample_fn(x0, self.forward, **model_kwargs)[-1]
         return self.decode(latents.flatten(0, 1), batch["entities"].flatten(0, 1), T=T)
+
+    def sample_stream(self, batches, noise: Optional[Tensor] = None):
+        """``sample()`` over an iterable of HOST batches (pinned memory), yielding pinned host tensors of the main output.
+        Same per-batch work as ``sample()`` (lightning_base.py:217-238), but the host->device copy of batch k + 1 and the
+        device->host copy of result k - 1 run on a second CUDA stream while batch k is being computed, so at steady state the
+        PCIe transfers cost no device time.  Results come out in order; each yielded tensor is valid until two more have been
+        produced (two rotating pinned buffers)."""
+        dev = self.device
+        main_key = self.cfg["main_output"]
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            # copy stream, two rotating sets of device input buffers and pinned result buffers, kept on the module between calls:
+            # no allocation at steady state (the caching allocator would otherwise cudaMalloc while blocks shared between the
+            # two streams are still in flight, and a pinned allocation costs milliseconds)
+            pipe = self.__dict__.setdefault("_pipe", {"side": torch.cuda.Stream(dev), "in": [None, None], "host": [None, None]})
+            side, in_bufs, host_bufs = pipe["side"], pipe["in"], pipe["host"]
+            in_free = [None, None]
+            side.wait_stream(main)
+
+            def upload(batch, slot):
+                with torch.cuda.stream(side):
+                    if in_free[slot] is not None:
+                        side.wait_event(in_free[slot])  # the compute that read this buffer set has finished
+                    tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
+                    cur = in_bufs[slot]
+                    if cur is None or any(k not in cur or cur[k].shape != v.shape or cur[k].dtype != v.dtype for k, v in tensors.items()):
+                        cur = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in tensors.items()}
+                        for t in cur.values():
+                            t.record_stream(main)
+                        in_bufs[slot] = cur
+                    for k, v in tensors.items():
+                        cur[k].copy_(v, non_blocking=True)
+                    d = dict(batch)
+                    d.update({k: cur[k] for k in tensors})
+                    return d, side.record_event()
+
+            it = iter(batches)
+            try:
+                nxt = upload(next(it), 0)
+            except StopIteration:
+                return
+            pending, k = None, 0
+            while nxt is not None:
+                cur, ready = nxt
+                try:
+                    nxt = upload(next(it), (k + 1) & 1)
+                except StopIteration:
+                    nxt = None
+                main.wait_event(ready)
+                out = self.sample(cur, noise=noise)[main_key]
+                done = main.record_event()
+                in_free[k & 1] = done
+                if host_bufs[k & 1] is None or host_bufs[k & 1].shape != out.shape:
+                    host_bufs[k & 1] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                with torch.cuda.stream(side):
+                    side.wait_event(done)
+                    host_bufs[k & 1].copy_(out, non_blocking=True)
+                    copied = side.record_event()
+                if pending is not None:
+                    pending[1].synchronize()
+                    yield pending[0]
+                pending = (host_bufs[k & 1], copied, out)  # `out` stays referenced until its copy has completed
+                k += 1
+            pending[1].synchronize()
+            yield pending[0]

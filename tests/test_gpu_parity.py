@@ -139,6 +139,25 @@ def test_public_sample_api_host_batch():
     assert rmsd(out["pos"].cpu(), fx["outputs"]["pos"]) < RMSD_TOL
 
 
+def test_sample_stream_matches_sample():
+    """sample_stream (host batches in, pinned host results out, copies overlapped with compute on a second stream) returns
+    exactly what sample() returns, batch by batch and in order."""
+    c = CASE_BY_NAME["nba_full"]
+    cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)
+    m = _build(cfg, fs_sd, bb_sd)
+    batches = []
+    for i in range(4):
+        b = {k: v.clone() for k, v in batch.items()}
+        b["pos"] = b["pos"] + 0.01 * i
+        batches.append({k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in b.items()})
+    want = [m.sample({k: v.clone() for k, v in b.items()}, noise=noise)["pos"].cpu() for b in batches]
+    got = [o.clone() for o in m.sample_stream(({k: v for k, v in b.items()} for b in batches), noise=noise)]
+    assert len(got) == len(want)
+    for g_, w_ in zip(got, want):
+        assert torch.equal(g_, w_)
+    assert not torch.equal(want[0], want[1])
+
+
 def test_errors_are_loud():
     import lam_slide_b200 as P
     with pytest.raises(ValueError):

@@ -13,12 +13,12 @@ cat gpurun_out/bench.json >> $LOG; tail -5 gpurun_out/bench.err >> $LOG
 if [ -z "$SKIP_NCU" ]; then
 echo "######## ncu launch list" >> $LOG
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile $BENCH_ARGS > gpurun_out/ncu_bench.log 2>&1
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log >> $LOG
 wc -l gpurun_out/launches.csv >> $LOG
 echo "######## ncu full: linear1 / linear2 / attention" >> $LOG
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_ws_kernel|mlp_fused_kernel|attn_seq_kernel|attn_rows_kernel|ln_modulate_kernel|linear_f32_v2_kernel' -s 120 -c 14 -f -o gpurun_out/prof_top \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile $BENCH_ARGS > gpurun_out/ncu_full.log 2>&1
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log >> $LOG
 ls -la gpurun_out >> $LOG
 fi

@@ -145,6 +145,118 @@ __global__ void __launch_bounds__(256) linear_f32_v2_kernel(LinearArgs a) {
   }
 }
 
+// Same contract on the (legacy) tensor path with fp32 accuracy: 3xTF32.  Every operand is split into a TF32 head and a TF32 tail
+// (x = hi + lo, both exactly representable), and x.w is accumulated as lo.hi + hi.lo + hi.hi with mma.sync.m16n8k8 (fp32
+// accumulate) — the dropped lo.lo term is 2^-22 relative, i.e. the result is as good as an fp32 FMA chain (the reference's
+// first stage is fp32 and its outputs are checked to 1e-4).  128 x 64 CTA tile, 8 warps of 32 x 32 (2 m16 x 4 n8 tiles),
+// 16-deep k slices staged through registers into K-contiguous shared-memory rows (pitch 20 floats: conflict-free fragment
+// loads).  Per k8 step a warp issues 24 MMAs for 16 k flop of useful work: ~90 TFLOP/s of fp32-accurate throughput against
+// ~31 TFLOP/s for the FMA kernel above (B200).  Needs K % 4 == 0, ldx % 4 == 0, 16-byte aligned rows, N % 2 == 0, ldy % 2 == 0.
+// hi = x truncated to TF32 (10 explicit mantissa bits), lo = x - hi (exact in fp32; the MMA reads only its upper 19 bits, a
+// 2^-11 relative truncation of lo = 2^-21 of x).  (cvt.rna.tf32.f32 is emulated on sm_100a — ~6 instructions with its NaN / Inf
+// handling, which made the first version of this kernel issue-bound: 277 instructions per k8 step for 24 MMAs.)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_1688(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__global__ void __launch_bounds__(256, 2) linear_f32_tc_kernel(LinearArgs a) {
+  constexpr int BM = 128, BN = 64, BK = 16, P = BK + 4;
+  __shared__ __align__(16) float Xs[2][BM][P];
+  __shared__ __align__(16) float Ws[2][BN][P];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;  // warp tile origin inside the CTA tile
+  const int r0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int xr0 = tid >> 2, xk = (tid & 3) * 4;  // staging: X rows xr0 and xr0 + 64, W row xr0 (tid < 256 -> 64 rows)
+  float4 xa, xb, wv;
+  auto gload = [&](int k0) {
+    const int k = k0 + xk;
+    const bool kin = k < a.K;  // K % 4 == 0: a float4 is all-in or all-out
+    const int ra = r0 + xr0, rb = ra + 64, n = n0 + xr0;
+    xa = (kin && ra < a.rows) ? *reinterpret_cast<const float4*>(a.X + (size_t)ra * a.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xb = (kin && rb < a.rows) ? *reinterpret_cast<const float4*>(a.X + (size_t)rb * a.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    wv = (kin && n < a.N) ? __ldg(reinterpret_cast<const float4*>(a.W + (size_t)n * a.K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto sstore = [&](int buf) {
+    *reinterpret_cast<float4*>(&Xs[buf][xr0][xk]) = xa;
+    *reinterpret_cast<float4*>(&Xs[buf][xr0 + 64][xk]) = xb;
+    *reinterpret_cast<float4*>(&Ws[buf][xr0][xk]) = wv;
+  };
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+  const int nk = (a.K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * BK);  // in flight during the MMAs below
+#pragma unroll
+    for (int k8 = 0; k8 < BK; k8 += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* xp = &Xs[buf][wm + mt * 16 + g][k8 + t];
+        split_tf32(xp[0], ah[mt][0], al[mt][0]);
+        split_tf32(xp[8 * P], ah[mt][1], al[mt][1]);
+        split_tf32(xp[4], ah[mt][2], al[mt][2]);
+        split_tf32(xp[8 * P + 4], ah[mt][3], al[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* wp = &Ws[buf][wn + nt * 8 + g][k8 + t];
+        split_tf32(wp[0], bh[nt][0], bl[nt][0]);
+        split_tf32(wp[4], bh[nt][1], bl[nt][1]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma_tf32_1688(acc[mt][nt], al[mt], bh[nt]);
+          mma_tf32_1688(acc[mt][nt], ah[mt], bl[nt]);
+          mma_tf32_1688(acc[mt][nt], ah[mt], bh[nt]);
+        }
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);  // the other buffer was last read in iteration kt - 1 (barrier at its end)
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int r = r0 + wm + mt * 16 + g + hr * 8;
+      if (r >= a.rows) continue;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = n0 + wn + nt * 8 + t * 2;
+        if (n >= a.N) continue;  // N % 2 == 0: a column pair is all-in or all-out
+        float v0 = acc[mt][nt][2 * hr] + (a.bias ? a.bias[n] : 0.f);
+        float v1 = acc[mt][nt][2 * hr + 1] + (a.bias ? a.bias[n + 1] : 0.f);
+        if (a.gelu) v0 = gelu_exact(v0), v1 = gelu_exact(v1);
+        if (a.rowadd) {
+          const float* ra = a.rowadd + (size_t)(r % a.rowadd_period) * a.ldra + n;
+          v0 += ra[0], v1 += ra[1];
+        }
+        if (a.res) {
+          const float* rs = a.res + (size_t)r * a.ldr + n;
+          v0 += rs[0], v1 += rs[1];
+        }
+        *reinterpret_cast<float2*>(a.Y + (size_t)r * a.ldy + n) = make_float2(v0, v1);
+      }
+    }
+}
+
 // ---- LayerNorm over rows (nn.LayerNorm semantics, eps given, optional affine), out-of-place with pitches; warp per row.
 // x_bcast_period > 0: the input row is x[r % period] (used to normalise the learned latents once per frame without
 // materialising the broadcast — encoder.py:39).

@@ -1295,7 +1295,13 @@ static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, 
   a.rows = (int)rows, a.N = L.out, a.K = L.in, a.gelu = gelu ? 1 : 0;
   static const bool legacy_fs = env_flag("LAMSLIDE_LEGACY_FS_LINEAR");
   const bool vec_ok = !legacy_fs && L.in % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)L.w & 15) == 0;
-  if (vec_ok) {
+  static const bool no_tc = env_flag("LAMSLIDE_FS_NO_TF32X3");
+  const bool tc_ok = vec_ok && !no_tc && L.out % 2 == 0 && ldy % 2 == 0 && ((uintptr_t)Y & 7) == 0 && (!res || (ldr % 2 == 0 && ((uintptr_t)res & 7) == 0)) &&
+                     rows >= 4096;  // tiny problems stay on the FMA kernel (launch-bound either way)
+  if (tc_ok) {
+    dim3 grid(cdiv(L.out, 64), cdiv(rows, 128));
+    linear_f32_tc_kernel<<<grid, 256, 0, st>>>(a);
+  } else if (vec_ok) {
     dim3 grid(cdiv(L.out, 64), cdiv(rows, 128));
     linear_f32_v2_kernel<<<grid, 256, 0, st>>>(a);
   } else {

@@ -27,7 +27,8 @@
 // Warps 4..19: epilogue (TMEM lane quarter = warp % 4, column quarter = (warp - 4) / 4): ACC1 -> + bias -> GELU -> bf16 -> G;
 // at the end of the m-block OUT -> gate * (acc + b2) -> TMA f32 reduce-add into h (16-column x 32-row boxes staged in G; measured,
 // scripts/drain_bench.cu: 4.8 us per m-block alone, 12 us when all CTAs drain at once (HBM read-modify-write), against 6.4 / 16 us
-// for 8-column boxes and worse for red.global or ld+st from registers).
+// for 8-column boxes and worse for red.global or ld+st from registers; sending 1..6 of a warp's 6 boxes through red.global.add.v4
+// next to the TMA path made the kernel 1..11 % slower).
 // Barrier protocol in the pair (same offsets in both CTAs): "full" barriers live on the leader (both producers' TMA loads
 // complete_tx there, the leader arms 2x the bytes; both CTAs' epilogue warps arrive there), "empty" barriers are per CTA (the
 // leader's issuing threads commit to both CTAs).  Every waiter follows its barrier phase by phase (a parity wait cannot tell

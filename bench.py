@@ -138,7 +138,12 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg['name']} sample(): T={cfg['T']}, num_steps={args.num_steps}, batch={B} (bounded CPU sample)"},
+        # the native arm's workload (same trajectories: T, entities, latents, num_steps); a step here is a bounded sample of it
+        "config": {"workload": f"{args.config} sample(): encode + Euler ODE (num_steps={args.num_steps} => {args.num_steps - 1} evals) + decode",
+                   "batch_per_step": B, "T": cfg["T"], "entities": cfg["N"], "latents": cfg["first_stage"]["encoder"]["num_latents"],
+                   "latent_dim": cfg["backbone"]["in_dim"], "parallelism": f"host threads x{cores}",
+                   "weights": "random-init (seeded), zero-init layers re-drawn N(0,0.02)",
+                   "sample": f"bounded CPU sample: {B} trajectory(ies) per step instead of {DEFAULT_BATCH.get(args.config, B)}"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{len(times)} x sample() of {B} trajectory(ies), fp32 torch CPU ops, {cores} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256, 2) linear_f32_tc_kernel(LinearArgs a) {
         if (n >= a.N) continue;  // N % 2 == 0: a column pair is all-in or all-out
         float v0 = acc[mt][nt][2 * hr] + (a.bias ? a.bias[n] : 0.f);
         float v1 = acc[mt][nt][2 * hr + 1] + (a.bias ? a.bias[n + 1] : 0.f);
-        if (a.gelu) v0 = gelu_exact(v0), v1 = gelu_exact(v1);
+        if (a.gelu) v0 = gelu_erf(v0), v1 = gelu_erf(v1);  // erf to 3e-7 abs in ~14 instructions (libm erff: ~40, half of this kernel at K = 128)
         if (a.rowadd) {
           const float* ra = a.rowadd + (size_t)(r % a.rowadd_period) * a.ldra + n;
           v0 += ra[0], v1 += ra[1];

@@ -158,6 +158,39 @@ def test_sample_stream_matches_sample():
     assert not torch.equal(want[0], want[1])
 
 
+def test_full_size_batch_properties():
+    """BASELINE.json's full configuration (4AA peptides, T = 1000, B = 64 => 128 000 tokens per launch; far beyond what the oracle
+    finishes in seconds) through size-independent properties of the path: trajectories are independent, so (1) the run is
+    deterministic, (2) permuting the batch permutes the result, (3) a sub-batch sampled alone equals its slice of the full run —
+    bit for bit, which exercises every tile that straddles two samples, the persistent kernels' multi-wave loops and the CTA-pair
+    tails."""
+    import lam_slide_b200 as P
+    from lam_slide_b200.synthetic import randomize_zero_init, synthetic_batch
+    cfg = P.get_config("peptide")
+    torch.manual_seed(0)
+    m = P.SecondStageSampler(cfg, sampling_kwargs={"sampling_method": "euler", "num_steps": 10})
+    randomize_zero_init(m, seed=1)
+    m = m.cuda()
+    B, T = 64, cfg["T"]
+    L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+    batch = synthetic_batch(cfg, B, seed=5)
+    noise = torch.randn(B, T, L, D, generator=torch.Generator().manual_seed(6))
+    key = cfg["main_output"]
+
+    def run(idx):
+        b = {k: v[idx].clone() for k, v in batch.items()}
+        return m.sample(b, noise=noise[idx].clone())[key]
+
+    full_idx = torch.arange(B)
+    full = run(full_idx)
+    assert torch.isfinite(full).all()
+    assert torch.equal(run(full_idx), full)                      # (1)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(7))
+    assert torch.equal(run(perm), full[perm.cuda()])             # (2)
+    sub = torch.tensor([3, 17, 18, 40, 63])
+    assert torch.equal(run(sub), full[sub.cuda()])               # (3)
+
+
 def test_errors_are_loud():
     import lam_slide_b200 as P
     with pytest.raises(ValueError):

@@ -5,9 +5,11 @@ Public surface (mirrors the reference's interfaces for this path; see DESIGN.md 
     FirstStage            BackboneBase + Encoder/Decoder           (lightning_base.py, encoder.py, decoder.py)
     CreateTransport, Sampler                                       (src/modules/transport)
     SecondStageSampler    encode -> conditioning -> Euler ODE -> decode  (SecondStageCondLightningBase.sample)
+    SIAtom14SamplingWrapper  autoregressive roll-out driver, batched on device  (src/modules/sampling.py)
 """
 from .backbone import LatentSIV3  # noqa: F401
 from .configs import CONFIGS, get_config  # noqa: F401
 from .first_stage import FirstStage  # noqa: F401
 from .model import SecondStageSampler  # noqa: F401
+from .rollout import SIAtom14SamplingWrapper  # noqa: F401
 from .transport import CreateTransport, Sampler, Transport  # noqa: F401

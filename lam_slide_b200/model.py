@@ -128,6 +128,22 @@ class SecondStageSampler(nn.Module):
         latents = sample_fn(x0, self.forward, **model_kwargs)[-1]
         return self.decode(latents.flatten(0, 1), batch["entities"].flatten(0, 1), T=T)
 
+    @torch.no_grad()
+    def sample_from_latents(self, latents: Tensor, entities: Tensor, noise: Optional[Tensor] = None,
+                            y: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """The part of ``sample()`` after the encoder (lightning_base.py:209-238): conditioning from the given first-stage
+        latents ``[B, T, L, D]`` (device), ODE, decode with ``entities [B, T, N]``.  Used by callers that can build the
+        latents cheaper than by encoding B·T frames — e.g. the roll-out driver, whose T frames are copies of one frame."""
+        sample_fn = Sampler(self.si).get_sample_fn(self.hparams.sampling_method, self.hparams.sampling_kwargs)
+        B, T = latents.shape[:2]
+        x_cond, x_cond_mask = self.setup_conditioning(latents)
+        model_kwargs = {"x_cond": x_cond, "x_cond_mask": x_cond_mask}
+        if y is not None:
+            model_kwargs["y"] = y
+        x0 = torch.randn_like(x_cond) if noise is None else noise.to(self.device, non_blocking=True)
+        out = sample_fn(x0, self.forward, **model_kwargs)[-1]
+        return self.decode(out.flatten(0, 1), entities.flatten(0, 1), T=T)
+
     def sample_stream(self, batches, noise: Optional[Tensor] = None):
         """``sample()`` over an iterable of HOST batches (pinned memory), yielding pinned host tensors of the main output.
         Same per-batch work as ``sample()`` (lightning_base.py:217-238), but the host->device copy of batch k + 1 and the

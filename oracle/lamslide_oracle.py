@@ -405,6 +405,53 @@ def sample(fs_sd: SD, bb_sd: SD, cfg: dict, batch: Dict[str, Tensor], noise: Ten
 
 
 # --------------------------------------------------------------------------------------------------
+# autoregressive roll-out driver
+# --------------------------------------------------------------------------------------------------
+def rollout_create_batch(pos: Tensor, res: Tensor, res_mask: Tensor, T: int) -> Dict[str, Tensor]:
+    """SIAtom14SamplingWrapper.create_batch — src/modules/sampling.py:24-43: one conditioning frame, masked by the
+    residue-type atom mask and repeated over all T frames of a B = 1 batch."""
+    pos = pos * res_mask[..., None].to(pos.dtype)
+    R = res.shape[0]
+    return {
+        "atom14_pos": pos[None, None].expand(1, T, R, 14, 3).contiguous(),
+        "aatype": res[None, None].expand(1, T, R).contiguous(),
+        "attention_mask": torch.ones(1, T, R, dtype=torch.bool),
+        "entities": torch.arange(R)[None, None].expand(1, T, R).contiguous(),
+    }
+
+
+def sample_rollout(fs_sd: SD, bb_sd: SD, cfg: dict, cond_pos: Tensor, res: Tensor, res_mask: Tensor, noises: Sequence[Tensor],
+                   *, shift: float = 0.0, scale: float = 1.0, num_steps: int = 10) -> Tensor:
+    """SIAtom14SamplingWrapper.sample_rollout — src/modules/sampling.py:45-63: normalise the conditioning frame, then
+    ``len(noises)`` times: build the batch from the current frame, ``sample()`` a block of T frames, continue from its last
+    frame; concatenate the blocks, put the conditioning frame back at index 0, de-normalise.  ``noises[i]`` ([1,T,L,D])
+    stands in for the ``randn_like`` of the i-th ``sample()`` call.  Returns [len(noises) * T, R, 14, 3]."""
+    T = cfg["T"]
+    cond = (cond_pos - shift) / scale
+    pos = cond.clone()
+    blocks = []
+    for nz in noises:
+        batch = rollout_create_batch(pos, res, res_mask, T)
+        pred = sample(fs_sd, bb_sd, cfg, batch, nz, num_steps=num_steps)["atom14_pos"]  # [1, T, R, 42]
+        pred = pred.unflatten(-1, (14, 3)).squeeze(0)  # Wrapper.decode: "(B T) L (A D) -> B T L A D" (second_stage/peptide.py:97-102)
+        blocks.append(pred)
+        pos = pred[-1].clone()
+    positions = torch.cat(blocks)
+    positions[0] = cond
+    return positions * scale + shift
+
+
+def rollout_inputs(R: int, seed: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Seeded synthetic conditioning frame for the roll-out tests: positions [R,14,3], residue types [R], atom mask [R,14]."""
+    g = torch.Generator().manual_seed(seed)
+    cond_pos = torch.randn(R, 14, 3, generator=g)
+    res = torch.randint(0, 20, (R,), generator=g)
+    res_mask = torch.rand(R, 14, generator=g) < 0.7
+    res_mask[:, :4] = True  # backbone atoms always present
+    return cond_pos, res, res_mask
+
+
+# --------------------------------------------------------------------------------------------------
 # deterministic parameters and synthetic batches (shared by the tests, smoke() and bench.py)
 # --------------------------------------------------------------------------------------------------
 def _rand(gen: torch.Generator, shape, std: float) -> Tensor:

@@ -24,7 +24,8 @@ sys.path.insert(0, ROOT)
 
 from lam_slide_b200.configs import get_config  # noqa: E402
 from oracle import lamslide_oracle as O  # noqa: E402
-from oracle.ref_loader import RefFirstStage, load_reference, reference_sample  # noqa: E402
+from oracle.ref_loader import (RefFirstStage, RefRolloutModel, load_reference, load_reference_rollout_wrapper,  # noqa: E402
+                               reference_sample)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
@@ -39,6 +40,47 @@ CASES = [
     dict(case="peptide_linear_velocity", cfg="peptide", overrides=dict(depth=1), B=1, T=16, num_steps=6,
          seeds=(121, 122, 123, 124), path_type="Linear", prediction="velocity"),
 ]
+
+
+# autoregressive roll-out: the reference's own SIAtom14SamplingWrapper.sample_rollout
+ROLLOUT_CASE = dict(case="peptide_rollout", cfg="peptide", overrides=dict(depth=2), T=16, R=4, num_rollouts=3, num_steps=6,
+                    shift=0.05, scale=2.0, seeds=(131, 132, 133, 134))
+
+
+def rollout_case_inputs(c: dict = ROLLOUT_CASE):
+    cfg = get_config(c["cfg"], **c["overrides"])
+    cfg["T"] = c["T"]
+    s_fs, s_bb, s_in, s_noise = c["seeds"]
+    fs_sd = O.init_first_stage_params(cfg["first_stage"], s_fs)
+    bb_sd = O.init_backbone_params(cfg["backbone"], s_bb)
+    cond_pos, res, res_mask = O.rollout_inputs(c["R"], s_in)
+    g = torch.Generator().manual_seed(s_noise)
+    L = cfg["first_stage"]["encoder"]["num_latents"]
+    noises = [torch.randn(1, c["T"], L, cfg["backbone"]["in_dim"], generator=g) for _ in range(c["num_rollouts"])]
+    return cfg, fs_sd, bb_sd, cond_pos, res, res_mask, noises
+
+
+def make_rollout_golden(ref) -> None:
+    c = ROLLOUT_CASE
+    cfg, fs_sd, bb_sd, cond_pos, res, res_mask, noises = rollout_case_inputs(c)
+    bb = cfg["backbone"]
+    fs = RefFirstStage(cfg["first_stage"]).eval()
+    fs.load_state_dict(fs_sd, strict=True)
+    net = ref.LatentSIV3(depth=bb["depth"], in_dim=bb["in_dim"], hidden_size=bb["hidden_size"], num_heads=bb["num_heads"],
+                         vec_in_dim=bb["vec_in_dim"], mlp_ratio=bb["mlp_ratio"], normalize=bb["normalize"], theta=bb["theta"]).eval()
+    net.load_state_dict(bb_sd, strict=True)
+    model = RefRolloutModel(fs, net, cfg, noises, c["shift"], c["scale"], c["num_steps"])
+    wrapper = load_reference_rollout_wrapper()(model)
+    with torch.no_grad():
+        positions = wrapper.sample_rollout(cond_pos.clone(), res.clone(), res_mask.clone(), num_rollouts=c["num_rollouts"])
+    assert model.calls == c["num_rollouts"] and positions.shape == (c["num_rollouts"] * c["T"], c["R"], 14, 3)
+    fixture = dict(case=dict(c), checksums=dict(fs=O.state_checksum(fs_sd), bb=O.state_checksum(bb_sd),
+                                                 inputs=float(cond_pos.double().sum() + res.double().sum() + res_mask.double().sum()),
+                                                 noise=float(sum(n.double().sum() for n in noises))),
+                   positions=positions.clone(), torch_version=torch.__version__)
+    path = os.path.join(GOLDEN_DIR, c["case"] + ".pt")
+    torch.save(fixture, path)
+    print(f"{c['case']:28s} -> {os.path.getsize(path) / 1024:8.1f} KiB   |pos| max {float(positions.abs().max()):.3f}")
 
 
 def case_inputs(c: dict):
@@ -64,6 +106,9 @@ def main() -> None:
     ref = load_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    make_rollout_golden(ref)
+    if "--rollout-only" in sys.argv:
+        return
     for c in CASES:
         cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)
         bb = cfg["backbone"]

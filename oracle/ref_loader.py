@@ -212,3 +212,41 @@ def reference_sample(first_stage: RefFirstStage, backbone: nn.Module, batch: Dic
         record.update(latents=latents, x_cond=x_cond, x_cond_mask=x_mask, states=states,
                       velocities=torch.stack(vel))
     return out
+
+
+def load_reference_rollout_wrapper():
+    """The reference's OWN ``SIAtom14SamplingWrapper`` (``src/modules/sampling.py:16-63``).  Its module cannot be imported here
+    (mdtraj, MDAnalysis, lightning ... are not in the image), so the class is compiled straight from the reference file —
+    only ``__init__``, ``create_batch`` and ``sample_rollout`` (the methods with no trajectory-file dependency) — with the
+    three names they use (torch, einops.repeat, tqdm) in scope.  Nothing is copied into this repository."""
+    import ast
+
+    from einops import repeat
+    from tqdm import tqdm
+    path = os.path.join(REFERENCE_ROOT, "src", "modules", "sampling.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "SIAtom14SamplingWrapper")
+    cls.body = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("__init__", "create_batch", "sample_rollout")]
+    mod = ast.Module(body=[cls], type_ignores=[])
+    ns = {"torch": torch, "Tensor": torch.Tensor, "Dict": Dict, "repeat": repeat, "tqdm": tqdm}
+    exec(compile(mod, path, "exec"), ns)  # nosec B102 - the reference's own source, dev container only
+    return ns["SIAtom14SamplingWrapper"]
+
+
+class RefRolloutModel:
+    """What ``SIAtom14SamplingWrapper`` needs from the Lightning wrapper: ``hparams.n_timesteps``, ``shift``, ``scale`` and
+    ``sample(batch) -> {"atom14_pos": [B, T, R, 14, 3]}`` (``second_stage/peptide.py:97-102`` reshapes the decoder's 42 columns).
+    ``noises`` replaces the ``randn_like`` of successive ``sample()`` calls."""
+
+    def __init__(self, first_stage, backbone, cfg, noises, shift, scale, num_steps):
+        self.fs, self.net, self.cfg, self.noises = first_stage, backbone, cfg, list(noises)
+        self.hparams = types.SimpleNamespace(n_timesteps=cfg["T"])
+        self.shift, self.scale, self.num_steps, self.calls = shift, scale, num_steps, 0
+
+    def sample(self, batch):
+        out = reference_sample(self.fs, self.net, batch, cond_idx=self.cfg["cond_idx"], path_type=self.cfg["path_type"],
+                               prediction=self.cfg["prediction"], num_steps=self.num_steps, noise=self.noises[self.calls],
+                               mask_cond_mean=self.cfg["mask_cond_mean"])
+        self.calls += 1
+        return {"atom14_pos": out["atom14_pos"].unflatten(-1, (14, 3))}
+

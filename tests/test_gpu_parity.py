@@ -158,6 +158,60 @@ def test_sample_stream_matches_sample():
     assert not torch.equal(want[0], want[1])
 
 
+def test_rollout_vs_reference_golden():
+    """Roll-out driver: SIAtom14SamplingWrapper.sample_rollout on the GPU path against the positions the
+    reference's own class produced (tests/golden/peptide_rollout.pt); three chained sample() calls, so the single-call RMSD
+    tolerance is applied per block with the error of the earlier blocks feeding forward (x3)."""
+    import lam_slide_b200 as P
+    from oracle.make_golden import ROLLOUT_CASE, rollout_case_inputs
+    c = ROLLOUT_CASE
+    fx = load_golden("peptide_rollout")
+    cfg, fs_sd, bb_sd, cond_pos, res, res_mask, noises = rollout_case_inputs(c)
+    m = _build(cfg, fs_sd, bb_sd)
+    m.hparams.sampling_kwargs["num_steps"] = c["num_steps"]
+    w = P.SIAtom14SamplingWrapper(m, shift=c["shift"], scale=c["scale"])
+    pos = w.sample_rollout(cond_pos, res, res_mask, num_rollouts=c["num_rollouts"], noise=torch.stack(noises)).cpu()
+    assert pos.shape == fx["positions"].shape
+    assert torch.allclose(pos[0], cond_pos, atol=1e-6)
+    T = c["T"]
+    for i in range(c["num_rollouts"]):
+        blk = slice(max(i * T, 1), (i + 1) * T)
+        assert rmsd(pos[blk], fx["positions"][blk]) < RMSD_TOL * (i + 1) * c["scale"], f"block {i}"
+
+
+def test_rollout_batched_equals_chain_by_chain():
+    """sample_rollouts (B chains together, one encoded frame per chain and step, latents broadcast over T) equals the
+    reference-style loop — model.sample(create_batch(...)) per chain, which encodes T copies of the frame — bit for bit."""
+    import lam_slide_b200 as P
+    from oracle.make_golden import ROLLOUT_CASE, rollout_case_inputs
+    c = ROLLOUT_CASE
+    cfg, fs_sd, bb_sd, _, _, _, _ = rollout_case_inputs(c)
+    m = _build(cfg, fs_sd, bb_sd)
+    m.hparams.sampling_kwargs["num_steps"] = c["num_steps"]
+    w = P.SIAtom14SamplingWrapper(m, shift=c["shift"], scale=c["scale"])
+    B, R, T, n_roll = 3, c["R"], c["T"], 2
+    ins = [O.rollout_inputs(R, 900 + b) for b in range(B)]
+    cond = torch.stack([x[0] for x in ins])
+    res = torch.stack([x[1] for x in ins])
+    msk = torch.stack([x[2] for x in ins])
+    L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+    noise = torch.randn(n_roll, B, T, L, D, generator=torch.Generator().manual_seed(5))
+    got = w.sample_rollouts(cond, res, msk, num_rollouts=n_roll, noise=noise).cpu()
+    assert got.shape == (B, n_roll * T, R, 14, 3)
+    for b in range(B):
+        pos = ((cond[b] - c["shift"]) / c["scale"]).cuda()
+        blocks = []
+        for i in range(n_roll):
+            batch = w.create_batch(pos, res[b].cuda(), msk[b].cuda())
+            pred = m.sample(batch, noise=noise[i, b:b + 1])["atom14_pos"].squeeze(0)
+            blocks.append(pred)
+            pos = pred[-1].clone()
+        want = torch.cat(blocks)
+        want[0] = ((cond[b] - c["shift"]) / c["scale"]).cuda()
+        want = (want * c["scale"] + c["shift"]).cpu()
+        assert torch.equal(got[b], want), f"chain {b}: max diff {float((got[b] - want).abs().max()):.3e}"
+
+
 def test_full_size_batch_properties():
     """BASELINE.json's full configuration (4AA peptides, T = 1000, B = 64 => 128 000 tokens per launch; far beyond what the oracle
     finishes in seconds) through size-independent properties of the path: trajectories are independent, so (1) the run is

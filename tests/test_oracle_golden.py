@@ -30,6 +30,27 @@ def test_oracle_matches_reference_golden(name):
         assert max_rel(out[k][:, sl], v) < 1e-4
 
 
+def test_oracle_rollout_matches_reference_golden():
+    """Autoregressive roll-out: the oracle restatement of SIAtom14SamplingWrapper.sample_rollout against the
+    positions produced by the reference's own class (oracle/make_golden.py: make_rollout_golden)."""
+    from oracle.make_golden import ROLLOUT_CASE, rollout_case_inputs
+    torch.set_num_threads(8)
+    fx = load_golden("peptide_rollout")
+    c = ROLLOUT_CASE
+    cfg, fs_sd, bb_sd, cond_pos, res, res_mask, noises = rollout_case_inputs(c)
+    cs = fx["checksums"]
+    assert abs(O.state_checksum(fs_sd) - cs["fs"]) <= 1e-6 * max(1.0, abs(cs["fs"]))
+    assert abs(O.state_checksum(bb_sd) - cs["bb"]) <= 1e-6 * max(1.0, abs(cs["bb"]))
+    assert abs(float(cond_pos.double().sum() + res.double().sum() + res_mask.double().sum()) - cs["inputs"]) < 1e-6
+    assert abs(float(sum(n.double().sum() for n in noises)) - cs["noise"]) < 1e-6
+    with torch.no_grad():
+        pos = O.sample_rollout(fs_sd, bb_sd, cfg, cond_pos, res, res_mask, noises, shift=c["shift"], scale=c["scale"],
+                               num_steps=c["num_steps"])
+    assert pos.shape == fx["positions"].shape == (c["num_rollouts"] * c["T"], c["R"], 14, 3)
+    assert torch.allclose(pos[0], cond_pos, atol=1e-6)  # sampling.py:62: the conditioning frame is put back at index 0 ...
+    assert max_rel(pos, fx["positions"]) < 2e-4  # ... and errors feed forward through three chained sample() calls
+
+
 def test_backbone_single_eval_matches_golden():
     fx = load_golden("nba_full")
     c = CASE_BY_NAME["nba_full"]

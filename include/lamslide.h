@@ -89,6 +89,16 @@ int lamslide_euler_step(float* x, const float* net_out, int32_t path_type, int32
 int lamslide_setup_conditioning(const float* latents, float* x_cond, int64_t* x_cond_mask, int32_t B, int32_t T, int32_t L,
                                 int32_t D, int32_t cond_begin, int32_t cond_end, int32_t mask_cond_mean, void* stream);
 
+/* K-sample evaluation metrics on the device.  preds [K, B, T, A, D] = K batched sample() results restricted
+ * to the frames after the conditioning window, target [B, T, A, D]; err = L2 norm over D.
+ *   mode 0 - Wrapper.test_step / _compute_errors of second_stage/nba.py:161-238 and pedestrian.py:149-226 (unclustered metric):
+ *            ades, fdes [B * A]: min over the first num_runs samples of the time-averaged / final-frame error of every agent
+ *            (the caller drops padded agents with batch["attention_mask"][:, -1], as the reference does before stacking);
+ *   mode 1 - Wrapper.test_step of second_stage/md17.py:139-171: ades, fdes [B]: mean over the K samples of the error averaged
+ *            over frames and atoms / over the atoms of the final frame. */
+int lamslide_ksample_errors(const float* preds, const float* target, float* ades, float* fdes, int32_t K, int32_t num_runs,
+                            int32_t B, int32_t T, int32_t A, int32_t D, int32_t mode, void* stream);
+
 /* ---- first stage: BackboneBase + Encoder / Decoder / DecoderQuerySplitter ------------------------------------------- */
 typedef enum { LAMSLIDE_FS_PEPTIDE = 0, LAMSLIDE_FS_MD17 = 1, LAMSLIDE_FS_NBA = 2, LAMSLIDE_FS_PEDESTRIAN = 3 } lamslide_fs_kind;
 

@@ -6,10 +6,12 @@ Public surface (mirrors the reference's interfaces for this path; see DESIGN.md 
     CreateTransport, Sampler                                       (src/modules/transport)
     SecondStageSampler    encode -> conditioning -> Euler ODE -> decode  (SecondStageCondLightningBase.sample)
     SIAtom14SamplingWrapper  autoregressive roll-out driver, batched on device  (src/modules/sampling.py)
+    KSampleEvaluator      K-sample min/mean ADE-FDE evaluation, one batched solve  (second_stage/{nba,pedestrian,md17}.py test_step)
 """
 from .backbone import LatentSIV3  # noqa: F401
 from .configs import CONFIGS, get_config  # noqa: F401
 from .first_stage import FirstStage  # noqa: F401
 from .model import SecondStageSampler  # noqa: F401
 from .rollout import SIAtom14SamplingWrapper  # noqa: F401
+from .evaluation import KSampleEvaluator, ksample_errors  # noqa: F401
 from .transport import CreateTransport, Sampler, Transport  # noqa: F401

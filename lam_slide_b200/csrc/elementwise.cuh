@@ -265,4 +265,62 @@ conditioning_kernel(const float* __restrict__ lat, float* __restrict__ x_cond, l
   }
 }
 
+// ---- K-sample trajectory errors: ADE / FDE of K sampled futures against the ground truth.
+// preds [K, B, T, A, D] (sample-major, as K batched sample() calls produce them), target [B, T, A, D]; T = frames after the
+// conditioning window, A agents / atoms, D coordinates.  err(k, b, t, a) = || preds - target ||_2 over D.
+//   mode 0 (nba.py:191-197,220-225; pedestrian.py idem): per (b, a): ade = min_{k < num_runs} mean_t err, fde = min_{k < num_runs} err(t = T-1)
+//   mode 1 (md17.py:158-168):                            per b:      ade = mean_k mean_{t,a} err,      fde = mean_k mean_a err(t = T-1)
+// One thread per output element; the reductions are sequential in the reference's index order (k, then t, then a) in fp32.
+__global__ void __launch_bounds__(128)
+ksample_errors_kernel(const float* __restrict__ preds, const float* __restrict__ target, float* __restrict__ ades, float* __restrict__ fdes,
+                      int K, int num_runs, int B, int T, int A, int D, int mode) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_out = mode == 0 ? B * A : B;
+  if (idx >= n_out) return;
+  const size_t frame = (size_t)A * D, traj = (size_t)T * frame, sample = (size_t)B * traj;
+  if (mode == 0) {
+    const int b = idx / A, a = idx % A;
+    float best_a = INFINITY, best_f = INFINITY;
+    for (int k = 0; k < num_runs; ++k) {
+      const float* p = preds + (size_t)k * sample + (size_t)b * traj + (size_t)a * D;
+      const float* q = target + (size_t)b * traj + (size_t)a * D;
+      float sum = 0.f, last = 0.f;
+      for (int t = 0; t < T; ++t) {
+        float e2 = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float df = p[(size_t)t * frame + d] - q[(size_t)t * frame + d];
+          e2 = fmaf(df, df, e2);
+        }
+        last = sqrtf(e2);
+        sum += last;
+      }
+      best_a = fminf(best_a, sum / (float)T);
+      best_f = fminf(best_f, last);
+    }
+    ades[idx] = best_a, fdes[idx] = best_f;
+  } else {
+    const int b = idx;
+    float acc_a = 0.f, acc_f = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float* p = preds + (size_t)k * sample + (size_t)b * traj;
+      const float* q = target + (size_t)b * traj;
+      float sum = 0.f, sum_last = 0.f;
+      for (int t = 0; t < T; ++t)
+        for (int a = 0; a < A; ++a) {
+          float e2 = 0.f;
+          for (int d = 0; d < D; ++d) {
+            const float df = q[(size_t)t * frame + (size_t)a * D + d] - p[(size_t)t * frame + (size_t)a * D + d];
+            e2 = fmaf(df, df, e2);
+          }
+          const float e = sqrtf(e2);
+          sum += e;
+          if (t == T - 1) sum_last += e;
+        }
+      acc_a += sum / (float)(T * A);
+      acc_f += sum_last / (float)A;
+    }
+    ades[idx] = acc_a / (float)K, fdes[idx] = acc_f / (float)K;
+  }
+}
+
 }  // namespace lam

@@ -1067,6 +1067,19 @@ extern "C" int lamslide_setup_conditioning(const float* latents, float* x_cond, 
   return 0;
 }
 
+// K-sample evaluation metrics (second_stage/nba.py:161-238, pedestrian.py:149-226: mode 0; md17.py:139-171: mode 1).
+extern "C" int lamslide_ksample_errors(const float* preds, const float* target, float* ades, float* fdes, int32_t K, int32_t num_runs,
+                                       int32_t B, int32_t T, int32_t A, int32_t D, int32_t mode, void* stream) {
+  if (!preds || !target || !ades || !fdes) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  if (K <= 0 || B <= 0 || T <= 0 || A <= 0 || D <= 0 || (mode != 0 && mode != 1))
+    return fail(LAMSLIDE_ERR_INVALID, "bad K-sample shape K %d B %d T %d A %d D %d mode %d", K, B, T, A, D, mode);
+  if (mode == 0 && (num_runs <= 0 || num_runs > K)) return fail(LAMSLIDE_ERR_INVALID, "num_runs %d outside [1, K = %d]", num_runs, K);
+  const int n_out = mode == 0 ? B * A : B;
+  ksample_errors_kernel<<<cdiv(n_out, 128), 128, 0, (cudaStream_t)stream>>>(preds, target, ades, fdes, K, num_runs, B, T, A, D, mode);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // ================================================================================================ first stage
 struct LNW {
   float *w = nullptr, *b = nullptr;

@@ -452,6 +452,54 @@ def rollout_inputs(R: int, seed: int) -> Tuple[Tensor, Tensor, Tensor]:
 
 
 # --------------------------------------------------------------------------------------------------
+# K-sample evaluation metrics
+# --------------------------------------------------------------------------------------------------
+def ksample_min_ade_fde(preds: Sequence[Tensor], true_pos: Tensor, attention_mask: Tensor, cond_end: int,
+                        num_runs: int) -> Tuple[Tensor, Tensor]:
+    """The unclustered metric of ``Wrapper.test_step`` — second_stage/nba.py:184-225 (pedestrian.py:172-213 is identical):
+    ``preds[k]`` is the k-th ``sample()`` result ``[B, T, A, D]``, ``true_pos [B, T, A, D]`` the ground truth, ``attention_mask
+    [B, T, A]`` marks real agents.  Frames before ``cond_end`` are dropped, padded agents removed (mask of the last frame),
+    and per remaining agent the minimum over the first ``num_runs`` samples of the time-averaged (ADE) and final-frame (FDE)
+    displacement is returned."""
+    B, T, A, D = true_pos.shape
+    mask = attention_mask[:, -1].reshape(B * A)
+    true = true_pos[:, cond_end:].permute(0, 2, 1, 3).reshape(B * A, T - cond_end, D)[mask]
+    all_traj = []
+    for p in preds:
+        p = p[:, cond_end:].permute(0, 2, 1, 3).reshape(B * A, T - cond_end, D)[mask]
+        all_traj.append(p)
+    all_traj = torch.stack(all_traj, dim=1)  # [n, K, T', D]
+    selected = all_traj[:, :num_runs]
+    error = torch.norm(selected - true[:, None], dim=-1)  # [n, runs, T']
+    return error.mean(dim=-1).min(dim=1).values, error[..., -1].min(dim=1).values
+
+
+def ksample_mean_ade_fde(preds: Sequence[Tensor], true_pos: Tensor, cond_end: int) -> Tuple[Tensor, Tensor]:
+    """``Wrapper.test_step`` of second_stage/md17.py:148-168: per sample, the mean over the K runs of the displacement averaged
+    over frames and atoms (ADE) and over the atoms of the last frame (FDE)."""
+    true = true_pos[:, cond_end:]
+    ades, fdes = [], []
+    for p in preds:
+        p = p[:, cond_end:]
+        ades.append(torch.norm(true - p, dim=-1).mean(dim=(1, 2)))
+        fdes.append(torch.norm(true[:, -1] - p[:, -1], dim=-1).mean(dim=1))
+    return torch.stack(ades).mean(dim=0), torch.stack(fdes).mean(dim=0)
+
+
+def ksample_inputs(B: int, T: int, A: int, D: int, K: int, seed: int, pad_agents: bool):
+    """Seeded synthetic inputs of the K-sample metric tests: K predictions, the ground truth, the agent mask."""
+    g = torch.Generator().manual_seed(seed)
+    true_pos = torch.randn(B, T, A, D, generator=g)
+    preds = [true_pos + 0.3 * torch.randn(B, T, A, D, generator=g) for _ in range(K)]
+    mask = torch.ones(B, T, A, dtype=torch.bool)
+    if pad_agents:
+        for b in range(B):
+            n_valid = int(torch.randint(max(1, A // 2), A + 1, (1,), generator=g))
+            mask[b, :, n_valid:] = False
+    return preds, true_pos, mask
+
+
+# --------------------------------------------------------------------------------------------------
 # deterministic parameters and synthetic batches (shared by the tests, smoke() and bench.py)
 # --------------------------------------------------------------------------------------------------
 def _rand(gen: torch.Generator, shape, std: float) -> Tensor:

@@ -24,8 +24,8 @@ sys.path.insert(0, ROOT)
 
 from lam_slide_b200.configs import get_config  # noqa: E402
 from oracle import lamslide_oracle as O  # noqa: E402
-from oracle.ref_loader import (RefFirstStage, RefRolloutModel, load_reference, load_reference_rollout_wrapper,  # noqa: E402
-                               reference_sample)
+from oracle.ref_loader import (RefFirstStage, RefRolloutModel, RefTestStepSelf, load_reference, load_reference_method,  # noqa: E402
+                               load_reference_rollout_wrapper, reference_sample)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
@@ -83,6 +83,38 @@ def make_rollout_golden(ref) -> None:
     print(f"{c['case']:28s} -> {os.path.getsize(path) / 1024:8.1f} KiB   |pos| max {float(positions.abs().max()):.3f}")
 
 
+# K-sample evaluation metrics: the reference's own Wrapper.test_step bodies on preset predictions
+KSAMPLE_CASES = [
+    dict(case="ksample_nba", file="src/models/composites/second_stage/nba.py", B=3, T=20, A=11, D=2, K=6, num_runs=4, cond_idx=(0, 8),
+         pad=False, seed=141, mode="min"),
+    dict(case="ksample_pedestrian", file="src/models/composites/second_stage/pedestrian.py", B=5, T=20, A=10, D=2, K=5, num_runs=5,
+         cond_idx=(0, 8), pad=True, seed=142, mode="min"),
+    dict(case="ksample_md17", file="src/models/composites/second_stage/md17.py", B=2, T=12, A=21, D=3, K=5, num_runs=5, cond_idx=(0, 4),
+         pad=False, seed=143, mode="mean"),
+]
+
+
+def make_ksample_golden() -> None:
+    fixtures = {}
+    for c in KSAMPLE_CASES:
+        preds, true_pos, mask = O.ksample_inputs(c["B"], c["T"], c["A"], c["D"], c["K"], c["seed"], c["pad"])
+        test_step = load_reference_method(c["file"], "Wrapper", "test_step", {"KMeans": None})
+        me = RefTestStepSelf(preds, c["K"], c["cond_idx"], c["num_runs"])
+        batch = {"pos": true_pos.clone(), "attention_mask": mask.clone()}
+        if c["mode"] == "mean":
+            batch["atom"] = torch.ones(c["B"], c["T"], c["A"], dtype=torch.int64)
+        with torch.no_grad():
+            test_step(me, batch, 0)
+        out = me.test_step_outputs["test"]
+        assert me.calls == c["K"]
+        # what the reference hands to sample(): the frames after the conditioning window are zeroed (nba.py:188-189, md17.py:149-151)
+        assert float(me.seen[0]["pos"][:, c["cond_idx"][1]:].abs().sum()) == 0.0
+        fixtures[c["case"]] = dict(case=dict(c), ades=out["ades"][0].clone(), fdes=out["fdes"][0].clone(),
+                                   checksum=float(sum(p.double().sum() for p in preds) + true_pos.double().sum() + mask.double().sum()))
+        print(f"{c['case']:28s} ades {tuple(out['ades'][0].shape)} mean {float(out['ades'][0].mean()):.4f}  fdes mean {float(out['fdes'][0].mean()):.4f}")
+    torch.save(fixtures, os.path.join(GOLDEN_DIR, "ksample_metrics.pt"))
+
+
 def case_inputs(c: dict):
     """Everything a test needs to re-create the inputs of a golden case (shared with tests/)."""
     cfg = get_config(c["cfg"], **c["overrides"])
@@ -107,7 +139,8 @@ def main() -> None:
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     make_rollout_golden(ref)
-    if "--rollout-only" in sys.argv:
+    make_ksample_golden()
+    if "--rollout-only" in sys.argv or "--widened-only" in sys.argv:
         return
     for c in CASES:
         cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)

@@ -250,3 +250,37 @@ class RefRolloutModel:
         self.calls += 1
         return {"atom14_pos": out["atom14_pos"].unflatten(-1, (14, 3))}
 
+
+def load_reference_method(relpath: str, class_name: str, method_name: str, extra_ns: Optional[dict] = None):
+    """One method of a reference class as a plain function ``f(self, ...)``, compiled from the reference file in place — for
+    classes whose modules cannot be imported here (Lightning / hydra / torchmetrics / torch_kmeans are not in the image)."""
+    import ast
+
+    from einops import rearrange
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    tree = ast.parse(open(path).read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == method_name)
+    ns = {"torch": torch, "Tensor": torch.Tensor, "Dict": Dict, "rearrange": rearrange}
+    ns.update(extra_ns or {})
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)  # nosec B102 - the reference's own source
+    return ns[method_name]
+
+
+class RefTestStepSelf:
+    """The attributes ``Wrapper.test_step`` touches (second_stage/nba.py:161-225, md17.py:139-171): ``hparams``, the datamodule's
+    dataloader name, the output dict, and ``sample(batch)`` — which here hands out preset predictions ``[B, T, A, D]`` in
+    the reference's ``(B T) A D`` layout."""
+
+    def __init__(self, preds, K, cond_idx, num_runs):
+        self.hparams = types.SimpleNamespace(K=K, cond_idx=list(cond_idx), num_runs=num_runs, post_process=False)
+        self.trainer = types.SimpleNamespace(datamodule=types.SimpleNamespace(dataloader_names=lambda idx: "test"))
+        self.test_step_outputs: dict = {}
+        self._preds, self.calls, self.seen = list(preds), 0, []
+
+    def sample(self, batch):
+        self.seen.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+        out = self._preds[self.calls].flatten(0, 1)
+        self.calls += 1
+        return {"pos": out}
+

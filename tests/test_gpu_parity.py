@@ -212,6 +212,58 @@ def test_rollout_batched_equals_chain_by_chain():
         assert torch.equal(got[b], want), f"chain {b}: max diff {float((got[b] - want).abs().max()):.3e}"
 
 
+def test_ksample_errors_kernel_vs_reference_golden():
+    """lamslide_ksample_errors (C-ABI) against the outputs of the reference's own test_step bodies (tests/golden/ksample_metrics.pt)."""
+    import lam_slide_b200 as P
+    from oracle.make_golden import KSAMPLE_CASES
+    fx = load_golden("ksample_metrics")
+    for c in KSAMPLE_CASES:
+        preds, true_pos, mask = O.ksample_inputs(c["B"], c["T"], c["A"], c["D"], c["K"], c["seed"], c["pad"])
+        c1 = c["cond_idx"][1]
+        pk = torch.stack(preds)[:, :, c1:].cuda()
+        ades, fdes = P.ksample_errors(pk, true_pos[:, c1:].cuda(), c["num_runs"], c["mode"])
+        if c["mode"] == "min":
+            sel = mask[:, -1].reshape(-1).cuda()
+            ades, fdes = ades[sel], fdes[sel]
+        f = fx[c["case"]]
+        assert torch.allclose(ades.cpu(), f["ades"], rtol=2e-6, atol=1e-6), c["case"]
+        assert torch.allclose(fdes.cpu(), f["fdes"], rtol=2e-6, atol=1e-6), c["case"]
+
+
+@pytest.mark.parametrize("name,mode", [("nba_full", "min"), ("pedestrian_full", "min"), ("md17_full", "mean")])
+def test_ksample_evaluator_equals_k_sample_calls(name, mode):
+    """KSampleEvaluator.test_step (one batched solve of B*K trajectories from once-encoded latents + the metric kernel) against K
+    separate model.sample() calls on the blanked batch reduced by the oracle's restatement of the reference's test_step."""
+    import lam_slide_b200 as P
+    c = CASE_BY_NAME[name]
+    cfg, fs_sd, bb_sd, batch, noise0, y = case_inputs(c)
+    m = _build(cfg, fs_sd, bb_sd)
+    m.hparams.sampling_kwargs["num_steps"] = c["num_steps"]
+    if cfg["n_classes"]:
+        g = torch.Generator().manual_seed(c["seeds"][3])
+        _ = torch.randn(c["B"], c["T"], cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"], generator=g)
+        m.vec_in_embedding.weight.data.copy_(torch.randn(cfg["n_classes"], 256, generator=g))
+    K, runs = 4, 3
+    noise = torch.randn(K, *noise0.shape, generator=torch.Generator().manual_seed(9))
+    ev = P.KSampleEvaluator(m, K=K, num_runs=runs, mode=mode)
+    ades, fdes = ev.test_step({k: v.clone() for k, v in batch.items()}, noise=noise)
+    c1 = cfg["cond_idx"][1]
+    blank = {k: v.clone() for k, v in batch.items()}
+    true_pos = blank["pos"].clone()
+    blank["pos"][:, c1:] = 0
+    if mode == "mean":
+        blank["atom"][:, c1:] = 0
+    preds = [m.sample({k: v.clone() for k, v in blank.items()}, noise=noise[k])["pos"].cpu() for k in range(K)]
+    if mode == "min":
+        mask = batch.get("attention_mask", torch.ones(true_pos.shape[:3], dtype=torch.bool))
+        want_a, want_f = O.ksample_min_ade_fde(preds, true_pos, mask, c1, runs)
+    else:
+        want_a, want_f = O.ksample_mean_ade_fde(preds, true_pos, c1)
+    assert ades.shape == want_a.shape
+    assert torch.allclose(ades.cpu(), want_a, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(fdes.cpu(), want_f, rtol=1e-5, atol=1e-6)
+
+
 def test_full_size_batch_properties():
     """BASELINE.json's full configuration (4AA peptides, T = 1000, B = 64 => 128 000 tokens per launch; far beyond what the oracle
     finishes in seconds) through size-independent properties of the path: trajectories are independent, so (1) the run is

@@ -51,6 +51,24 @@ def test_oracle_rollout_matches_reference_golden():
     assert max_rel(pos, fx["positions"]) < 2e-4  # ... and errors feed forward through three chained sample() calls
 
 
+def test_oracle_ksample_metrics_match_reference_golden():
+    """K-sample ADE / FDE: the oracle restatements against the outputs of the reference's own
+    Wrapper.test_step bodies (nba / pedestrian: min over runs per agent; md17: mean over runs per sample) on preset predictions."""
+    from oracle.make_golden import KSAMPLE_CASES
+    fx = load_golden("ksample_metrics")
+    for c in KSAMPLE_CASES:
+        preds, true_pos, mask = O.ksample_inputs(c["B"], c["T"], c["A"], c["D"], c["K"], c["seed"], c["pad"])
+        f = fx[c["case"]]
+        assert abs(float(sum(p.double().sum() for p in preds) + true_pos.double().sum() + mask.double().sum()) - f["checksum"]) < 1e-6
+        if c["mode"] == "min":
+            ades, fdes = O.ksample_min_ade_fde(preds, true_pos, mask, c["cond_idx"][1], c["num_runs"])
+        else:
+            ades, fdes = O.ksample_mean_ade_fde(preds, true_pos, c["cond_idx"][1])
+        assert ades.shape == f["ades"].shape and fdes.shape == f["fdes"].shape
+        assert torch.allclose(ades, f["ades"], rtol=1e-6, atol=1e-7), c["case"]
+        assert torch.allclose(fdes, f["fdes"], rtol=1e-6, atol=1e-7), c["case"]
+
+
 def test_backbone_single_eval_matches_golden():
     fx = load_golden("nba_full")
     c = CASE_BY_NAME["nba_full"]

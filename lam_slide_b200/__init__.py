@@ -14,4 +14,5 @@ from .first_stage import FirstStage  # noqa: F401
 from .model import SecondStageSampler  # noqa: F401
 from .rollout import SIAtom14SamplingWrapper  # noqa: F401
 from .evaluation import KSampleEvaluator, ksample_errors  # noqa: F401
+from .checkpoint import load_checkpoint, select_state_dict  # noqa: F401
 from .transport import CreateTransport, Sampler, Transport  # noqa: F401

@@ -48,3 +48,60 @@ def test_reference_default_init_is_zero_output():
     with torch.no_grad():
         out = net(x=x, t=torch.tensor([0.5]), x_cond=x, x_cond_mask=torch.zeros(1, 3, 2, dtype=torch.int64))
     assert float(out.abs().max()) == 0.0
+
+
+def test_checkpoint_ingestion_against_reference_ema_class():
+    """lam_slide_b200.load_checkpoint on a checkpoint assembled the way the reference's LightningModule writes it
+    (lightning_base.py:114-119: ``checkpoint["ema"] = self.ema.state_dict()``) with the reference's OWN ExponentialMovingAverage
+    (src/modules/ema.py, compiled from the reference file: its module imports lightning) around the reference's own modules."""
+    import ast
+    import os
+    from collections import OrderedDict
+
+    import torch.nn as nn
+
+    import lam_slide_b200 as P
+    from oracle.ref_loader import REFERENCE_ROOT, RefFirstStage, load_reference
+    ref = load_reference()
+    cfg = P.get_config("pedestrian", depth=1)
+    bb = cfg["backbone"]
+
+    class FirstStageModel(nn.Module):  # FirstStageLightningBase: .backbone
+        def __init__(self):
+            super().__init__()
+            self.backbone = RefFirstStage(cfg["first_stage"])
+
+    class Lightning(nn.Module):  # the attribute names of SecondStageCondLightningBase / CondWrapper (pedestrian.py:242-251)
+        def __init__(self):
+            super().__init__()
+            self.backbone = ref.LatentSIV3(depth=bb["depth"], in_dim=bb["in_dim"], hidden_size=bb["hidden_size"], num_heads=bb["num_heads"],
+                                           vec_in_dim=bb["vec_in_dim"], mlp_ratio=bb["mlp_ratio"], normalize=bb["normalize"])
+            self.first_stage_model = FirstStageModel()
+            self.vec_in_embedding = nn.Embedding(cfg["n_classes"], bb["vec_in_dim"])
+
+    torch.manual_seed(3)
+    lm = Lightning()
+    path = os.path.join(REFERENCE_ROOT, "src", "modules", "ema.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ExponentialMovingAverage")
+    ns = {"torch": torch, "nn": nn, "OrderedDict": OrderedDict,
+          "tensor_tree_map": lambda fn, tree_: OrderedDict((k, fn(v)) for k, v in tree_.items())}
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, "exec"), ns)  # nosec B102 - the reference's own source
+    ema = ns["ExponentialMovingAverage"](model=lm, decay=0.9)
+    with torch.no_grad():
+        for p_ in lm.parameters():
+            p_.add_(0.1 * torch.randn_like(p_))
+    ema.update(lm)  # EMA parameters now differ from the raw ones
+    ckpt = {"epoch": 3, "state_dict": lm.state_dict(), "ema": ema.state_dict()}
+
+    m = P.SecondStageSampler(cfg)
+    P.load_checkpoint(m, ckpt, use_ema=True)
+    for k, v in m.backbone.state_dict().items():
+        assert torch.equal(v, ema.params[f"backbone.{k}"]), k
+        assert not torch.equal(v, lm.state_dict()[f"backbone.{k}"]) or v.numel() == 0 or float(v.abs().sum()) == 0.0
+    for k, v in m.first_stage_model.backbone.state_dict().items():
+        assert torch.equal(v, ema.params[f"first_stage_model.backbone.{k}"]), k
+    assert torch.equal(m.vec_in_embedding.weight.data, ema.params["vec_in_embedding.weight"])
+    P.load_checkpoint(m, ckpt, use_ema=False)
+    for k, v in m.backbone.state_dict().items():
+        assert torch.equal(v, lm.state_dict()[f"backbone.{k}"]), k

@@ -89,6 +89,12 @@ int lamslide_euler_step(float* x, const float* net_out, int32_t path_type, int32
 int lamslide_setup_conditioning(const float* latents, float* x_cond, int64_t* x_cond_mask, int32_t B, int32_t T, int32_t L,
                                 int32_t D, int32_t cond_begin, int32_t cond_end, int32_t mask_cond_mean, void* stream);
 
+/* out = px * x + pm * m + pw * w over numel floats (m, w nullable; out may alias x; numel % 4 == 0, 16-byte aligned): the building
+ * block of the SDE sampler's steps — sde.__Euler_Maruyama_step / __Heun_step (integrators.py:29-52) and the last step of
+ * Sampler.sample_sde (transport.py:266-299) are linear in (state, network output, noise) with time-only coefficients. */
+int lamslide_lincomb3(float* out, const float* x, const float* m, const float* w, float px, float pm, float pw, int64_t numel,
+                      void* stream);
+
 /* K-sample evaluation metrics on the device.  preds [K, B, T, A, D] = K batched sample() results restricted
  * to the frames after the conditioning window, target [B, T, A, D]; err = L2 norm over D.
  *   mode 0 - Wrapper.test_step / _compute_errors of second_stage/nba.py:161-238 and pedestrian.py:149-226 (unclustered metric):

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "liblamslide.so")
 SYMBOLS = [
     "lamslide_abi_version", "lamslide_last_error", "lamslide_launch_count",
     "lamslide_backbone_create", "lamslide_backbone_destroy", "lamslide_backbone_workspace_bytes",
-    "lamslide_backbone_forward", "lamslide_ode_sample", "lamslide_euler_step", "lamslide_setup_conditioning", "lamslide_ksample_errors",
+    "lamslide_backbone_forward", "lamslide_ode_sample", "lamslide_euler_step", "lamslide_setup_conditioning", "lamslide_ksample_errors", "lamslide_lincomb3",
     "lamslide_first_stage_create", "lamslide_first_stage_destroy", "lamslide_first_stage_workspace_bytes",
     "lamslide_encode", "lamslide_decode", "lamslide_debug_gemm", "lamslide_debug_attention",
     "lamslide_debug_linear1", "lamslide_debug_linear2", "lamslide_debug_gemm_mainloop", "lamslide_debug_fused_mlp",
@@ -90,6 +90,7 @@ def load() -> C.CDLL:
     lib.lamslide_euler_step.argtypes = [vp, vp, i32, i32, C.c_float, C.c_float, vp, i64, vp]
     lib.lamslide_setup_conditioning.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.lamslide_ksample_errors.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.lamslide_lincomb3.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i64, vp]
     lib.lamslide_first_stage_create.argtypes = [C.POINTER(FirstStageConfig), C.POINTER(TensorDesc), i32, C.POINTER(vp)]
     lib.lamslide_first_stage_destroy.argtypes = [vp]
     lib.lamslide_first_stage_destroy.restype = None

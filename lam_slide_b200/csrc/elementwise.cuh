@@ -323,4 +323,22 @@ ksample_errors_kernel(const float* __restrict__ preds, const float* __restrict__
   }
 }
 
+// ---- out = px * x + pm * m + pw * w  (w nullable) — the update rules of the SDE sampler (integrators.py:29-52: Euler-Maruyama,
+// Heun; transport.py:266-299: last step) are all linear in (state, network output, noise) with time-only coefficients, which the
+// host evaluates in fp64 (lam_slide_b200/transport.py).  out may alias x.
+__global__ void __launch_bounds__(256)
+lincomb3_kernel(float4* __restrict__ out, const float4* __restrict__ x, const float4* __restrict__ m, const float4* __restrict__ w,
+                float px, float pm, float pw, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 xv = x[i], mv = m ? m[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 o;
+  o.x = fmaf(pm, mv.x, px * xv.x), o.y = fmaf(pm, mv.y, px * xv.y), o.z = fmaf(pm, mv.z, px * xv.z), o.w = fmaf(pm, mv.w, px * xv.w);
+  if (w) {
+    const float4 wv = w[i];
+    o.x = fmaf(pw, wv.x, o.x), o.y = fmaf(pw, wv.y, o.y), o.z = fmaf(pw, wv.z, o.z), o.w = fmaf(pw, wv.w, o.w);
+  }
+  out[i] = o;
+}
+
 }  // namespace lam

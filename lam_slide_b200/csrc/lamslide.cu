@@ -1067,6 +1067,19 @@ extern "C" int lamslide_setup_conditioning(const float* latents, float* x_cond, 
   return 0;
 }
 
+// out = px * x + pm * m + pw * w (m, w nullable; out may alias x): one step piece of the SDE sampler (integrators.py:29-52).
+extern "C" int lamslide_lincomb3(float* out, const float* x, const float* m, const float* w, float px, float pm, float pw, int64_t numel,
+                                 void* stream) {
+  if (!out || !x) return fail(LAMSLIDE_ERR_INVALID, "null argument");
+  if (numel <= 0 || numel % 4) return fail(LAMSLIDE_ERR_INVALID, "numel %lld must be a positive multiple of 4", (long long)numel);
+  if (((uintptr_t)out | (uintptr_t)x | (uintptr_t)m | (uintptr_t)w) & 15) return fail(LAMSLIDE_ERR_INVALID, "operands must be 16-byte aligned");
+  const long long n4 = numel / 4;
+  lincomb3_kernel<<<cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>((float4*)out, (const float4*)x, (const float4*)m, (const float4*)w, px,
+                                                                   pm, pw, n4);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // K-sample evaluation metrics (second_stage/nba.py:161-238, pedestrian.py:149-226: mode 0; md17.py:139-171: mode 1).
 extern "C" int lamslide_ksample_errors(const float* preds, const float* target, float* ades, float* fdes, int32_t K, int32_t num_runs,
                                        int32_t B, int32_t T, int32_t A, int32_t D, int32_t mode, void* stream) {

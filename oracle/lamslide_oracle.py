@@ -235,6 +235,114 @@ def ode_sample(model_fn, x0: Tensor, *, path_type: str = "GVP", prediction: str 
     return torch.stack(states)
 
 
+# ---- SDE sampler: Sampler.sample_sde + integrators.sde --------------------------------------
+def _plan(path_type: str, tt: Tensor):
+    """(alpha, d_alpha, sigma, d_sigma, d_alpha / alpha) of ICPlan (path.py:27-37) / GVPCPlan (path.py:192-206) at ``tt``."""
+    if path_type == "GVP":
+        return (torch.sin(tt * math.pi / 2), math.pi / 2 * torch.cos(tt * math.pi / 2), torch.cos(tt * math.pi / 2),
+                -math.pi / 2 * torch.sin(tt * math.pi / 2), math.pi / (2 * torch.tan(tt * math.pi / 2)))
+    if path_type == "Linear":
+        return tt, 1.0, 1 - tt, -1.0, 1 / tt
+    raise NotImplementedError(path_type)
+
+
+def score(path_type: str, prediction: str, x: Tensor, t: Tensor, m: Tensor) -> Tensor:
+    """Transport.get_score — transport.py:204-226 with path.py:73-95 (score from velocity / data), ``m`` = network output."""
+    tt = t.reshape(-1, *([1] * (x.dim() - 1)))
+    alpha, d_alpha, sigma, d_sigma, _ = _plan(path_type, tt)
+    if prediction == "noise":
+        return m / -sigma
+    if prediction == "score":
+        return m
+    if prediction == "velocity":
+        rar = alpha / d_alpha
+        var = sigma ** 2 - rar * d_sigma * sigma
+        return (rar * m - x) / var
+    if prediction == "data":
+        return -(1 / sigma ** 2) * (x - alpha * m)
+    raise NotImplementedError(prediction)
+
+
+def diffusion(path_type: str, x: Tensor, t: Tensor, form: str, norm: float) -> Tensor:
+    """ICPlan.compute_diffusion — path.py:49-71 (the SBDM entry is compute_drift(x, t)[1], path.py:39-47)."""
+    tt = t.reshape(-1, *([1] * (x.dim() - 1)))
+    _, _, sigma, d_sigma, ratio = _plan(path_type, tt)
+    choices = {
+        "constant": lambda: norm,
+        "SBDM": lambda: norm * (ratio * sigma ** 2 - sigma * d_sigma),
+        "sigma": lambda: norm * sigma,
+        "linear": lambda: norm * (1 - tt),
+        "decreasing": lambda: 0.25 * (norm * torch.cos(math.pi * tt) + 1) ** 2,
+        "inccreasing-decreasing": lambda: norm * torch.sin(math.pi * tt) ** 2,
+    }
+    return choices[form]()
+
+
+def sde_interval(path_type: str, prediction: str, diffusion_form: str, last_step_size: float) -> Tuple[float, float]:
+    """Transport.check_interval (transport.py:69-101) for sde=True, eval=True, reverse=False on the Linear / GVP plans with the
+    default eps of CreateTransport (transport/__init__.py:57-68: 1e-3 unless velocity, then 0)."""
+    eps = 0.0 if prediction == "velocity" else 1e-3
+    t0 = eps if (diffusion_form == "SBDM") or prediction != "velocity" else 0
+    t1 = 1 - eps if last_step_size == 0 else 1 - last_step_size
+    return t0, t1
+
+
+def sde_sample(model_fn, x0: Tensor, noises: Sequence[Tensor], *, path_type: str = "GVP", prediction: str = "data",
+               sampling_method: str = "Euler", diffusion_form: str = "SBDM", diffusion_norm: float = 1.0,
+               last_step: Optional[str] = "Mean", last_step_size: float = 0.04, num_steps: int = 250) -> List[Tensor]:
+    """Sampler.sample_sde (transport.py:301-363) around integrators.sde (integrators.py:7-78): Euler-Maruyama or Heun over
+    ``linspace(t0, t1, num_steps)`` (num_steps - 1 steps), then the last step (None / Mean / Tweedie / Euler).  ``noises[i]``
+    stands in for the ``th.randn`` of step i.  Returns the ``num_steps`` states the reference returns."""
+    if last_step is None:
+        last_step_size = 0.0
+    t0, t1 = sde_interval(path_type, prediction, diffusion_form, last_step_size)
+    grid = torch.linspace(t0, t1, num_steps)
+    dt = grid[1] - grid[0]
+
+    def ode_drift(x, t):
+        return drift(path_type, prediction, x, t, model_fn(x, t))
+
+    def sde_drift(x, t):
+        m = model_fn(x, t)
+        return drift(path_type, prediction, x, t, m) + diffusion(path_type, x, t, diffusion_form, diffusion_norm) * score(
+            path_type, prediction, x, t, m)
+
+    x = x0
+    xs: List[Tensor] = []
+    for i, ti in enumerate(grid[:-1]):
+        w = noises[i]
+        dw = w * torch.sqrt(dt)
+        t = torch.ones(x.shape[0]) * ti
+        if sampling_method == "Euler":
+            d = sde_drift(x, t)
+            mean_x = x + d * dt
+            x = mean_x + torch.sqrt(2 * torch.as_tensor(diffusion(path_type, x, t, diffusion_form, diffusion_norm))) * dw
+        elif sampling_method == "Heun":
+            dif = diffusion(path_type, x, t, diffusion_form, diffusion_norm)
+            xhat = x + torch.sqrt(2 * torch.as_tensor(dif)) * dw
+            k1 = sde_drift(xhat, t)
+            xp = xhat + dt * k1
+            k2 = sde_drift(xp, t + dt)
+            x = xhat + 0.5 * dt * (k1 + k2)
+        else:
+            raise NotImplementedError(sampling_method)
+        xs.append(x)
+    ts = torch.ones(x0.shape[0]) * t1
+    if last_step is None:
+        x = xs[-1]
+    elif last_step == "Mean":
+        x = xs[-1] + sde_drift(xs[-1], ts) * last_step_size
+    elif last_step == "Tweedie":
+        alpha, _, sigma, _, _ = _plan(path_type, ts)
+        x = xs[-1] / alpha[0] + (sigma[0] ** 2) / alpha[0] * score(path_type, prediction, xs[-1], ts, model_fn(xs[-1], ts))
+    elif last_step == "Euler":
+        x = xs[-1] + ode_drift(xs[-1], ts) * last_step_size
+    else:
+        raise NotImplementedError(last_step)
+    xs.append(x)
+    return xs
+
+
 def setup_conditioning(latents: Tensor, cond_idx: Sequence[int], mask_cond_mean: bool = True) -> Tuple[Tensor, Tensor]:
     """SecondStageCondLightningBase.setup_conditioning — lightning_base.py:240-263."""
     B, T, L, _ = latents.shape

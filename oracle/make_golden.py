@@ -115,6 +115,74 @@ def make_ksample_golden() -> None:
     torch.save(fixtures, os.path.join(GOLDEN_DIR, "ksample_metrics.pt"))
 
 
+# SDE sampler: the reference's own Sampler.sample_sde / integrators.sde around its LatentSIV3
+SDE_CASES = [
+    dict(case="sde_gvp_data_euler", cfg="pedestrian", overrides=dict(depth=1), B=2, T=6, path_type="GVP", prediction="data",
+         kwargs=dict(sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0, last_step="Mean", last_step_size=0.04, num_steps=8),
+         seeds=(151, 152, 153)),
+    dict(case="sde_gvp_data_heun", cfg="pedestrian", overrides=dict(depth=1), B=2, T=6, path_type="GVP", prediction="data",
+         kwargs=dict(sampling_method="Heun", diffusion_form="sigma", diffusion_norm=0.7, last_step="Euler", last_step_size=0.04, num_steps=6),
+         seeds=(161, 162, 163)),
+    dict(case="sde_linear_velocity_tweedie", cfg="pedestrian", overrides=dict(depth=1), B=2, T=6, path_type="Linear", prediction="velocity",
+         kwargs=dict(sampling_method="Euler", diffusion_form="linear", diffusion_norm=1.0, last_step="Tweedie", last_step_size=0.04, num_steps=7),
+         seeds=(171, 172, 173)),
+    dict(case="sde_gvp_data_nolast", cfg="pedestrian", overrides=dict(depth=1), B=2, T=6, path_type="GVP", prediction="data",
+         kwargs=dict(sampling_method="Euler", diffusion_form="decreasing", diffusion_norm=1.0, last_step=None, last_step_size=0.04, num_steps=5),
+         seeds=(181, 182, 183)),
+]
+
+
+def sde_case_inputs(c: dict):
+    cfg = get_config(c["cfg"], **c["overrides"])
+    s_bb, s_x, s_noise = c["seeds"]
+    bb_sd = O.init_backbone_params(cfg["backbone"], s_bb)
+    g = torch.Generator().manual_seed(s_x)
+    L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+    shape = (c["B"], c["T"], L, D)
+    x0 = torch.randn(shape, generator=g)
+    x_cond = torch.randn(shape, generator=g)
+    mask = torch.zeros(c["B"], c["T"], L, dtype=torch.int64)
+    mask[:, :2] = 1
+    y = torch.randn(c["B"], cfg["backbone"]["vec_in_dim"], generator=g) if cfg["backbone"]["vec_in_dim"] else None
+    return cfg, bb_sd, x0, x_cond, mask, y, s_noise
+
+
+def make_sde_golden(ref) -> None:
+    import src.modules.transport.integrators as integ  # the reference module (torchdiffeq shim installed by load_reference)
+    fixtures = {}
+    for c in SDE_CASES:
+        cfg, bb_sd, x0, x_cond, mask, y, s_noise = sde_case_inputs(c)
+        bb = cfg["backbone"]
+        net = ref.LatentSIV3(depth=bb["depth"], in_dim=bb["in_dim"], hidden_size=bb["hidden_size"], num_heads=bb["num_heads"],
+                             vec_in_dim=bb["vec_in_dim"], mlp_ratio=bb["mlp_ratio"], normalize=bb["normalize"], theta=bb["theta"]).eval()
+        net.load_state_dict(bb_sd, strict=True)
+        si = ref.CreateTransport(path_type=c["path_type"], prediction=c["prediction"])()
+        fn = ref.Sampler(si).get_sample_fn("SDE", dict(c["kwargs"]))
+        noises = []
+        real_randn = integ.th.randn
+
+        def recording_randn(*a, **k):  # integrators.py:31,41 draw th.randn(x.size()) per step: keep what was drawn
+            w = real_randn(*a, **k)
+            noises.append(w.clone())
+            return w
+
+        kw = dict(x_cond=x_cond, x_cond_mask=mask)
+        if y is not None:
+            kw["y"] = y
+        torch.manual_seed(s_noise)
+        integ.th.randn = recording_randn
+        try:
+            with torch.no_grad():
+                xs = fn(x0, lambda xt, t, **k: net(x=xt, t=t, **k), **kw)
+        finally:
+            integ.th.randn = real_randn
+        assert len(xs) == c["kwargs"]["num_steps"] and len(noises) == c["kwargs"]["num_steps"] - 1
+        fixtures[c["case"]] = dict(case=dict(c), checksums=dict(bb=O.state_checksum(bb_sd), x0=float(x0.double().sum())),
+                                   noises=torch.stack(noises), states=torch.stack(xs))
+        print(f"{c['case']:28s} states {tuple(torch.stack(xs).shape)}  |x| max {float(torch.stack(xs).abs().max()):.3f}")
+    torch.save(fixtures, os.path.join(GOLDEN_DIR, "sde_sampler.pt"))
+
+
 def case_inputs(c: dict):
     """Everything a test needs to re-create the inputs of a golden case (shared with tests/)."""
     cfg = get_config(c["cfg"], **c["overrides"])
@@ -140,6 +208,7 @@ def main() -> None:
     torch.set_num_threads(os.cpu_count())
     make_rollout_golden(ref)
     make_ksample_golden()
+    make_sde_golden(ref)
     if "--rollout-only" in sys.argv or "--widened-only" in sys.argv:
         return
     for c in CASES:

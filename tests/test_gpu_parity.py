@@ -264,6 +264,36 @@ def test_ksample_evaluator_equals_k_sample_calls(name, mode):
     assert torch.allclose(fdes.cpu(), want_f, rtol=1e-5, atol=1e-6)
 
 
+def test_sde_sampler_vs_reference_golden():
+    """SDE sampler: Sampler.get_sample_fn("SDE", ...) on the GPU path (C-ABI backbone forward + lamslide_lincomb3
+    updates, fp64 host coefficients) against the states of the reference's own Sampler.sample_sde, replaying its recorded noise."""
+    import lam_slide_b200 as P
+    from oracle.make_golden import SDE_CASES, sde_case_inputs
+    fx = load_golden("sde_sampler")
+    for c in SDE_CASES:
+        cfg, bb_sd, x0, x_cond, mask, y, _ = sde_case_inputs(c)
+        f = fx[c["case"]]
+        bb = cfg["backbone"]
+        net = P.LatentSIV3(depth=bb["depth"], in_dim=bb["in_dim"], hidden_size=bb["hidden_size"], num_heads=bb["num_heads"],
+                           vec_in_dim=bb.get("vec_in_dim"), mlp_ratio=bb["mlp_ratio"], theta=bb.get("theta", 10_000),
+                           normalize=bb.get("normalize", False), n_timesteps=c["T"])
+        net.load_state_dict(bb_sd, strict=True)
+        net = net.cuda()
+        noises = list(f["noises"])
+        si = P.CreateTransport(path_type=c["path_type"], prediction=c["prediction"])()
+        fn = P.Sampler(si, noise_fn=lambda shape, device: noises.pop(0)).get_sample_fn("SDE", dict(c["kwargs"]))
+        kw = dict(x_cond=x_cond.cuda(), x_cond_mask=mask.cuda())
+        if y is not None:
+            kw["y"] = y.cuda()
+        xs = fn(x0.cuda(), lambda xt, t, **k: net(x=xt, t=t, **k), **kw)
+        assert len(xs) == c["kwargs"]["num_steps"] and not noises
+        got = torch.stack(xs).cpu()
+        # the stochastic integrators amplify the bf16 network error step by step (SBDM near t0 = 1e-3 by ~1/t): same tolerance class as
+        # the per-step velocity of the ODE path, relative to the state magnitude of each step
+        for i in range(got.shape[0]):
+            assert max_rel(got[i], f["states"][i]) < VEL_TOL, (c["case"], i, max_rel(got[i], f["states"][i]))
+
+
 def test_full_size_batch_properties():
     """BASELINE.json's full configuration (4AA peptides, T = 1000, B = 64 => 128 000 tokens per launch; far beyond what the oracle
     finishes in seconds) through size-independent properties of the path: trajectories are independent, so (1) the run is

@@ -69,6 +69,26 @@ def test_oracle_ksample_metrics_match_reference_golden():
         assert torch.allclose(fdes, f["fdes"], rtol=1e-6, atol=1e-7), c["case"]
 
 
+def test_oracle_sde_sampler_matches_reference_golden():
+    """SDE sampler: the oracle restatement of Sampler.sample_sde + integrators.sde (Euler-Maruyama / Heun, four
+    diffusion forms, all last-step variants) against the states the reference's own Sampler produced with the recorded noise."""
+    from oracle.make_golden import SDE_CASES, sde_case_inputs
+    torch.set_num_threads(8)
+    fx = load_golden("sde_sampler")
+    for c in SDE_CASES:
+        cfg, bb_sd, x0, x_cond, mask, y, _ = sde_case_inputs(c)
+        f = fx[c["case"]]
+        assert abs(O.state_checksum(bb_sd) - f["checksums"]["bb"]) <= 1e-6 * max(1.0, abs(f["checksums"]["bb"]))
+        assert abs(float(x0.double().sum()) - f["checksums"]["x0"]) < 1e-6
+        with torch.no_grad():
+            xs = O.sde_sample(lambda x, t: O.backbone_forward(bb_sd, cfg["backbone"], x, t, x_cond, mask, y), x0, list(f["noises"]),
+                              path_type=c["path_type"], prediction=c["prediction"], **c["kwargs"])
+        got = torch.stack(xs)
+        assert got.shape == f["states"].shape
+        for i in range(got.shape[0]):
+            assert max_rel(got[i], f["states"][i]) < 5e-4, (c["case"], i)
+
+
 def test_backbone_single_eval_matches_golden():
     fx = load_golden("nba_full")
     c = CASE_BY_NAME["nba_full"]

@@ -73,8 +73,9 @@ def test_transport_interval_and_api():
     assert tr.check_interval(tr.train_eps, tr.sample_eps, eval=True) == (1e-3, 1 - 1e-3)
     tr = P.CreateTransport()()
     assert tr.check_interval(tr.train_eps, tr.sample_eps, eval=True) == (0, 1)
+    assert callable(P.Sampler(tr).get_sample_fn("SDE", {}))  # Euler-Maruyama with the reference's defaults (transport.py:480-487)
     with pytest.raises(NotImplementedError):
-        P.Sampler(tr).get_sample_fn("SDE", {})
+        P.Sampler(tr).get_sample_fn("SDE", {"sampling_method": "Milstein"})
     with pytest.raises(NotImplementedError):
         P.Sampler(tr).get_sample_fn("ODE", {})  # reference default dopri5 is not implemented
     fn = P.Sampler(tr).get_sample_fn("ODE", {"sampling_method": "euler", "num_steps": 10})

@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(float* __restrict__
 // a [W_hi | W_hi | W_lo] weight the ordinary bf16 GEMM then evaluates u_hi W_hi + u_lo W_hi + u_hi W_lo, i.e. the head
 // projection at ~16 mantissa bits.  The head is 0.4 % of the FLOPs but its operand rounding would otherwise dominate the
 // error of the predicted latent (and hence the decoded coordinates).
+// (A variant with two rows per warp — 16 lanes per row, 32-byte loads and 16-byte stores per lane — measured 9.2 ms per step against
+// 8.4 ms for this one on B200, 4AA: more bytes in flight per warp did not help, the kernel runs at 4.7 TB/s.)
 template <int HV, bool SPLIT3 = false>
 __global__ void __launch_bounds__(256)
 ln_modulate_kernel(const float* __restrict__ h, __nv_bfloat16* __restrict__ u, const float* __restrict__ shift,

@@ -262,6 +262,11 @@ def test_ksample_evaluator_equals_k_sample_calls(name, mode):
     assert ades.shape == want_a.shape
     assert torch.allclose(ades.cpu(), want_a, rtol=1e-5, atol=1e-6)
     assert torch.allclose(fdes.cpu(), want_f, rtol=1e-5, atol=1e-6)
+    # the runs may be solved in chunks (memory bound on B * K): same numbers up to fp32 rounding (the ODE is bit-identical; the
+    # first-stage decoder picks its GEMM kernel by row count, FMA below 4096 rows, 3xTF32 above)
+    ev1 = P.KSampleEvaluator(m, K=K, num_runs=runs, mode=mode, max_trajectories=c["B"])
+    a1, f1 = ev1.test_step({k: v.clone() for k, v in batch.items()}, noise=noise)
+    assert torch.allclose(a1, ades, rtol=1e-5, atol=1e-5) and torch.allclose(f1, fdes, rtol=1e-5, atol=1e-5)
 
 
 def test_sde_sampler_vs_reference_golden():

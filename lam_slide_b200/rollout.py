@@ -6,8 +6,9 @@ The reference rolls ONE peptide at a time: every roll-out step builds a B = 1 ba
 frame, calls ``sample()`` (which encodes all T identical frames), moves the block to the host side of the loop and continues
 from its last frame.  Here many chains advance together (``[B, R, 14, 3]`` conditioning frames), everything stays on the
 device between steps, and the conditioning frame is encoded ONCE per chain and step — the first stage treats frames
-independently, so broadcasting its latents over T is bit-identical to encoding T copies (tests/test_gpu_parity.py checks
-exactly that against ``model.sample(create_batch(...))``).
+independently, so broadcasting its latents over T is identical to encoding T copies (tests/test_gpu_parity.py checks
+that bit for bit against ``model.sample(create_batch(...))``; at sizes where the first stage switches its GEMM kernel by row
+count — FMA below 4096 rows, 3xTF32 above — the two agree to fp32 rounding instead).
 Trajectory-file I/O (``sample_traj``, mdtraj / PDB writers; sampling.py:65-142) is out of scope.
 """
 from __future__ import annotations

@@ -22,8 +22,10 @@
 //     stream 1 (warps 0,1):  for each hidden chunk j (128 columns):  ACC1 = u W1m_j^T     (units of 2 k-blocks = 8 MMAs, N = 128)
 //     stream 2 (warps 2,3):  OUT = attn W2[:, :H]^T ;  then per chunk j:  OUT += gelu(ACC1 + b1m_j) W2[:, H+128j ..]^T
 //                            (units of NU = 192 output columns for H = 384, else min(H, 256); 4 MMAs each)
-// The attention tiles travel through ring 1 (between the W1m units of chunk 0 and chunk 1 of the same m-block), so they are
-// prefetched while the previous m-block drains and G stays free for the first GELU chunk.
+// The attention tiles travel through ring 1: half of them right behind the W1m units of chunk 0 (prefetched while the previous
+// m-block drains), the other half behind the units of the last chunk (prefetched during the last chunks), so neither group
+// waits for a load and G stays free for the GELU chunks.  (All six at the start cost 7.9k cycles for 4.6k of MMA: with three ring
+// stages the later tiles were loaded only after the earlier ones had been consumed.)
 // Warps 4..19: epilogue (TMEM lane quarter = warp % 4, column quarter = (warp - 4) / 4): ACC1 -> + bias -> GELU -> bf16 -> G;
 // at the end of the m-block OUT -> gate * (acc + b2) -> TMA f32 reduce-add into h (16-column x 32-row boxes staged in G; measured,
 // scripts/drain_bench.cu: 4.8 us per m-block alone, 12 us when all CTAs drain at once (HBM read-modify-write), against 6.4 / 16 us
@@ -84,6 +86,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
   const int NI = H / NU;               // stream-2 units per k-block
   const int NJ = M / 128;              // hidden chunks
   const int kUnit2 = NU * 64;          // this CTA's half of a W2 unit: [NU/2 rows x 64 k]
+  const int KB1 = KB / 2;              // attention k-blocks consumed at the start of an m-block; the other KB - KB1 at its end
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -203,8 +206,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
           __syncwarp();
           if (++s == stages1) s = 0, ph ^= 1;
         }
-        if (j == 0) {
-          for (int kk = 0; kk < KB; ++kk) {
+        if (j == 0 || j == NJ - 1) {  // attention k-blocks: the first KB1 after chunk 0's units, the rest after the last chunk's
+          const int k_lo = j == 0 ? 0 : KB1, k_hi = j == NJ - 1 ? KB : KB1;
+          for (int kk = k_lo; kk < k_hi; ++kk) {
             mbar_wait(&empty1[s], ph ^ 1);
             if (elect_one()) {
               if (leader) mbar_arrive_expect_tx(&full1[s], 2 * kTile);
@@ -225,6 +229,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
       int s = 0;
       uint32_t ph = 0, it = 0, n_acc1 = 0;
       for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++it) {
+        // attn_done completes twice per m-block (first / second group of attention tiles): wait for each in turn
+        if (it > 0) mbar_wait(attn_done, 1);  // the previous m-block's trailing attention tiles have left ring 1
         for (int j = 0; j < NJ; ++j, ++n_acc1) {
           mbar_wait(acc1_empty, (n_acc1 & 1) ^ 1);  // the epilogue warps of both CTAs have read the previous chunk
           tcgen05_fence_after();
@@ -254,11 +260,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
             if (++s == stages1) s = 0, ph ^= 1;
           }
           TRACE(1, 2);
-          if (j == 0) {  // the attention tiles (issuer 2)
-            mbar_wait(attn_done, it & 1);
+          if (j == 0) {  // the leading attention tiles (issuer 2)
+            mbar_wait(attn_done, 0);
             TRACE(1, 3);
-            ring1_skip(s, ph, KB);
+            ring1_skip(s, ph, KB1);
           }
+          if (j == NJ - 1) ring1_skip(s, ph, KB - KB1);  // the trailing ones (waited for at the top of the next m-block)
         }
       }
     }
@@ -280,11 +287,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
       if (++s == stages2) s = 0, ph ^= 1;
     };
     for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step) {
-      for (int kk = 0; kk < KB; ++kk)
+      for (int kk = 0; kk < KB1; ++kk)
         for (int i = 0; i < NI; ++i) unit(i * NU, kk * 64);
       for (int j = 0; j < NJ; ++j)
         for (int kk = 0; kk < 2; ++kk)
           for (int i = 0; i < NI; ++i) unit(i * NU, H + j * 128 + kk * 64);
+      for (int kk = KB1; kk < KB; ++kk)
+        for (int i = 0; i < NI; ++i) unit(i * NU, kk * 64);
     }
   } else if (warp == 3) {
     // ===== issuer 2 (leader): OUT = attn W2a^T, then OUT += gelu chunk j W2[:, H + 128 j ..]^T =====
@@ -314,18 +323,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
         TRACE(2, 2);
         mbar_wait(acc1_full, n_chunk & 1);  // chunk 0 of this m-block is complete: its W1m units (issuer 1) have left ring 1
         ring1_skip(s1, ph1, KB / 2);
-        for (int kk = 0; kk < KB; ++kk) {
-          mbar_wait(&full1[s1], ph1);
-          tcgen05_fence_after();
-          const uint64_t a_desc = t_desc0 + static_cast<uint64_t>(s1 * (kTile >> 4));
-          for (int i = 0; i < NI; ++i) mma_unit(tmem_out + i * NU, a_desc, kk == 0);
-          if (elect_one()) {
-            umma_commit_pair(&empty1[s1]);
-            if (kk == KB - 1) umma_commit_pair(attn_done);
+        auto attn_tiles = [&](int k_lo, int k_hi) {
+          for (int kk = k_lo; kk < k_hi; ++kk) {
+            mbar_wait(&full1[s1], ph1);
+            tcgen05_fence_after();
+            const uint64_t a_desc = t_desc0 + static_cast<uint64_t>(s1 * (kTile >> 4));
+            for (int i = 0; i < NI; ++i) mma_unit(tmem_out + i * NU, a_desc, kk == 0);
+            if (elect_one()) {
+              umma_commit_pair(&empty1[s1]);
+              if (kk == k_hi - 1) umma_commit_pair(attn_done);
+            }
+            __syncwarp();
+            if (++s1 == stages1) s1 = 0, ph1 ^= 1;
           }
-          __syncwarp();
-          if (++s1 == stages1) s1 = 0, ph1 ^= 1;
-        }
+        };
+        attn_tiles(0, KB1);  // prefetched into ring 1 while the previous m-block drained
         TRACE(2, 3);
         ring1_skip(s1, ph1, (NJ - 1) * (KB / 2));  // the W1m units of chunks 1.. (issuer 1)
         for (int j = 0; j < NJ; ++j, ++n_chunk) {
@@ -339,6 +351,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
             __syncwarp();
           }
         }
+        // the trailing attention tiles were loaded behind the last chunk's W1m units, i.e. during the last chunks' compute (the last
+        // G2 above implies chunk NJ - 1 is complete, so those ring-1 stages have been through issuer 1)
+        attn_tiles(KB1, KB);
         TRACE(2, 6);
         if (elect_one()) umma_commit_pair(out_full);
         __syncwarp();

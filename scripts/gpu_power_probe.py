@@ -1,5 +1,5 @@
 """Developer probe: loop one kernel for ~2 s while sampling nvidia-smi power / clocks, to tell power-capped from structural limits.
-Usage: python scripts/gpu_power_probe.py mainloop|cublas|attn"""
+Usage: python scripts/gpu_power_probe.py mainloop|mainloop1|cublas|bigcublas|attn|attn_tc|fused|linear1"""
 import os
 import subprocess
 import sys
@@ -28,6 +28,41 @@ def main():
     elif what == "mainloop1":
         fn = lambda: L.check(lib.lamslide_debug_gemm_mainloop(a.data_ptr(), b.data_ptr(), rows, N, K, -192, st))
         flops = 2.0 * rows * N * K
+    elif what in ("attn", "attn_tc"):
+        B, T, Lx, H, heads = 64, 1000, 2, 384, 16
+        n = B * T * Lx
+        qkv = (torch.randn(n, 3 * H, device="cuda") * 0.5).to(torch.bfloat16)
+        out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
+        mode = 2 if what == "attn" else 3
+        fn = lambda: L.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, mode, st))
+        flops = 4.0 * 24 * T * T * heads * B * Lx
+    elif what == "fused":
+        import math
+        H, M = 384, 1536
+        u = torch.randn(rows, H, device="cuda").to(torch.bfloat16)
+        act = torch.randn(rows, H + M, device="cuda").to(torch.bfloat16)
+        w1 = (torch.randn(3 * H + M, H, device="cuda") / math.sqrt(H)).to(torch.bfloat16)
+        w2 = (torch.randn(H, H + M, device="cuda") / math.sqrt(H + M)).to(torch.bfloat16)
+        b1 = torch.randn(3 * H + M, device="cuda") * 0.1
+        b2 = torch.randn(H, device="cuda") * 0.1
+        gate = torch.randn(rows // 2000 + 1, H, device="cuda")
+        hh = torch.zeros(rows, H, device="cuda")
+        fn = lambda: L.check(lib.lamslide_debug_fused_mlp(u.data_ptr(), act.data_ptr(), w1.data_ptr(), w2.data_ptr(), b1.data_ptr(), b2.data_ptr(),
+                                                          gate.data_ptr(), hh.data_ptr(), rows, H, M, 2000, st))
+        flops = 2.0 * rows * (H * M + (H + M) * H)
+    elif what == "linear1":
+        import math
+        H, M, heads = 384, 0, 16
+        u = torch.randn(rows, H, device="cuda").to(torch.bfloat16)
+        w1 = (torch.randn(3 * H + 1536, H, device="cuda") / math.sqrt(H)).to(torch.bfloat16)
+        bias = torch.randn(3 * H + 1536, device="cuda") * 0.1
+        gq = torch.ones(24, device="cuda")
+        gk = torch.ones(24, device="cuda")
+        qkv = torch.empty(rows, 3 * H, device="cuda", dtype=torch.bfloat16)
+        act = torch.empty(rows, H + 1536, device="cuda", dtype=torch.bfloat16)
+        fn = lambda: L.check(lib.lamslide_debug_linear1(u.data_ptr(), w1.data_ptr(), bias.data_ptr(), gq.data_ptr(), gk.data_ptr(), qkv.data_ptr(),
+                                                        act.data_ptr(), rows, H, 1536, heads, 2, 1000, 10000.0, 32, st))
+        flops = 2.0 * rows * (3 * H + 1536) * H
     elif what == "cublas":
         fn = lambda: torch.matmul(a, b.t(), out=c)
         flops = 2.0 * rows * N * K

@@ -64,3 +64,22 @@ def sample_sharded(model, batch: Dict[str, Tensor], seed: int = 0, gather: bool 
     noise = per_sample_noise(seed, lo, hi, (T, L, D), model.device)
     out = model.sample(dict(local), noise=noise)[cfg["main_output"]]
     return gather_samples(out, B, group) if gather else out
+
+
+@torch.no_grad()
+def rollouts_sharded(wrapper, cond_pos: Tensor, res: Tensor, res_mask: Tensor, num_rollouts: int = 1, seed: int = 0,
+                     gather: bool = True, group=None) -> Tensor:
+    """``SIAtom14SamplingWrapper.sample_rollouts`` with the B chains sharded over the ranks (chains are independent: no data-path
+    collective), one all-gather of the ``[b_r, num_rollouts * T, R, 14, 3]`` blocks at the end.  The noise of roll-out step ``i`` of
+    global chain ``c`` is seeded by ``(seed, i, c)``, so the result does not depend on the number of ranks."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = cond_pos.shape[0]
+    lo, hi = shard_range(B, rank, world)
+    m = wrapper.model
+    cfg = m.cfg
+    T = m.hparams.n_timesteps
+    L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+    noise = torch.stack([per_sample_noise(seed * 7919 + i + 1, lo, hi, (T, L, D), m.device) for i in range(num_rollouts)])
+    out = wrapper.sample_rollouts(cond_pos[lo:hi], res[lo:hi], res_mask[lo:hi], num_rollouts=num_rollouts, noise=noise)
+    return gather_samples(out, B, group) if gather else out

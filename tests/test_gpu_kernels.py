@@ -207,7 +207,8 @@ def test_tcgen05_attention_matches_softmax_reference(B, T, L, H, heads, temporal
 
 @pytest.mark.parametrize("rows,H,M,rps", [
     (1000, 384, 1536, 250), (20000 + 37, 384, 1536, 2000), (128 * 150, 384, 1536, 2000), (333, 256, 1024, 160), (777, 128, 256, 40),
-    (4096, 256, 512, 5760), (100, 384, 1536, 50),
+    (4096, 256, 512, 5760), (100, 384, 1536, 50), (1, 384, 1536, 7), (128 * 149 * 2 + 5, 256, 1024, 1000), (40000, 128, 128, 640),
+    (256 * 75, 384, 128, 2000),
 ])
 def test_fused_mlp_linear2(rows, H, M, rps):
     """h += gate[b] * ([attn | gelu(u W1m^T + b1m)] W2^T + b2): the MLP half of linear1, GELU and linear2 in one kernel

@@ -40,7 +40,9 @@ def parse_args():
     ap.add_argument("--T", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--ref-batch", type=int, default=1)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the NBA / pedestrian / sweep lines and the GPU eager comparator")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay the headline step from a CUDA graph")
+    ap.add_argument("--ref-batch", type=int, default=4, help="trajectories per CPU step of the reference arm / cpu_baseline")
     return ap.parse_args()
 
 
@@ -125,6 +127,105 @@ def cpu_baseline(cfg, num_steps: int, B: int, reps: int, warmup: int):
     return times, torch.get_num_threads()
 
 
+def gpu_eager_baseline(cfg, num_steps: int, B: int, dev):
+    """Same-box GPU comparator: the oracle port (plain torch ops = what the reference's eager PyTorch modules execute) on the GPU,
+    (a) fp32 with TF32 matmuls (`matmul_precision: high`, src/train.py:48) and (b) under bf16 autocast (the reference's in-training
+    validation mode), SDPA attention as in mmdit.py:51.  A REPORTED baseline next to the CUDA path — never on the product path."""
+    from oracle import lamslide_oracle as O
+    O.USE_SDPA = True
+    fs_sd = {k: v.to(dev) for k, v in O.init_first_stage_params(cfg["first_stage"], 1).items()}
+    bb_sd = {k: v.to(dev) for k, v in O.init_backbone_params(cfg["backbone"], 2).items()}
+    batch = {k: v.to(dev) for k, v in O.synthetic_batch(cfg, B, 3).items()}
+    L = cfg["first_stage"]["encoder"]["num_latents"]
+    g = torch.Generator().manual_seed(4)
+    noise = torch.randn(B, cfg["T"], L, cfg["backbone"]["in_dim"], generator=g).to(dev)
+    y = torch.randn(B, 256, generator=g).to(dev) if cfg["n_classes"] else None
+    out = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for name, ctx in (("fp32_tf32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            def run():
+                with torch.no_grad():
+                    if ctx is None:
+                        return O.sample(fs_sd, bb_sd, cfg, batch, noise, num_steps=num_steps, y=y)
+                    with ctx:
+                        return O.sample(fs_sd, bb_sd, cfg, batch, noise, num_steps=num_steps, y=y)
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 2
+            e0.record()
+            for _ in range(reps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out[name] = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    out["what"] = "oracle port (eager torch ops, SDPA) on this GPU; same workload per trajectory as the headline line"
+    return out
+
+
+def secondary_lines(P, _lib, args, dev):
+    """BASELINE.json configs[1], [2], [4] on ONE GPU: NBA B=1024, pedestrian B=1024 (ragged agent counts), and a batch x ODE-steps
+    sweep of the 4AA shape.  Each entry: trajectories/s, ms per step, kernel launches per step; the small configurations also replayed
+    from a CUDA graph (SecondStageSampler.use_cuda_graphs)."""
+    from lam_slide_b200.synthetic import randomize_zero_init, synthetic_batch
+
+    def build(name, num_steps):
+        cfg = P.get_config(name)
+        torch.manual_seed(0)
+        m = P.SecondStageSampler(cfg, sampling_kwargs={"sampling_method": "euler", "num_steps": num_steps})
+        randomize_zero_init(m, seed=1)
+        return cfg, m.to(dev)
+
+    def time_sample(m, cfg, B, steps, warm, graph):
+        batch = {k: v.to(dev) for k, v in synthetic_batch(cfg, B, seed=2000 + B).items()}
+        L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+        noise = torch.randn(B, cfg["T"], L, D, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        m.use_cuda_graphs = graph
+        for _ in range(warm):
+            m.sample(dict(batch), noise=noise)
+        torch.cuda.synchronize()
+        _lib.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            m.sample(dict(batch), noise=noise)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        launches = _lib.launch_count() / steps
+        m.use_cuda_graphs = False
+        return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+                "launches_per_step": launches if not graph else "1 graph replay"}
+
+    from lam_slide_b200.configs import flops_per_trajectory
+    out = {}
+    for name in ("nba", "pedestrian"):
+        cfg, m = build(name, 10)
+        eager = time_sample(m, cfg, 1024, 10, 3, False)
+        graphed = time_sample(m, cfg, 1024, 10, 3, True)
+        eager["tflops"] = flops_per_trajectory(cfg, 10) * eager["value"] / 1e12
+        graphed["tflops"] = flops_per_trajectory(cfg, 10) * graphed["value"] / 1e12
+        out[f"{name}_b1024"] = {"workload": f"{name} sample(): T={cfg['T']}, N={cfg['N']}, num_steps=10", "eager": eager, "cuda_graph": graphed}
+        del m
+    sweep = []
+    for ns in (5, 10, 20, 50):
+        cfg, m = build("peptide", ns)
+        for B in ((8, 64, 512) if ns == 10 else (8, 64)):
+            r = time_sample(m, cfg, B, 2, 1, False)
+            r["num_steps"] = ns
+            r["tflops"] = flops_per_trajectory(cfg, ns) * r["value"] / 1e12
+            sweep.append(r)
+        del m
+    out["peptide_sweep"] = sweep
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, cfg):
     """--impl reference: the reference's own CPU path (oracle port; the Python reference cannot travel to the GPU box)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -184,52 +285,29 @@ def main():
     randomize_zero_init(model, seed=1)
     model = model.to(dev)
 
-    # synthetic inputs: per-rank shard of the global batch (seed derived from the global sample index range)
-    host_batch = synthetic_batch(cfg, B, seed=1004 + rank, pin=True)
+    # synthetic inputs: ONE global batch of world * B trajectories, replicated on every rank (host: pinned; device: resident in HBM);
+    # lam_slide_b200.dist.sample_sharded / sample_stream_sharded — the product's multi-GPU entry points — take this rank's rows,
+    # sample them and all-gather the decoded coordinates (world = 1: the same calls, the gather is a no-op)
+    from lam_slide_b200 import dist as D_
+    GB = world * B
+    host_batch = synthetic_batch(cfg, GB, seed=1004, pin=True)
     dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
-    g = torch.Generator(device=dev).manual_seed(77 + rank)
-    noise = torch.randn(B, T, L, D, device=dev, generator=g)
+    noise = D_.local_noise(model, host_batch, seed=77)  # this rank's rows of the global noise (row i depends on (seed, i) only)
     main_key = cfg["main_output"]
-    gather_buf = None
+    model.use_cuda_graphs = bool(args.cuda_graph)
 
     def step_device():
-        out = model.sample(dict(dev_batch), noise=noise)[main_key]
-        if dist_on:
-            nonlocal gather_buf
-            if gather_buf is None:
-                gather_buf = torch.empty((world * out.shape[0],) + tuple(out.shape[1:]), device=dev, dtype=out.dtype)
-            dist.all_gather_into_tensor(gather_buf, out.contiguous())
-        return out
+        return D_.sample_sharded(model, dev_batch, noise=noise)
 
     host_out = None
+    keep = {}
 
     def run_e2e(steps):
-        """`steps` calls of the public sampling API on HOST (pinned) batches: every step copies its inputs host->device and its
-        result device->host; SecondStageSampler.sample_stream overlaps those copies with the neighbouring steps' compute."""
+        """`steps` calls of the public sampling API on HOST (pinned) batches: every step copies this rank's rows host->device and its
+        result device->host (and all-gathers on the device when N > 1); the copies overlap the neighbouring steps' compute."""
         nonlocal host_out
-        for host_out in model.sample_stream(dict(host_batch) for _ in range(steps)):  # noise drawn on device like the reference
+        for host_out in D_.sample_stream_sharded(model, (host_batch for _ in range(steps)), keep=keep):  # noise drawn on device like the reference
             pass
-
-    def timed(fn, steps, whole=False):
-        if dist_on:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if whole:
-            fn(steps)  # returns after the last result has reached the host (sample_stream synchronises on its copy)
-        else:
-            for _ in range(steps):
-                fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if dist_on:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            dist.barrier()
-        return ms
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -246,8 +324,8 @@ def main():
     run_e2e(2)
     ms_e2e = timed(run_e2e, args.steps, whole=True)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
-    d2h = host_out.numel() * host_out.element_size()
+    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())  # all ranks together: each uploads its own rows
+    d2h = host_out.numel() * host_out.element_size() * world
 
     # per-kernel-class timing (CUDA events on the launching stream) on extra steps after the timed region
     peaks, peaks_src = load_peaks()
@@ -255,8 +333,9 @@ def main():
     if not args.no_profile:
         _lib.profile_begin()
         pr_steps = 2
+        model.use_cuda_graphs = False  # CUDA events cannot be recorded inside a graph replay
         for _ in range(pr_steps):
-            model.sample(dict(dev_batch), noise=noise)
+            D_.sample_sharded(model, dev_batch, noise=noise, gather=False)
         prof = _lib.profile_end()
         tot = sum(v["ms"] for v in prof.values())
         shares = {k: round(v["ms"] / tot, 4) for k, v in prof.items() if v["ms"] > 0}
@@ -290,11 +369,19 @@ def main():
     else:
         whole = None
 
+    secondary, gpu_eager = None, None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        dev_batch.clear()
+        torch.cuda.empty_cache()
+        secondary = secondary_lines(P, _lib, args, dev)
+        gpu_eager = gpu_eager_baseline(cfg, args.num_steps, 4, dev)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        times, cores = cpu_baseline(cfg, args.num_steps, 1, reps=3, warmup=1)
-        cpu = {"value": len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"3 x sample() of 1 trajectory (T={T}, num_steps={args.num_steps}), oracle port of the reference, fp32 torch CPU ops"}
+        rb = args.ref_batch
+        times, cores = cpu_baseline(cfg, args.num_steps, rb, reps=2, warmup=1)
+        cpu = {"value": rb * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"2 x sample() of {rb} trajectories (T={T}, num_steps={args.num_steps}), oracle port of the reference, fp32 torch CPU ops"}
 
     if rank == 0:
         line = {
@@ -304,7 +391,8 @@ def main():
             "config": {"workload": f"{args.config} sample(): encode + Euler ODE (num_steps={args.num_steps} => {args.num_steps - 1} evals) + decode"
                                    + (" + all_gather" if dist_on else ""),
                        "batch_per_gpu": B, "global_batch": B * world, "T": T, "entities": N, "latents": L, "latent_dim": D,
-                       "parallelism": f"batch-sharded x{world}", "weights": "random-init (seeded), zero-init layers re-drawn N(0,0.02)",
+                       "parallelism": f"batch-sharded x{world} (lam_slide_b200.dist.sample_sharded)", "cuda_graph": bool(args.cuda_graph),
+                       "weights": "random-init (seeded), zero-init layers re-drawn N(0,0.02)",
                        "l2": "working set (activations ~GBs per step) is far larger than the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -314,6 +402,8 @@ def main():
             "whole_step": whole,
             "kernel_time_shares": shares,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": gpu_eager,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if dist_on:

@@ -163,6 +163,10 @@ const char* lamslide_last_error(void);
 /* number of kernels this library launched on the calling thread since the last reset (bench.py's gpu_launches). */
 int64_t lamslide_launch_count(int32_t reset);
 
+/* test hook: launches of one named kernel family on the calling thread since the last reset ("attn_tc", "attn_seq", "attn_flash",
+ * "attn_rows", "attn_small", ...); reset != 0 clears ALL named counters after reading. */
+int64_t lamslide_debug_kernel_count(const char* name, int32_t reset);
+
 /* Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline and time shares).
  * begin() arms it for the calling thread; end() synchronises the device and writes a JSON object
  * {"gemm_linear1": {"ms": .., "launch_groups": ..}, ...} into json_out.  Not for use under CUDA-graph capture. */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "lamslide_first_stage_create", "lamslide_first_stage_destroy", "lamslide_first_stage_workspace_bytes",
     "lamslide_encode", "lamslide_decode", "lamslide_debug_gemm", "lamslide_debug_attention",
     "lamslide_debug_linear1", "lamslide_debug_linear2", "lamslide_debug_gemm_mainloop", "lamslide_debug_fused_mlp",
-    "lamslide_profile_begin", "lamslide_profile_end",
+    "lamslide_profile_begin", "lamslide_profile_end", "lamslide_debug_kernel_count",
 ]
 
 
@@ -105,6 +105,8 @@ def load() -> C.CDLL:
     lib.lamslide_debug_gemm_mainloop.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.lamslide_debug_fused_mlp.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.lamslide_profile_end.argtypes = [C.c_char_p, sz]
+    lib.lamslide_debug_kernel_count.argtypes = [C.c_char_p, i32]
+    lib.lamslide_debug_kernel_count.restype = i64
     if lib.lamslide_abi_version() != 1:
         raise LamSlideError("liblamslide.so ABI version mismatch")
     _lib = lib
@@ -123,6 +125,11 @@ def check(status: int) -> None:
 
 def launch_count(reset: bool = False) -> int:
     return int(load().lamslide_launch_count(1 if reset else 0))
+
+
+def kernel_count(name: str, reset: bool = False) -> int:
+    """Launches of one named kernel family since the last reset (test hook)."""
+    return int(load().lamslide_debug_kernel_count(name.encode(), 1 if reset else 0))
 
 
 def pack_state_dict(sd: Dict[str, torch.Tensor]) -> Tuple[C.Array, List[torch.Tensor]]:

@@ -57,18 +57,23 @@ def _layer(hidden: int, heads: int, mlp_hidden: int) -> nn.Module:  # latent_si_
 class _DeviceWorkspace:
     """Grow-only byte buffer on one device (PyTorch owns the memory; the C ABI never allocates)."""
 
+    ALIGN = 1024
+
     def __init__(self):
         self.buf: Optional[Tensor] = None
 
-    def get(self, nbytes: int, device: torch.device) -> Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
-            self.buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-        return self.buf
+    def get(self, nbytes: int, device: torch.device, align: int = ALIGN):
+        """``(aligned pointer, bytes available behind it)`` with at least ``nbytes`` available.  The capacity check is made on what
+        is left AFTER alignment (torch's allocations are 512-byte aligned, so up to ``align - 1`` bytes are skipped), and the true
+        remaining size goes to the C ABI, which checks it against what it needs."""
+        def avail(buf: Tensor) -> int:
+            p = buf.data_ptr()
+            return buf.numel() - ((p + align - 1) // align * align - p)
 
-    @staticmethod
-    def aligned_ptr(buf: Tensor, align: int = 1024) -> int:
-        p = buf.data_ptr()
-        return (p + align - 1) // align * align
+        if self.buf is None or self.buf.device != device or avail(self.buf) < nbytes:
+            self.buf = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
+        p = self.buf.data_ptr()
+        return (p + align - 1) // align * align, avail(self.buf)
 
 
 class LatentSIV3(nn.Module):
@@ -167,8 +172,7 @@ class LatentSIV3(nn.Module):
 
     def _workspace(self, B: int, T: int, L: int, device: torch.device):
         need = _lib.load().lamslide_backbone_workspace_bytes(self._handle, B, T, L)
-        buf = self._ws.get(need, device)
-        return _DeviceWorkspace.aligned_ptr(buf), need
+        return self._ws.get(need, device)
 
     @staticmethod
     def _prep(x: Tensor, dtype=torch.float32) -> Tensor:

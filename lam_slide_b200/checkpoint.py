@@ -26,15 +26,30 @@ def _read(ckpt: _PathOrDict) -> Mapping[str, Any]:
     return ckpt
 
 
+def _strip_compile_wrappers(sd: Mapping[str, Any]) -> Dict[str, Any]:
+    """``torch.compile`` wraps a module in ``OptimizedModule``, whose parameters live under ``_orig_mod.``: with ``compile: true``
+    (second_stage/peptide.py:58-60; the md17 / nba experiment configs) the reference's keys read ``backbone._orig_mod.x_in.weight``
+    and ``first_stage_model._orig_mod.backbone.*``.  The wrapper adds no parameters of its own, so dropping the path component
+    gives the eager names."""
+    out: Dict[str, Any] = {}
+    for k, v in sd.items():
+        k2 = ".".join(part for part in k.split(".") if part != "_orig_mod")
+        if k2 in out:
+            raise KeyError(f"checkpoint holds '{k2}' both under its eager name and under a torch.compile alias")
+        out[k2] = v
+    return out
+
+
 def select_state_dict(ckpt: _PathOrDict, use_ema: bool = True) -> Dict[str, torch.Tensor]:
     """The parameter dict ``sample()`` would run with: ``ckpt["ema"]["params"]`` when present and ``use_ema`` (lightning_base.py:
-    63-70), else ``ckpt["state_dict"]``; a bare state dict passes through."""
+    63-70), else ``ckpt["state_dict"]``; a bare state dict passes through.  ``_orig_mod.`` path components (checkpoints of
+    ``torch.compile``d modules) are removed."""
     c = _read(ckpt)
     if use_ema and isinstance(c.get("ema"), Mapping) and "params" in c["ema"]:
-        return dict(c["ema"]["params"])
+        return _strip_compile_wrappers(c["ema"]["params"])
     if "state_dict" in c:
-        return dict(c["state_dict"])
-    return dict(c)
+        return _strip_compile_wrappers(c["state_dict"])
+    return _strip_compile_wrappers(c)
 
 
 def load_checkpoint(model: SecondStageSampler, ckpt: _PathOrDict, first_stage_ckpt: Optional[_PathOrDict] = None,

@@ -39,7 +39,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, float* __rest
 // One warp per output column, 8 samples per block staged in shared memory.  pre/post: 0 = identity, 1 = SiLU.
 __global__ void __launch_bounds__(256)
 vec_linear_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ W, const float* __restrict__ bias,
-                  const float* __restrict__ add, float* __restrict__ out, int ldo, int B, int N, int K, int pre, int post) {
+                  const float* add, float* out, int ldo, int B, int N, int K, int pre, int post) {
   extern __shared__ float xs[];  // [8][K]
   const int b0 = blockIdx.y * 8;
   for (int i = threadIdx.x; i < 8 * K; i += 256) {
@@ -329,7 +329,7 @@ ksample_errors_kernel(const float* __restrict__ preds, const float* __restrict__
 // Heun; transport.py:266-299: last step) are all linear in (state, network output, noise) with time-only coefficients, which the
 // host evaluates in fp64 (lam_slide_b200/transport.py).  out may alias x.
 __global__ void __launch_bounds__(256)
-lincomb3_kernel(float4* __restrict__ out, const float4* __restrict__ x, const float4* __restrict__ m, const float4* __restrict__ w,
+lincomb3_kernel(float4* out, const float4* x, const float4* __restrict__ m, const float4* __restrict__ w,
                 float px, float pm, float pw, long long n4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;

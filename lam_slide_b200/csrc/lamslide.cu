@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -31,6 +33,8 @@ using namespace lam;
 // ================================================================================================ error handling
 static thread_local std::string g_err;
 static thread_local int64_t g_launches = 0;
+static thread_local std::unordered_map<std::string, int64_t> g_named_launches;  // lamslide_debug_kernel_count (tests)
+#define COUNT_KERNEL(name) (++g_named_launches[name])
 
 static int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -188,15 +192,31 @@ static bool env_flag(const char* name) {
   const char* v = getenv(name);
   return v && v[0] && v[0] != '0';
 }
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+// cudaFuncSetAttribute is per device: remember (device, kernel) pairs, not a process-wide flag — one process may hold handles on
+// several GPUs (include/lamslide.h: a handle belongs to the device that was current at *_create).
+static int ensure_dynamic_smem(const void* kernel, int bytes, bool carveout_max = false) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({dev, kernel})) return 0;
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (carveout_max) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  done.insert({dev, kernel});
+  return 0;
+}
+static int num_sms() {  // of the current device
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 // ================================================================================================ GEMM launch
@@ -211,11 +231,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int rows, i
   constexpr int STAGES = StagesFor<BN>::value;
   using SM = GemmSmem<BN, STAGES>;
   auto kern = gemm_tc_kernel<BN, STAGES, Epi>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    configured = true;
-  }
+  TRY(ensure_dynamic_smem((const void*)kern, SM::kTotal));
   dim3 grid(N / BN, cdiv(rows, kBlockM));
   kern<<<grid, kGemmThreads, SM::kTotal, st>>>(ta, tb, K / kBlockK, ep);
   LAUNCH_CHECK();
@@ -259,11 +275,7 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   cudaLaunchAttribute attr[1];
   if (use_pair) {
     auto kern = gemm_ws_kernel<BN, 2, Epi>;
-    static bool configured = false;
-    if (!configured) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-      configured = true;
-    }
+    TRY(ensure_dynamic_smem((const void*)kern, kSmemMax));
     static const int grid_cap = getenv("LAMSLIDE_WS_GRID") ? atoi(getenv("LAMSLIDE_WS_GRID")) : 1 << 30;  // profiling aid
     const int grid = std::min(std::min(num_sms(), grid_cap) / 2 * 2, cdiv(mblocks, 2) * 2);
     cfg.gridDim = dim3(grid);
@@ -273,11 +285,7 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, *tb_half, o0, o1, mblocks, N / BN, kblocks, stages, a_res, ep));
   } else {
     auto kern = gemm_ws_kernel<BN, 1, Epi>;
-    static bool configured = false;
-    if (!configured) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-      configured = true;
-    }
+    TRY(ensure_dynamic_smem((const void*)kern, kSmemMax));
     static const int grid_cap = getenv("LAMSLIDE_WS_GRID") ? atoi(getenv("LAMSLIDE_WS_GRID")) : 1 << 30;  // profiling aid
     cfg.gridDim = dim3(std::min(std::min(num_sms(), grid_cap), mblocks));
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, o0, o1, mblocks, N / BN, kblocks, stages, a_res, ep));
@@ -622,11 +630,7 @@ static int launch_fused_mlp(const CUtensorMap& tm_u, const CUtensorMap& tm_attn,
   if (const char* e = getenv("LAMSLIDE_FUSED_TRACE")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));  // device buffer, 3 x 4096 x 8 B
   if (const char* e = getenv("LAMSLIDE_FUSED_STAGES")) s1 = std::max(2, std::min(s1, atoi(e))), s2 = std::max(2, std::min(s2, atoi(e)));
   const FusedMlpSmem plan = fused_mlp_smem(p.H, p.M, s1, s2);
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    configured = true;
-  }
+  TRY(ensure_dynamic_smem((const void*)mlp_fused_kernel, 232448));
   const int mblocks = cdiv(rows, kBlockM);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -685,13 +689,9 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
     static const int poly = getenv("LAMSLIDE_ATTN_TC_POLY") ? atoi(getenv("LAMSLIDE_ATTN_TC_POLY")) : 0;
     void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int, int) =
         poly == 1 ? attn_tc_kernel<HD, 1> : poly == 2 ? attn_tc_kernel<HD, 2> : poly == 3 ? attn_tc_kernel<HD, 3> : attn_tc_kernel<HD, 0>;
-    static const void* configured = nullptr;
-    if (configured != (const void*)kern) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      configured = (const void*)kern;
-    }
+    TRY(ensure_dynamic_smem((const void*)kern, 232448, true));
     kern<<<(unsigned)(n_seq * heads), kAtcThreads, tc_smem, st>>>(qkv, out, H, ldo, sm, heads, tc_forced ? (mode >> 2) : 0);
+    COUNT_KERNEL("attn_tc");
   } else if ((sm.S > 32 && seq_ok && !force_flash) || mode == 2) {
     // share of the exponentials evaluated on the FMA pipe (poly_exp2) instead of MUFU (of 16 per thread and key block).
     // Measured on B200 (4AA temporal attention): 0 -> 677 us, 2 -> 706, 4 -> 742, 8 -> 820: the kernel is issue-bound, so the
@@ -706,12 +706,9 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
     void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int) =
         mt1 ? attn_seq_kernel<HD, 0x0000u, 1> : poly == 0 ? attn_seq_kernel<HD, 0x0000u> : poly == 2 ? attn_seq_kernel<HD, 0x0808u> : poly == 6 ? attn_seq_kernel<HD, 0xA8A8u>
         : poly == 8 ? attn_seq_kernel<HD, 0xAAAAu> : attn_seq_kernel<HD, 0x8888u>;
-    static const void* configured = nullptr;
-    if (configured != (const void*)kern) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-      configured = (const void*)kern;
-    }
+    TRY(ensure_dynamic_smem((const void*)kern, 232448 - 1024));
     kern<<<(unsigned)(n_seq * heads), mt1 ? 512 : 256, seq_smem, st>>>(qkv, out, H, ldo, sm, heads);
+    COUNT_KERNEL("attn_seq");
   } else if (sm.S <= 32 && !force_flash) {
     // contiguous sequences whose q|k|v rows fit 8 warps x 6 KB of shared memory: warp per sequence (attn_rows_kernel)
     static const bool legacy_small = env_flag("LAMSLIDE_LEGACY_SMALL_ATTN");
@@ -719,14 +716,17 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
     const size_t rows_smem = (size_t)8 * sm.S * 3 * H * 2;
     if (!legacy_small && contiguous && rows_smem <= 48 * 1024 && ldo % 8 == 0 && H % 8 == 0) {
       attn_rows_kernel<HD><<<(unsigned)cdiv((long long)n_seq, 8), 256, rows_smem, st>>>(qkv, out, H, ldo, heads, sm.S, n_seq);
+      COUNT_KERNEL("attn_rows");
     } else {
       long long items = (long long)n_seq * sm.S * heads;
       attn_small_kernel<HD><<<cdiv(items, 256), 256, 0, st>>>(qkv, out, H, ldo, heads, sm, items);
+      COUNT_KERNEL("attn_small");
     }
   } else {
     int nqt = cdiv(sm.S, 128);
     dim3 grid((unsigned)(n_seq * nqt), heads);
     attn_flash_kernel<HD><<<grid, 256, 0, st>>>(qkv, out, H, ldo, sm, nqt);
+    COUNT_KERNEL("attn_flash");
   }
   LAUNCH_CHECK();
   return 0;
@@ -1558,6 +1558,14 @@ extern "C" const char* lamslide_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t lamslide_launch_count(int32_t reset) {
   int64_t v = g_launches;
   if (reset) g_launches = 0;
+  return v;
+}
+
+extern "C" int64_t lamslide_debug_kernel_count(const char* name, int32_t reset) {
+  if (!name) return -1;
+  auto it = g_named_launches.find(name);
+  const int64_t v = it == g_named_launches.end() ? 0 : it->second;
+  if (reset) g_named_launches.clear();
   return v;
 }
 

@@ -51,19 +51,53 @@ def gather_samples(local: Tensor, global_batch: int, group=None) -> Tensor:
     return torch.cat([buf[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)])
 
 
-@torch.no_grad()
-def sample_sharded(model, batch: Dict[str, Tensor], seed: int = 0, gather: bool = True, group=None) -> Tensor:
-    """``model.sample`` on this rank's shard of a replicated host/device batch, then one all-gather of the main output."""
+def local_noise(model, batch: Dict[str, Tensor], seed: int = 0, group=None) -> Tensor:
+    """The initial noise of this rank's shard of ``batch``: rows ``shard_range(B, rank, world)`` of the global noise, whose row ``i``
+    depends on ``(seed, i)`` only."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B, T = batch["entities"].shape[:2]
     lo, hi = shard_range(B, rank, world)
-    local = shard_batch(batch, rank, world)
     cfg = model.cfg
     L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
-    noise = per_sample_noise(seed, lo, hi, (T, L, D), model.device)
-    out = model.sample(dict(local), noise=noise)[cfg["main_output"]]
+    return per_sample_noise(seed, lo, hi, (T, L, D), model.device)
+
+
+@torch.no_grad()
+def sample_sharded(model, batch: Dict[str, Tensor], seed: int = 0, gather: bool = True, group=None,
+                   noise: Optional[Tensor] = None) -> Tensor:
+    """``model.sample`` on this rank's shard of a replicated host/device batch, then one all-gather of the main output.
+    ``noise`` (optional): this rank's rows of the initial noise (``local_noise``), for callers that draw it once."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = batch["entities"].shape[0]
+    local = shard_batch(batch, rank, world)
+    if noise is None:
+        noise = local_noise(model, batch, seed, group)
+    out = model.sample(dict(local), noise=noise)[model.cfg["main_output"]]
     return gather_samples(out, B, group) if gather else out
+
+
+def sample_stream_sharded(model, host_batches, seed: int = 0, group=None, noise: Optional[Tensor] = None, keep: Optional[dict] = None):
+    """``SecondStageSampler.sample_stream`` over replicated HOST batches, sharded like ``sample_sharded``: every rank uploads only its
+    rows of each batch, samples them, all-gathers the decoded coordinates on the device (``keep["gathered"]`` holds the latest
+    ``[B, ...]`` device tensor when a dict is given) and yields its OWN rows as a pinned host tensor — one process per GPU, each
+    feeding its consumer, with the copies of neighbouring batches overlapped with compute."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    sizes = []
+
+    def shards():
+        for b in host_batches:
+            sizes.append(b["entities"].shape[0])
+            yield shard_batch(b, rank, world)
+
+    def on_device(out: Tensor) -> None:
+        g = gather_samples(out, sizes.pop(0), group)
+        if keep is not None:
+            keep["gathered"] = g
+
+    yield from model.sample_stream(shards(), noise=noise, on_device=on_device)
 
 
 @torch.no_grad()

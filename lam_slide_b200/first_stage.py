@@ -228,8 +228,7 @@ class FirstStage(nn.Module):
 
     def _workspace(self, frames: int, N: int, device: torch.device):
         need = _lib.load().lamslide_first_stage_workspace_bytes(self._handle, frames, N)
-        buf = self._ws.get(need, device)
-        return _DeviceWorkspace.aligned_ptr(buf, 256), need
+        return self._ws.get(need, device, 256)
 
     # -- BackboneBase.encode (lightning_base.py:37-40) ----------------------------------------------------------------------
     @torch.no_grad()

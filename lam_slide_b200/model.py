@@ -52,6 +52,10 @@ class SecondStageSampler(nn.Module):
         self.hparams = SimpleNamespace(cond_idx=list(cfg["cond_idx"]), mask_cond_mean=cfg["mask_cond_mean"],
                                        sampling_method=sampling_method, sampling_kwargs=dict(sampling_kwargs),
                                        n_timesteps=cfg["T"])
+        # CUDA graphs (opt-in, ``use_cuda_graphs``): one captured graph of the whole sample() per input signature; the small
+        # configurations (pedestrian: ~700 launches of a few microseconds each) are launch-bound without it
+        self.use_cuda_graphs = False
+        self.__dict__["_graphs"] = {}
 
     @classmethod
     def from_name(cls, name: str, **kw) -> "SecondStageSampler":
@@ -116,6 +120,66 @@ class SecondStageSampler(nn.Module):
     # lightning_base.py:217-238.  ``noise`` (optional) replaces torch.randn_like for reproducible parity tests.
     @torch.no_grad()
     def sample(self, batch: Dict[str, Tensor], noise: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        if self.use_cuda_graphs:
+            return self._sample_graphed(batch, noise)
+        return self._sample_eager(batch, noise)
+
+    def _graph_signature(self, batch: Dict[str, Tensor], noise: Optional[Tensor]):
+        sig = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in batch.items() if isinstance(v, torch.Tensor)))
+        hp = self.hparams
+        return (sig, None if noise is None else tuple(noise.shape), str(self.device), hp.sampling_method,
+                tuple(sorted((k, str(v)) for k, v in hp.sampling_kwargs.items())), tuple(hp.cond_idx), hp.mask_cond_mean)
+
+    def _param_versions(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    @torch.no_grad()
+    def _sample_graphed(self, batch: Dict[str, Tensor], noise: Optional[Tensor]) -> Dict[str, Tensor]:
+        """``sample()`` replayed from a CUDA graph: the first call with a new input signature (shapes, dtypes, sampler settings)
+        runs once eagerly (packs weights, sizes workspaces, sets kernel attributes), captures the whole call — encode, conditioning,
+        every network evaluation and Euler update, decode — on static input buffers, and later calls copy their inputs into those
+        buffers and replay.  The C ABI never allocates, synchronises or touches the default stream (include/lamslide.h), so the
+        capture holds exactly the kernels of the eager call; the results are bit-identical to it.  Graphs are dropped when a
+        parameter changes; the workspaces a graph was captured with are kept alive with it."""
+        dev = self.device
+        key = self._graph_signature(batch, noise)
+        graphs = self.__dict__["_graphs"]
+        versions = self._param_versions()
+        ent = graphs.get(key)
+        if ent is not None and ent["versions"] != versions:
+            graphs.clear()
+            ent = None
+        tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
+        if ent is None:
+            with torch.cuda.device(dev):
+                static_in = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in tensors.items()}
+                static_noise = None if noise is None else torch.empty(noise.shape, dtype=torch.float32, device=dev)
+                for k, v in tensors.items():
+                    static_in[k].copy_(v, non_blocking=True)
+                if noise is not None:
+                    static_noise.copy_(noise, non_blocking=True)
+                cur = torch.cuda.current_stream(dev)
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):  # warm-up outside the capture (torch's capture rules; also packs and sizes everything)
+                    self._sample_eager(dict(static_in), static_noise)
+                cur.wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self._sample_eager(dict(static_in), static_noise)
+                ent = {"graph": graph, "in": static_in, "noise": static_noise, "out": out, "versions": versions,
+                       "keep": [self.backbone._ws.buf, self.first_stage_model.backbone._ws.buf]}
+                graphs[key] = ent
+        with torch.cuda.device(dev):
+            for k, v in tensors.items():
+                ent["in"][k].copy_(v, non_blocking=True)
+            if noise is not None:
+                ent["noise"].copy_(noise, non_blocking=True)
+            ent["graph"].replay()
+            return {k: v.clone() for k, v in ent["out"].items()}
+
+    @torch.no_grad()
+    def _sample_eager(self, batch: Dict[str, Tensor], noise: Optional[Tensor] = None) -> Dict[str, Tensor]:
         sample_fn = Sampler(self.si).get_sample_fn(self.hparams.sampling_method, self.hparams.sampling_kwargs)
         B, T = batch["entities"].shape[:2]
         dev = self.device
@@ -144,12 +208,14 @@ class SecondStageSampler(nn.Module):
         out = sample_fn(x0, self.forward, **model_kwargs)[-1]
         return self.decode(out.flatten(0, 1), entities.flatten(0, 1), T=T)
 
-    def sample_stream(self, batches, noise: Optional[Tensor] = None):
+    def sample_stream(self, batches, noise: Optional[Tensor] = None, on_device=None):
         """``sample()`` over an iterable of HOST batches (pinned memory), yielding pinned host tensors of the main output.
         Same per-batch work as ``sample()`` (lightning_base.py:217-238), but the host->device copy of batch k + 1 and the
         device->host copy of result k - 1 run on a second CUDA stream while batch k is being computed, so at steady state the
-        PCIe transfers cost no device time.  Results come out in order; each yielded tensor is valid until two more have been
-        produced (two rotating pinned buffers)."""
+        PCIe transfers cost no device time.  Results come out in order.  Three pinned result buffers rotate: the copy of result
+        k + 1 is already in flight when result k is yielded, so a yielded tensor stays untouched until the consumer has asked for
+        two more results (``next()`` twice) — keep the previous result while working on the current one, clone anything kept longer.  ``on_device(out)`` (optional) runs on the
+        compute stream right after each ``sample()`` with the device result (e.g. the all-gather of ``dist.sample_stream_sharded``)."""
         dev = self.device
         main_key = self.cfg["main_output"]
         with torch.cuda.device(dev):
@@ -157,7 +223,7 @@ class SecondStageSampler(nn.Module):
             # copy stream, two rotating sets of device input buffers and pinned result buffers, kept on the module between calls:
             # no allocation at steady state (the caching allocator would otherwise cudaMalloc while blocks shared between the
             # two streams are still in flight, and a pinned allocation costs milliseconds)
-            pipe = self.__dict__.setdefault("_pipe", {"side": torch.cuda.Stream(dev), "in": [None, None], "host": [None, None]})
+            pipe = self.__dict__.setdefault("_pipe", {"side": torch.cuda.Stream(dev), "in": [None, None], "host": [None, None, None]})
             side, in_bufs, host_bufs = pipe["side"], pipe["in"], pipe["host"]
             in_free = [None, None]
             side.wait_stream(main)
@@ -193,18 +259,21 @@ class SecondStageSampler(nn.Module):
                     nxt = None
                 main.wait_event(ready)
                 out = self.sample(cur, noise=noise)[main_key]
+                if on_device is not None:
+                    on_device(out)
                 done = main.record_event()
                 in_free[k & 1] = done
-                if host_bufs[k & 1] is None or host_bufs[k & 1].shape != out.shape:
-                    host_bufs[k & 1] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                hb = k % 3
+                if host_bufs[hb] is None or host_bufs[hb].shape != out.shape or host_bufs[hb].dtype != out.dtype:
+                    host_bufs[hb] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
                 with torch.cuda.stream(side):
                     side.wait_event(done)
-                    host_bufs[k & 1].copy_(out, non_blocking=True)
+                    host_bufs[hb].copy_(out, non_blocking=True)
                     copied = side.record_event()
                 if pending is not None:
                     pending[1].synchronize()
                     yield pending[0]
-                pending = (host_bufs[k & 1], copied, out)  # `out` stays referenced until its copy has completed
+                pending = (host_bufs[hb], copied, out)  # `out` stays referenced until its copy has completed
                 k += 1
             pending[1].synchronize()
             yield pending[0]

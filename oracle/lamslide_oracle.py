@@ -83,16 +83,16 @@ def softmax_attention(q: Tensor, k: Tensor, v: Tensor, scale: float, key_mask: O
 def timestep_embedding(t: Tensor, dim: int = 256, max_period: float = 10000.0, time_factor: float = 1000.0) -> Tensor:
     """mmdit.py:93-113 — cat[cos, sin](1000·t·exp(−ln(1e4)·i/half)); frequencies built in fp32."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = (time_factor * t)[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1).to(t.dtype)
 
 
-def rope_tables(S: int, hd: int, theta: float) -> Tuple[Tensor, Tensor]:
+def rope_tables(S: int, hd: int, theta: float, device=None) -> Tuple[Tensor, Tensor]:
     """mmdit.py:75-82 — angle = p·theta^(−2i/hd) in fp64, cos/sin cast to fp32. Returns [S, hd/2] each."""
-    scale = torch.arange(0, hd, 2, dtype=torch.float64) / hd
+    scale = torch.arange(0, hd, 2, dtype=torch.float64, device=device) / hd
     omega = 1.0 / (float(theta) ** scale)
-    ang = torch.arange(S, dtype=torch.float64)[:, None] * omega[None]
+    ang = torch.arange(S, dtype=torch.float64, device=device)[:, None] * omega[None]
     return torch.cos(ang).float(), torch.sin(ang).float()
 
 
@@ -148,8 +148,8 @@ def backbone_forward(sd: SD, cfg: dict, x: Tensor, t: Tensor, x_cond: Tensor, x_
         h = layer_norm(h, 1e-5)  # F.layer_norm default eps (:174)
     vec = backbone_vec(sd, cfg, t, y)
     svec = silu(vec)
-    cs_s, sn_s = rope_tables(L, hd, cfg.get("theta", 10_000))
-    cs_t, sn_t = rope_tables(T, hd, cfg.get("theta", 10_000))
+    cs_s, sn_s = rope_tables(L, hd, cfg.get("theta", 10_000), x.device)
+    cs_t, sn_t = rope_tables(T, hd, cfg.get("theta", 10_000), x.device)
     cs_s, sn_s, cs_t, sn_t = (a.to(x.dtype) for a in (cs_s, sn_s, cs_t, sn_t))
     if trace is not None:
         trace["h0"] = h.clone()
@@ -226,7 +226,7 @@ def ode_sample(model_fn, x0: Tensor, *, path_type: str = "GVP", prediction: str 
     states = [x0]
     x = x0
     for i in range(num_steps - 1):
-        t = torch.ones(x.shape[0]) * grid[i]
+        t = torch.ones(x.shape[0], device=x.device) * grid[i]
         v = drift(path_type, prediction, x, t.to(x.dtype), model_fn(x, t.to(x.dtype)))
         if record_velocity is not None:
             record_velocity.append(v)
@@ -346,7 +346,7 @@ def sde_sample(model_fn, x0: Tensor, noises: Sequence[Tensor], *, path_type: str
 def setup_conditioning(latents: Tensor, cond_idx: Sequence[int], mask_cond_mean: bool = True) -> Tuple[Tensor, Tensor]:
     """SecondStageCondLightningBase.setup_conditioning — lightning_base.py:240-263."""
     B, T, L, _ = latents.shape
-    mask = torch.zeros(B, T, L, dtype=torch.int64)
+    mask = torch.zeros(B, T, L, dtype=torch.int64, device=latents.device)
     mask[:, cond_idx[0]: cond_idx[1]] = 1
     if mask_cond_mean:
         fill = latents[:, cond_idx[0]: cond_idx[1]].mean(dim=1, keepdim=True).expand_as(latents)

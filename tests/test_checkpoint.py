@@ -69,3 +69,39 @@ def test_load_checkpoint_is_strict():
         P.load_checkpoint(m, no_vec)
     with pytest.raises(KeyError):
         P.load_checkpoint(m, {"state_dict": {"loss.weight": torch.ones(1)}})
+
+
+def test_load_checkpoint_of_compiled_modules():
+    """``compile: true`` runs (second_stage/peptide.py:58-60: ``torch.compile`` around the backbone and the first-stage model) store
+    their parameters under ``backbone._orig_mod.*`` / ``first_stage_model._orig_mod.backbone.*`` — in ``state_dict`` and in the EMA copy."""
+    cfg = P.get_config("nba", depth=1)
+    ckpt = _lightning_ckpt(cfg, 41, with_ema=True, conditional=True)
+
+    def compiled(k):
+        if k.startswith("backbone."):
+            return "backbone._orig_mod." + k[len("backbone."):]
+        if k.startswith("first_stage_model."):
+            return "first_stage_model._orig_mod." + k[len("first_stage_model."):]
+        return k
+
+    cc = {"state_dict": {compiled(k): v for k, v in ckpt["state_dict"].items()},
+          "ema": {"params": {compiled(k): v for k, v in ckpt["ema"]["params"].items()}, "decay": 0.999}}
+    assert "backbone._orig_mod.x_in.weight" in cc["state_dict"]
+    m = P.SecondStageSampler(cfg)
+    n = P.load_checkpoint(m, cc)
+    assert n["backbone"] == len(m.backbone.state_dict()) and n["first_stage"] == len(m.first_stage_model.backbone.state_dict())
+    for k, v in m.backbone.state_dict().items():
+        assert torch.equal(v, ckpt["ema"]["params"][f"backbone.{k}"]), k
+    for k, v in m.first_stage_model.backbone.state_dict().items():
+        assert torch.equal(v, ckpt["ema"]["params"][f"first_stage_model.backbone.{k}"]), k
+    # a compiled first-stage-only checkpoint (FirstStageLightningBase with a compiled backbone: ``backbone._orig_mod.*``)
+    fs_only = {"state_dict": {"backbone._orig_mod." + k[len("first_stage_model.backbone."):]: v + 2.0
+                              for k, v in ckpt["state_dict"].items() if k.startswith("first_stage_model.backbone.")}}
+    P.load_checkpoint(m, cc, first_stage_ckpt=fs_only, use_ema=False)
+    k0 = next(iter(m.first_stage_model.backbone.state_dict()))
+    assert torch.equal(m.first_stage_model.backbone.state_dict()[k0], ckpt["state_dict"][f"first_stage_model.backbone.{k0}"] + 2.0)
+    # an eager and a compiled alias of the same tensor in one dict is a malformed checkpoint
+    both = dict(cc["state_dict"])
+    both["backbone.x_in.weight"] = both["backbone._orig_mod.x_in.weight"]
+    with pytest.raises(KeyError):
+        P.load_checkpoint(m, {"state_dict": both}, use_ema=False)

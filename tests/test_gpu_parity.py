@@ -88,7 +88,7 @@ def test_backbone_forward_vs_oracle(name, depth, B, T):
 
 
 @pytest.mark.parametrize("name", ["peptide_small", "md17_small", "nba_full", "pedestrian_full", "peptide_linear_velocity",
-                                  "md17_full", "peptide_full"])
+                                  "md17_full", "peptide_full", "peptide_steps20", "peptide_steps50"])
 def test_sample_vs_reference_golden(name):
     """Full sample(): encode -> conditioning -> Euler ODE -> decode vs the golden vectors of the REAL reference."""
     fx = load_golden(name)
@@ -156,6 +156,16 @@ def test_sample_stream_matches_sample():
     for g_, w_ in zip(got, want):
         assert torch.equal(g_, w_)
     assert not torch.equal(want[0], want[1])
+    # a yielded (pinned) result stays valid while the consumer works on the next one: keep the previous result WITHOUT cloning
+    prev, n = None, 0
+    for k, o in enumerate(m.sample_stream(({kk: v for kk, v in b.items()} for b in batches), noise=noise)):
+        assert o.is_pinned()
+        if prev is not None:
+            torch.cuda.synchronize()  # whatever copies are in flight have landed: prev must still hold result k - 1
+            assert torch.equal(prev, want[k - 1]), k
+        assert torch.equal(o, want[k])
+        prev, n = o, n + 1
+    assert n == len(want)
 
 
 def test_rollout_vs_reference_golden():
@@ -330,6 +340,184 @@ def test_full_size_batch_properties():
     assert torch.equal(run(perm), full[perm.cuda()])             # (2)
     sub = torch.tensor([3, 17, 18, 40, 63])
     assert torch.equal(run(sub), full[sub.cuda()])               # (3)
+
+
+def test_full_batch_sample0_equals_golden_run():
+    """The headline batch (B = 64 4AA trajectories, T = 1000, full depth) chained to the reference DIRECTLY: sample 0 of the batch is
+    the `peptide_full` golden case (same weights, frames and noise), the other 63 are unrelated synthetic trajectories.  Sample 0 of
+    the B = 64 run must equal the B = 1 run bit for bit, and both must match what the real reference produced."""
+    from lam_slide_b200.synthetic import synthetic_batch
+    c = CASE_BY_NAME["peptide_full"]
+    fx = load_golden("peptide_full")
+    cfg, fs_sd, bb_sd, batch1, noise1, _ = case_inputs(c)
+    check_inputs_match_fixture(fx, fs_sd, bb_sd, batch1, noise1)
+    m = _build(cfg, fs_sd, bb_sd)
+    B, T = 64, c["T"]
+    L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+    rest = synthetic_batch(cfg, B - 1, seed=77)
+    batch = {k: torch.cat([batch1[k], rest[k].to(batch1[k].dtype)]) for k in batch1}
+    noise = torch.cat([noise1, torch.randn(B - 1, T, L, D, generator=torch.Generator().manual_seed(78))])
+    one = m.sample({k: v.clone() for k, v in batch1.items()}, noise=noise1.clone())["atom14_pos"]
+    full = m.sample({k: v.clone() for k, v in batch.items()}, noise=noise.clone())["atom14_pos"]
+    assert torch.isfinite(full).all()
+    assert torch.equal(full[:1], one)
+    sl = frame_slice(fx)
+    got = full[:1].cpu()[:, sl]
+    assert rmsd(got[:, -1], fx["outputs"]["atom14_pos"][:, -1]) < RMSD_TOL
+    assert rmsd(got, fx["outputs"]["atom14_pos"]) < RMSD_TOL
+
+
+@pytest.mark.parametrize("name", ["nba", "pedestrian"])
+def test_large_batch_properties_and_golden_slice(name):
+    """BASELINE.json configs[1] / [2] at their real batch size (B = 1024: second-stage.sh:12, configs/data/pedestrian.yaml:15; ragged
+    agent counts for pedestrians).  The first samples of the batch are the golden case of the REAL reference; trajectories are
+    independent, so (1) their slice of the B = 1024 run equals the small run bit for bit and matches the golden outputs, (2) the
+    run is deterministic, (3) an arbitrary sub-batch sampled alone equals its slice."""
+    from lam_slide_b200.synthetic import synthetic_batch
+    c = CASE_BY_NAME[name + "_full"]
+    fx = load_golden(name + "_full")
+    cfg, fs_sd, bb_sd, batch_g, noise_g, _ = case_inputs(c)
+    m = _build(cfg, fs_sd, bb_sd)
+    g = torch.Generator().manual_seed(c["seeds"][3])
+    L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
+    _ = torch.randn(c["B"], c["T"], L, D, generator=g)
+    m.vec_in_embedding.weight.data.copy_(torch.randn(cfg["n_classes"], 256, generator=g))  # the table the golden case drew y from
+    B, T, Bg = 1024, c["T"], c["B"]
+    rest = synthetic_batch(cfg, B - Bg, seed=91)
+    batch = {}
+    for k in batch_g:
+        a, b = batch_g[k], rest[k].to(batch_g[k].dtype)
+        if a.dim() >= 3 and a.shape[2] != b.shape[2]:  # ragged pedestrians: pad the entity axis to the larger N_max
+            n = max(a.shape[2], b.shape[2])
+            pad = lambda t: torch.cat([t, t.new_zeros(t.shape[:2] + (n - t.shape[2],) + t.shape[3:])], 2) if t.shape[2] < n else t
+            a, b = pad(a), pad(b)
+        batch[k] = torch.cat([a, b])
+    noise = torch.cat([noise_g, torch.randn(B - Bg, T, L, D, generator=torch.Generator().manual_seed(92))])
+    key = cfg["main_output"]
+
+    def run(idx):
+        return m.sample({k: v[idx].clone() for k, v in batch.items()}, noise=noise[idx].clone())[key]
+
+    full = run(torch.arange(B))
+    assert torch.isfinite(full).all()
+    small = run(torch.arange(Bg))
+    assert torch.equal(full[:Bg], small)                                             # (1)
+    n_g = fx["outputs"][key].shape[2]
+    assert rmsd(small.cpu()[:, :, :n_g], fx["outputs"][key]) < RMSD_TOL
+    assert torch.equal(run(torch.arange(B)), full)                                   # (2)
+    sub = torch.tensor([1, 100, 511, 512, 777, 1023])
+    assert torch.equal(run(sub), full[sub.cuda()])                                   # (3)
+
+
+def test_unbounded_logits_take_the_streaming_softmax_path():
+    """The default temporal-attention kernels evaluate softmax WITHOUT a running maximum, which is only valid while the logits are
+    bounded: |q.k| hd^-0.5 log2(e) <= sqrt(hd) log2(e) max|gamma_q| max|gamma_k| <= 64 (checked per block at pack time from the
+    QK-RMSNorm scales, mmdit.py:132-148).  Trained checkpoints can exceed it: with one large scale entry the bound is ~68, the
+    dispatcher must fall back to the streaming (online-max) kernel for those blocks, and the result must still match the oracle."""
+    import lam_slide_b200 as P
+    from lam_slide_b200 import _lib
+    from lam_slide_b200.configs import get_config
+    cfg = get_config("peptide", depth=2)
+    bb = cfg["backbone"]
+    bb_sd = O.init_backbone_params(bb, 41)
+    big = "blocks.1.temporal_block.norm.query_norm.scale"
+    bb_sd[big] = bb_sd[big].clone()
+    bb_sd[big][0] = 9.5  # bound = sqrt(24) * 1.4427 * 9.5 * 1.02 = 68.5 > 64 for this block only
+    net = P.LatentSIV3(depth=2, in_dim=bb["in_dim"], hidden_size=bb["hidden_size"], num_heads=bb["num_heads"],
+                       vec_in_dim=bb["vec_in_dim"], mlp_ratio=bb["mlp_ratio"], normalize=bb["normalize"]).cuda()
+    net.load_state_dict(bb_sd, strict=True)
+    B, T, L = 2, 512, 2
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(B, T, L, bb["in_dim"], generator=g)
+    xc = torch.randn(B, T, L, bb["in_dim"], generator=g)
+    mk = (torch.rand(B, T, L, generator=g) < 0.3).long()
+    t = torch.rand(B, generator=g)
+    with torch.no_grad():
+        ref = O.backbone_forward(bb_sd, bb, x, t, xc, mk, None)
+    net(x.cuda(), t.cuda(), xc.cuda(), mk.cuda())  # packs the weights
+    _lib.kernel_count("attn_flash", reset=True)
+    out = net(x.cuda(), t.cuda(), xc.cuda(), mk.cuda())
+    assert _lib.kernel_count("attn_flash") == 1  # exactly the one block whose bound exceeds the limit
+    assert torch.isfinite(out).all()
+    assert max_rel(out.cpu(), ref) < VEL_TOL
+
+
+@pytest.mark.parametrize("name", ["nba_full", "pedestrian_full", "peptide_small"])
+def test_cuda_graph_replay_equals_eager(name):
+    """include/lamslide.h: "no allocation, no host sync and no default-stream work happens inside forward / sample / encode / decode,
+    so calls can be captured in a CUDA graph".  SecondStageSampler.use_cuda_graphs captures the whole sample() (encode ->
+    conditioning -> every network evaluation + Euler update -> decode) once per input signature and replays it: the replayed
+    results must equal the eager ones bit for bit, for new inputs of the same shape too, and survive a weight update."""
+    c = CASE_BY_NAME[name]
+    cfg, fs_sd, bb_sd, batch, noise, y = case_inputs(c)
+    m = _build(cfg, fs_sd, bb_sd)
+    m.hparams.sampling_kwargs["num_steps"] = c["num_steps"]
+    key = cfg["main_output"]
+    batches = []
+    for i in range(3):
+        b = {k: v.clone() for k, v in batch.items()}
+        b[_pos_key(cfg)] = b[_pos_key(cfg)] * (1.0 + 0.05 * i)
+        batches.append(b)
+    noises = [noise, noise.flip(0).contiguous(), noise * 0.9]
+    want = [m.sample({k: v.clone() for k, v in b.items()}, noise=n)[key].clone() for b, n in zip(batches, noises)]
+    m.use_cuda_graphs = True
+    got = [m.sample({k: v.clone() for k, v in b.items()}, noise=n)[key].clone() for b, n in zip(batches, noises)]
+    assert len(m.__dict__["_graphs"]) == 1
+    for g_, w_ in zip(got, want):
+        assert torch.equal(g_, w_)
+    assert not torch.equal(want[0], want[1])
+    # a parameter update invalidates the captured graph (the packed weights it points to are replaced)
+    with torch.no_grad():
+        m.backbone.linear.bias.add_(0.01)
+    g2 = m.sample({k: v.clone() for k, v in batches[0].items()}, noise=noises[0])[key]
+    m.use_cuda_graphs = False
+    w2 = m.sample({k: v.clone() for k, v in batches[0].items()}, noise=noises[0])[key]
+    assert torch.equal(g2, w2) and not torch.equal(g2, want[0])
+    # without given noise the replay draws fresh noise every time (graph-safe philox offsets), like torch.randn_like in the reference
+    m.use_cuda_graphs = True
+    a = m.sample({k: v.clone() for k, v in batches[0].items()})[key].clone()
+    b2 = m.sample({k: v.clone() for k, v in batches[0].items()})[key].clone()
+    assert torch.isfinite(a).all() and not torch.equal(a, b2)
+
+
+def _pos_key(cfg):
+    return "atom14_pos" if cfg["main_output"] == "atom14_pos" else "pos"
+
+
+def test_ode_sample_capturable_through_the_c_abi():
+    """lamslide_ode_sample itself under stream capture (the raw C-ABI call, not the Python wrapper's graph cache)."""
+    import lam_slide_b200 as P
+    from lam_slide_b200.configs import get_config
+    cfg = get_config("pedestrian", depth=2)
+    bb = cfg["backbone"]
+    bb_sd = O.init_backbone_params(bb, 51)
+    net = P.LatentSIV3(depth=2, in_dim=bb["in_dim"], hidden_size=bb["hidden_size"], num_heads=bb["num_heads"],
+                       vec_in_dim=bb["vec_in_dim"], mlp_ratio=bb["mlp_ratio"], normalize=bb["normalize"]).cuda()
+    net.load_state_dict(bb_sd, strict=True)
+    g = torch.Generator().manual_seed(52)
+    B, T, L, D = 7, 20, 2, bb["in_dim"]
+    x0 = torch.randn(B, T, L, D, generator=g).cuda()
+    xc = torch.randn(B, T, L, D, generator=g).cuda()
+    mk = (torch.rand(B, T, L, generator=g) < 0.4).long().cuda()
+    y = torch.randn(B, bb["vec_in_dim"], generator=g).cuda()
+    want = net.ode_sample(x0, xc, mk, y, num_steps=10, return_states=False).clone()
+    static_x = x0.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        net.ode_sample(static_x, xc, mk, y, num_steps=10, return_states=False)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = net.ode_sample(static_x, xc, mk, y, num_steps=10, return_states=False)
+    for scale in (1.0, 0.5):
+        static_x.copy_(x0 * scale)
+        graph.replay()
+        ref = net.ode_sample(x0 * scale, xc, mk, y, num_steps=10, return_states=False)
+        assert torch.equal(out, ref)
+    static_x.copy_(x0)
+    graph.replay()
+    assert torch.equal(out, want)
 
 
 def test_errors_are_loud():

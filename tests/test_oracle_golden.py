@@ -6,7 +6,8 @@ import torch
 from oracle import lamslide_oracle as O
 from tests.helpers import CASE_BY_NAME, case_inputs, check_inputs_match_fixture, frame_slice, load_golden, max_rel
 
-FAST = ["peptide_small", "md17_small", "nba_full", "pedestrian_full", "peptide_linear_velocity", "md17_full", "peptide_full"]
+FAST = ["peptide_small", "md17_small", "nba_full", "pedestrian_full", "peptide_linear_velocity", "md17_full", "peptide_full", "peptide_steps20",
+        "peptide_steps50"]
 
 
 @pytest.mark.parametrize("name", FAST)

@@ -309,6 +309,27 @@ def main():
         for host_out in D_.sample_stream_sharded(model, (host_batch for _ in range(steps)), keep=keep):  # noise drawn on device like the reference
             pass
 
+    def timed(fn, steps, whole=False):
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if whole:
+            fn(steps)  # returns after the last result has reached the host (sample_stream synchronises on its copy)
+        else:
+            for _ in range(steps):
+                fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist_on:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms
+
     for _ in range(max(args.warmup, 3)):
         step_device()
     clocks = ClockSampler(local_rank)

@@ -95,6 +95,17 @@ int lamslide_setup_conditioning(const float* latents, float* x_cond, int64_t* x_
 int lamslide_lincomb3(float* out, const float* x, const float* m, const float* w, float px, float pm, float pw, int64_t numel,
                       void* stream);
 
+/* Building blocks of the ODE integrators other than fixed-grid Euler — Sampler.sample_ode hands its drift to torchdiffeq.odeint with
+ * sampling_method "dopri5" by default (transport.py:365-411, integrators.py:103-120, configs/eval_peptide.yaml:21-23); the host
+ * side (lam_slide_b200/odeint.py) restates torchdiffeq's adaptive Runge-Kutta controller around these:
+ *   lincomb_n:       out = sum_j coefs[j] * srcs[j]  (1 <= n <= 8; srcs: HOST array of device pointers, coefs: HOST array; out may be
+ *                    one of the sources) — stage combinations y0 + sum_j (dt beta_ij) k_j, solution, mid-point, interpolant;
+ *   rk_error_sumsq:  *acc (device double, caller zeroes it) += sum_i ((sum_j coefs[j] srcs[j][i]) / (atol + rtol max(|a_i|, |b_i|)))^2
+ *                    — the squared RMS error norm of an embedded step (torchdiffeq rk_common.py: _compute_error_ratio), fused. */
+int lamslide_lincomb_n(float* out, const float* const* srcs, const float* coefs, int32_t n, int64_t numel, void* stream);
+int lamslide_rk_error_sumsq(const float* const* srcs, const float* coefs, int32_t n, const float* a, const float* b, double rtol,
+                            double atol, int64_t numel, double* acc, void* stream);
+
 /* K-sample evaluation metrics on the device.  preds [K, B, T, A, D] = K batched sample() results restricted
  * to the frames after the conditioning window, target [B, T, A, D]; err = L2 norm over D.
  *   mode 0 - Wrapper.test_step / _compute_errors of second_stage/nba.py:161-238 and pedestrian.py:149-226 (unclustered metric):
@@ -166,6 +177,10 @@ int64_t lamslide_launch_count(int32_t reset);
 /* test hook: launches of one named kernel family on the calling thread since the last reset ("attn_tc", "attn_seq", "attn_flash",
  * "attn_rows", "attn_small", ...); reset != 0 clears ALL named counters after reading. */
 int64_t lamslide_debug_kernel_count(const char* name, int32_t reset);
+
+/* profiling aid: device buffer (148 x 32 x 8 bytes) that the tcgen05 attention kernel's trace variants (lamslide_debug_attention mode
+ * 3 + 4 * 5 / 3 + 4 * 6) fill with the cycles its MMA warp and one softmax warp spend per kind of wait / work.  NULL turns it off. */
+void lamslide_debug_attention_trace(void* device_buffer);
 
 /* Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline and time shares).
  * begin() arms it for the calling thread; end() synchronises the device and writes a JSON object

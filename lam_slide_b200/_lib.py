@@ -19,10 +19,11 @@ SYMBOLS = [
     "lamslide_abi_version", "lamslide_last_error", "lamslide_launch_count",
     "lamslide_backbone_create", "lamslide_backbone_destroy", "lamslide_backbone_workspace_bytes",
     "lamslide_backbone_forward", "lamslide_ode_sample", "lamslide_euler_step", "lamslide_setup_conditioning", "lamslide_ksample_errors", "lamslide_lincomb3",
+    "lamslide_lincomb_n", "lamslide_rk_error_sumsq",
     "lamslide_first_stage_create", "lamslide_first_stage_destroy", "lamslide_first_stage_workspace_bytes",
     "lamslide_encode", "lamslide_decode", "lamslide_debug_gemm", "lamslide_debug_attention",
     "lamslide_debug_linear1", "lamslide_debug_linear2", "lamslide_debug_gemm_mainloop", "lamslide_debug_fused_mlp",
-    "lamslide_profile_begin", "lamslide_profile_end", "lamslide_debug_kernel_count",
+    "lamslide_profile_begin", "lamslide_profile_end", "lamslide_debug_kernel_count", "lamslide_debug_attention_trace",
 ]
 
 
@@ -91,6 +92,8 @@ def load() -> C.CDLL:
     lib.lamslide_setup_conditioning.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.lamslide_ksample_errors.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.lamslide_lincomb3.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, i64, vp]
+    lib.lamslide_lincomb_n.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_float), i32, i64, vp]
+    lib.lamslide_rk_error_sumsq.argtypes = [C.POINTER(vp), C.POINTER(C.c_float), i32, vp, vp, C.c_double, C.c_double, i64, vp, vp]
     lib.lamslide_first_stage_create.argtypes = [C.POINTER(FirstStageConfig), C.POINTER(TensorDesc), i32, C.POINTER(vp)]
     lib.lamslide_first_stage_destroy.argtypes = [vp]
     lib.lamslide_first_stage_destroy.restype = None
@@ -105,6 +108,8 @@ def load() -> C.CDLL:
     lib.lamslide_debug_gemm_mainloop.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.lamslide_debug_fused_mlp.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.lamslide_profile_end.argtypes = [C.c_char_p, sz]
+    lib.lamslide_debug_attention_trace.argtypes = [vp]
+    lib.lamslide_debug_attention_trace.restype = None
     lib.lamslide_debug_kernel_count.argtypes = [C.c_char_p, i32]
     lib.lamslide_debug_kernel_count.restype = i64
     if lib.lamslide_abi_version() != 1:

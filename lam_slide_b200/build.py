@@ -25,6 +25,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC]
+    if os.environ.get("LAMSLIDE_DEBUG_KNOBS"):  # A/B switches and profiling aids read from the environment (lamslide.cu: env_flag)
+        cmd.insert(1, "-DLAMSLIDE_DEBUG_KNOBS")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -343,4 +343,63 @@ lincomb3_kernel(float4* out, const float4* x, const float4* __restrict__ m, cons
   out[i] = o;
 }
 
+// ---- out = sum_j coef[j] * src[j], j < n <= 8 (out may be one of the sources): stage combinations y0 + sum_j (dt beta_ij) k_j, the
+// solution / mid-point combinations and the interpolant of the Runge-Kutta integrators (lam_slide_b200/odeint.py; torchdiffeq
+// rk_common.py: _runge_kutta_step, interp.py).  Pointers and coefficients travel by value.
+struct LincombN {
+  const float4* src[8];
+  float coef[8];
+  int n;
+};
+__global__ void __launch_bounds__(256) lincomb_n_kernel(float4* out, LincombN a, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < a.n) {
+      const float4 v = a.src[j][i];
+      const float c = a.coef[j];
+      o.x = fmaf(c, v.x, o.x), o.y = fmaf(c, v.y, o.y), o.z = fmaf(c, v.z, o.z), o.w = fmaf(c, v.w, o.w);
+    }
+  }
+  out[i] = o;
+}
+
+// ---- *acc += sum_i ( (sum_j coef[j] src[j][i]) / (atol + rtol * max(|a[i]|, |b[i]|)) )^2 in fp64: the squared RMS error norm of an
+// embedded Runge-Kutta step (rk_common.py: _compute_error_ratio) and the norms of the initial step selection (misc.py:
+// _select_initial_step, with a = b = y0), fused so that the error vector is never written.  One fp64 atomic per block.
+__global__ void __launch_bounds__(256)
+rk_error_sumsq_kernel(LincombN e, const float4* __restrict__ a, const float4* __restrict__ b, double rtol, double atol, long long n4,
+                      double* __restrict__ acc) {
+  double local = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < e.n) {
+        const float4 v = e.src[j][i];
+        const float c = e.coef[j];
+        o.x = fmaf(c, v.x, o.x), o.y = fmaf(c, v.y, o.y), o.z = fmaf(c, v.z, o.z), o.w = fmaf(c, v.w, o.w);
+      }
+    }
+    const float4 av = a[i], bv = b[i];
+    const double r0 = (double)o.x / (atol + rtol * (double)fmaxf(fabsf(av.x), fabsf(bv.x)));
+    const double r1 = (double)o.y / (atol + rtol * (double)fmaxf(fabsf(av.y), fabsf(bv.y)));
+    const double r2 = (double)o.z / (atol + rtol * (double)fmaxf(fabsf(av.z), fabsf(bv.z)));
+    const double r3 = (double)o.w / (atol + rtol * (double)fmaxf(fabsf(av.w), fabsf(bv.w)));
+    local += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  __shared__ double warp_sum[8];
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += warp_sum[w];
+    atomicAdd(acc, t);
+  }
+}
+
 }  // namespace lam

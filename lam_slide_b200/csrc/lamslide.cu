@@ -188,10 +188,21 @@ static int make_tmap_ex(CUtensorMap* map, const void* ptr, CUtensorMapDataType d
   if (r != CUDA_SUCCESS) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)r);
   return 0;
 }
+// A/B switches and profiling aids read from the environment exist only in debug builds (-DLAMSLIDE_DEBUG_KNOBS, see
+// lam_slide_b200/build.py); the shipped library takes no behaviour from the environment.
+#ifdef LAMSLIDE_DEBUG_KNOBS
 static bool env_flag(const char* name) {
   const char* v = getenv(name);
   return v && v[0] && v[0] != '0';
 }
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && v[0] ? atoi(v) : dflt;
+}
+#else
+static constexpr bool env_flag(const char*) { return false; }
+static constexpr int env_int(const char*, int dflt) { return dflt; }
+#endif
 // cudaFuncSetAttribute is per device: remember (device, kernel) pairs, not a process-wide flag — one process may hold handles on
 // several GPUs (include/lamslide.h: a handle belongs to the device that was current at *_create).
 static int ensure_dynamic_smem(const void* kernel, int bytes, bool carveout_max = false) {
@@ -252,7 +263,7 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   const bool use_pair = tb_half && !no_cluster && mblocks >= 2 && num_sms() >= 2 && BN % 16 == 0;
   const int cl = use_pair ? 2 : 1;
   int a_res = kblocks <= kWsMaxKBlocksResident ? 1 : 0, stages = 0;
-  static const int max_stages = getenv("LAMSLIDE_WS_STAGES") ? atoi(getenv("LAMSLIDE_WS_STAGES")) : 8;  // profiling aid
+  static const int max_stages = env_int("LAMSLIDE_WS_STAGES", 8);  // profiling aid
   static const bool no_resident = env_flag("LAMSLIDE_WS_NO_RESIDENT");
   if (no_resident) a_res = 0;
   for (int pass = 0; pass < 2 && !stages; ++pass) {
@@ -276,7 +287,7 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   if (use_pair) {
     auto kern = gemm_ws_kernel<BN, 2, Epi>;
     TRY(ensure_dynamic_smem((const void*)kern, kSmemMax));
-    static const int grid_cap = getenv("LAMSLIDE_WS_GRID") ? atoi(getenv("LAMSLIDE_WS_GRID")) : 1 << 30;  // profiling aid
+    static const int grid_cap = env_int("LAMSLIDE_WS_GRID", 1 << 30);  // profiling aid
     const int grid = std::min(std::min(num_sms(), grid_cap) / 2 * 2, cdiv(mblocks, 2) * 2);
     cfg.gridDim = dim3(grid);
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -286,7 +297,7 @@ static int launch_gemm_ws(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   } else {
     auto kern = gemm_ws_kernel<BN, 1, Epi>;
     TRY(ensure_dynamic_smem((const void*)kern, kSmemMax));
-    static const int grid_cap = getenv("LAMSLIDE_WS_GRID") ? atoi(getenv("LAMSLIDE_WS_GRID")) : 1 << 30;  // profiling aid
+    static const int grid_cap = env_int("LAMSLIDE_WS_GRID", 1 << 30);  // profiling aid
     cfg.gridDim = dim3(std::min(std::min(num_sms(), grid_cap), mblocks));
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, o0, o1, mblocks, N / BN, kblocks, stages, a_res, ep));
   }
@@ -626,16 +637,18 @@ static int launch_fused_mlp(const CUtensorMap& tm_u, const CUtensorMap& tm_attn,
   int s1 = 0, s2 = 0;
   if (!fused_mlp_stages(p_in.H, p_in.M, &s1, &s2)) return 1;
   FusedMlpParams p = p_in;
+#ifdef LAMSLIDE_DEBUG_KNOBS
   if (const char* e = getenv("LAMSLIDE_FUSED_DEBUG")) p.debug = atoi(e);  // profiling aids (mlp_fused.cuh)
   if (const char* e = getenv("LAMSLIDE_FUSED_TRACE")) p.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));  // device buffer, 3 x 4096 x 8 B
   if (const char* e = getenv("LAMSLIDE_FUSED_STAGES")) s1 = std::max(2, std::min(s1, atoi(e))), s2 = std::max(2, std::min(s2, atoi(e)));
+#endif
   const FusedMlpSmem plan = fused_mlp_smem(p.H, p.M, s1, s2);
   TRY(ensure_dynamic_smem((const void*)mlp_fused_kernel, 232448));
   const int mblocks = cdiv(rows, kBlockM);
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   int grid_cap = num_sms();
-  if (const char* e = getenv("LAMSLIDE_FUSED_GRID")) grid_cap = std::max(2, std::min(grid_cap, atoi(e)));  // profiling aid
+  grid_cap = std::max(2, std::min(grid_cap, env_int("LAMSLIDE_FUSED_GRID", grid_cap)));  // profiling aid
   cfg.gridDim = dim3(std::min(grid_cap / 2 * 2, cdiv(mblocks, 2) * 2));
   cfg.blockDim = dim3(kFusedThreads);
   cfg.dynamicSmemBytes = plan.total;
@@ -663,51 +676,45 @@ static int launch_plain(int bn, const CUtensorMap& ta, const CUtensorMap& tb, in
   }
 }
 
-// mode: 0 = auto, 1 = force the streaming (online-max) flash kernel, 2 = force the whole-sequence kernel.
-// logit_bound: upper bound of |q.k| in the exp2 domain (<= 0: unknown) — the whole-sequence kernel skips the running maximum.
+// mode: 0 = auto, 1 = force the streaming (online-max) flash kernel, 2 = force the mma.sync whole-sequence kernel, 3 + 4 v = force the
+// tcgen05 kernel (v = 0: shipped exponential mix; v = 1, 2, 3: 0, 2 or 4 of every 8 exponential pairs on the FMA-pipe polynomial; v = 4: profiling
+// aid, no exponentials — wrong results; v = 5 / 6: v = 0 / 4 with the cycle trace of lamslide_debug_attention_trace).
+// logit_bound: upper bound of |q.k| in the exp2 domain (<= 0: unknown) — the tcgen05 and whole-sequence kernels skip the running maximum.
 constexpr float kSeqKernelMaxLogit = 64.f;
+static long long* g_atc_trace = nullptr;  // profiling aid (lamslide_debug_attention_trace): device buffer of 32 x 8 bytes per CTA
+constexpr int kAtcPolyDefault = 3;  // measured (scripts/attn_ubench.cu): 3 of 8 pairs on the polynomial keeps MUFU and the FMA pipe level
 template <int HD>
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H, int ldo, int heads, const SeqMap& sm, int n_seq,
                             int mode, float logit_bound, cudaStream_t st) {
   const bool force_flash = mode == 1;
+  const bool bounded = logit_bound > 0.f && logit_bound <= kSeqKernelMaxLogit;
   const size_t seq_smem = AttnSeqCfg<HD>::smem_bytes(sm.S);
-  static const bool legacy_attn = env_flag("LAMSLIDE_LEGACY_ATTN");
-  const bool seq_ok = seq_smem <= 232448 - 1024 && (mode == 2 || (!legacy_attn && logit_bound > 0.f && logit_bound <= kSeqKernelMaxLogit));
+  static const bool legacy_attn = env_flag("LAMSLIDE_LEGACY_ATTN");   // debug builds: streaming flash kernel everywhere
+  static const bool no_tc = env_flag("LAMSLIDE_ATTN_NO_TC");          // debug builds: mma.sync whole-sequence kernel instead of tcgen05
+  const bool seq_ok = seq_smem <= 232448 - 1024 && (mode == 2 || (!legacy_attn && bounded));
   if (mode == 2 && !seq_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the whole-sequence attention kernel", sm.S);
-  // tcgen05 kernel (attn_tc.cuh): long sequences with bounded logits; mode 3 + 4 * variant forces it (tests / layout probes)
+  // tcgen05 kernel (attn_tc.cuh): long sequences with bounded logits whose double-buffered K / V images fit in shared memory
   const size_t tc_smem = AtcCfg<HD>::smem_bytes(sm.S);
-  // Measured on B200 (4AA temporal attention, 128 sequences x 16 heads, S = 1000, hd = 24): 755 us against 677 us for the mma.sync
-  // whole-sequence kernel — S has to come back from TMEM through tcgen05.ld (measured 100 B/clk/SM, scripts/ldtm_bench.cu), which
-  // costs 0.31 ms on top of the 0.48 ms of MUFU exponentials, and the two did not overlap in any of the variants tried.  The
-  // tcgen05 kernel is therefore opt-in (LAMSLIDE_ATTN_TC=1); tests exercise it through mode 3.
-  static const bool use_tc = env_flag("LAMSLIDE_ATTN_TC");
   const bool tc_forced = (mode & 3) == 3;
-  const bool tc_ok = tc_smem <= 232448 && (tc_forced || (mode == 0 && use_tc && !legacy_attn && sm.S >= 384 && logit_bound > 0.f &&
-                                                          logit_bound <= kSeqKernelMaxLogit));
+  const bool tc_ok = tc_smem <= 232448 && (tc_forced || (mode == 0 && !legacy_attn && !no_tc && sm.S >= 384 && bounded));
   if (tc_forced && !tc_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the tcgen05 attention kernel", sm.S);
   if (tc_ok) {
-    static const int poly = getenv("LAMSLIDE_ATTN_TC_POLY") ? atoi(getenv("LAMSLIDE_ATTN_TC_POLY")) : 0;
-    void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int, int) =
-        poly == 1 ? attn_tc_kernel<HD, 1> : poly == 2 ? attn_tc_kernel<HD, 2> : poly == 3 ? attn_tc_kernel<HD, 3> : attn_tc_kernel<HD, 0>;
+    const int variant = tc_forced ? (mode >> 2) : env_int("LAMSLIDE_ATTN_TC_VARIANT", 0);
+    void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int, int, long long*) =
+        variant == 1 ? attn_tc_kernel<HD, 0> : variant == 2 ? attn_tc_kernel<HD, 2> : variant == 3 ? attn_tc_kernel<HD, 4>
+        : variant == 4 ? attn_tc_kernel<HD, -1> : variant == 5 ? attn_tc_kernel<HD, kAtcPolyDefault, true>
+        : variant == 6 ? attn_tc_kernel<HD, -1, true> : attn_tc_kernel<HD, kAtcPolyDefault>;
     TRY(ensure_dynamic_smem((const void*)kern, 232448, true));
-    kern<<<(unsigned)(n_seq * heads), kAtcThreads, tc_smem, st>>>(qkv, out, H, ldo, sm, heads, tc_forced ? (mode >> 2) : 0);
+    const int n_items = n_seq * heads;
+    kern<<<(unsigned)std::min(num_sms(), n_items), kAtcThreads, tc_smem, st>>>(qkv, out, H, ldo, sm, heads, n_items, g_atc_trace);
     COUNT_KERNEL("attn_tc");
   } else if ((sm.S > 32 && seq_ok && !force_flash) || mode == 2) {
-    // share of the exponentials evaluated on the FMA pipe (poly_exp2) instead of MUFU (of 16 per thread and key block).
-    // Measured on B200 (4AA temporal attention): 0 -> 677 us, 2 -> 706, 4 -> 742, 8 -> 820: the kernel is issue-bound, so the
-    // extra FMA-pipe instructions cost more than the MUFU slots they free.  Default 0.
-    // Also tried (B200, same shape): exponentials on packed f16x2 with f16 P.V and row sums from an extra "ones column" MMA — 677 us
-    // again with all-MUFU (ex2.approx.f16x2 compiles to TWO MUFU.EX2.F16, there is no packed MUFU), 729-855 us with 1/4 .. 4/4 of the
-    // pairs on an HFMA2 polynomial.  Legacy mma.sync peaks at 8.3 cycles per m16n8k16 and SM sub-partition (550 TFLOP/s,
-    // scripts/hmma_bench.cu): 14 HMMA + 16 MUFU per warp and 16-key block = 116 + 128 pipe cycles against 189 measured.
-    static const int poly = getenv("LAMSLIDE_ATTN_POLY") ? atoi(getenv("LAMSLIDE_ATTN_POLY")) : 0;
-    // 16 query rows per warp and 16 warps per CTA (63 registers) instead of 32 rows x 8 warps: 661 us against 677 us (B200, 4AA)
-    static const int mt1 = getenv("LAMSLIDE_ATTN_MT1") ? atoi(getenv("LAMSLIDE_ATTN_MT1")) : 1;
-    void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int) =
-        mt1 ? attn_seq_kernel<HD, 0x0000u, 1> : poly == 0 ? attn_seq_kernel<HD, 0x0000u> : poly == 2 ? attn_seq_kernel<HD, 0x0808u> : poly == 6 ? attn_seq_kernel<HD, 0xA8A8u>
-        : poly == 8 ? attn_seq_kernel<HD, 0xAAAAu> : attn_seq_kernel<HD, 0x8888u>;
+    // mma.sync whole-sequence kernel: shapes the tcgen05 kernel does not take (short sequences: MD17 L = 192; K / V images too large
+    // for double buffering).  16 query rows per warp and 16 warps per CTA.  Measured on B200 (4AA temporal attention): 661 us; it is
+    // bound by the 14 HMMA + 16 MUFU.EX2 per warp and 16-key block (scripts/hmma_bench.cu), exponentials on the FMA pipe made it slower.
+    void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int) = attn_seq_kernel<HD, 0x0000u, 1>;
     TRY(ensure_dynamic_smem((const void*)kern, 232448 - 1024));
-    kern<<<(unsigned)(n_seq * heads), mt1 ? 512 : 256, seq_smem, st>>>(qkv, out, H, ldo, sm, heads);
+    kern<<<(unsigned)(n_seq * heads), 512, seq_smem, st>>>(qkv, out, H, ldo, sm, heads);
     COUNT_KERNEL("attn_seq");
   } else if (sm.S <= 32 && !force_flash) {
     // contiguous sequences whose q|k|v rows fit 8 warps x 6 KB of shared memory: warp per sequence (attn_rows_kernel)
@@ -1076,6 +1083,43 @@ extern "C" int lamslide_lincomb3(float* out, const float* x, const float* m, con
   const long long n4 = numel / 4;
   lincomb3_kernel<<<cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>((float4*)out, (const float4*)x, (const float4*)m, (const float4*)w, px,
                                                                    pm, pw, n4);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int fill_lincomb(LincombN* a, const float* const* srcs, const float* coefs, int32_t n) {
+  if (!srcs || !coefs || n < 1 || n > 8) return fail(LAMSLIDE_ERR_INVALID, "between 1 and 8 terms (got %d)", n);
+  a->n = n;
+  for (int j = 0; j < 8; ++j) {
+    a->src[j] = j < n ? reinterpret_cast<const float4*>(srcs[j]) : nullptr;
+    a->coef[j] = j < n ? coefs[j] : 0.f;
+    if (j < n && (!srcs[j] || ((uintptr_t)srcs[j] & 15))) return fail(LAMSLIDE_ERR_INVALID, "term %d: null or not 16-byte aligned", j);
+  }
+  return 0;
+}
+
+// out = sum_j coefs[j] * srcs[j]: the stage / solution / interpolant combinations of the Runge-Kutta ODE integrators.
+extern "C" int lamslide_lincomb_n(float* out, const float* const* srcs, const float* coefs, int32_t n, int64_t numel, void* stream) {
+  if (!out || ((uintptr_t)out & 15)) return fail(LAMSLIDE_ERR_INVALID, "out: null or not 16-byte aligned");
+  if (numel <= 0 || numel % 4) return fail(LAMSLIDE_ERR_INVALID, "numel %lld must be a positive multiple of 4", (long long)numel);
+  LincombN a;
+  TRY(fill_lincomb(&a, srcs, coefs, n));
+  const long long n4 = numel / 4;
+  lincomb_n_kernel<<<cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>((float4*)out, a, n4);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// *acc (device fp64) += sum_i ((sum_j coefs[j] srcs[j][i]) / (atol + rtol max(|a_i|, |b_i|)))^2
+extern "C" int lamslide_rk_error_sumsq(const float* const* srcs, const float* coefs, int32_t n, const float* a, const float* b, double rtol,
+                                       double atol, int64_t numel, double* acc, void* stream) {
+  if (!a || !b || !acc || (((uintptr_t)a | (uintptr_t)b) & 15)) return fail(LAMSLIDE_ERR_INVALID, "a / b / acc: null or not 16-byte aligned");
+  if (numel <= 0 || numel % 4) return fail(LAMSLIDE_ERR_INVALID, "numel %lld must be a positive multiple of 4", (long long)numel);
+  LincombN e;
+  TRY(fill_lincomb(&e, srcs, coefs, n));
+  const long long n4 = numel / 4;
+  const int grid = (int)std::min<long long>(cdiv(n4, 256), 4LL * num_sms());
+  rk_error_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(e, (const float4*)a, (const float4*)b, rtol, atol, n4, acc);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1560,6 +1604,8 @@ extern "C" int64_t lamslide_launch_count(int32_t reset) {
   if (reset) g_launches = 0;
   return v;
 }
+
+extern "C" void lamslide_debug_attention_trace(void* device_buffer) { g_atc_trace = (long long*)device_buffer; }
 
 extern "C" int64_t lamslide_debug_kernel_count(const char* name, int32_t reset) {
   if (!name) return -1;

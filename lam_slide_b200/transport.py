@@ -10,7 +10,10 @@ integrators.py:84-120).  When ``model`` is (a bound method of an object whose ``
 Euler-Maruyama / Heun with every diffusion form and last-step variant on the Linear and GVP plans; the network runs through
 the same C-ABI forward, each update is one or two ``lamslide_lincomb3`` launches with coefficients evaluated here in fp64 (all of
 the reference's update rules are linear in state, network output and noise with time-only coefficients).
-Out of scope: likelihood, adaptive dopri5, the VP path and the training losses — requesting them raises
+``get_sample_fn("ODE", {...})`` with any other torchdiffeq method the reference can name — ``dopri5`` (its default; what
+``configs/eval_peptide.yaml`` runs), ``bosh3``, ``adaptive_heun``, ``midpoint``, ``rk4``, ``heun2``, ``heun3`` — goes through
+``lam_slide_b200/odeint.py`` (torchdiffeq's adaptive Runge-Kutta controller restated on device tensors).
+Out of scope: likelihood, the VP path, reverse time and the training losses — requesting them raises
 ``NotImplementedError``.
 """
 from __future__ import annotations
@@ -250,8 +253,13 @@ class Sampler:
         return _sample
 
     def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3, reverse=False):
-        if sampling_method != "euler":
-            raise NotImplementedError(f"ODE method '{sampling_method}' is not implemented (fixed-grid 'euler' only)")
+        """transport.py:365-411 + integrators.py:84-120.  ``euler`` with a ``LatentSIV3`` model is one fused C-ABI call; every other
+        torchdiffeq method the reference can name here (``dopri5`` — its default —, ``bosh3``, ``adaptive_heun``, ``midpoint``, ``rk4``,
+        ``heun2``, ``heun3``) goes through ``lam_slide_b200.odeint``.  ``fn.stats`` holds the function-evaluation / step counts of the
+        last call of an adaptive method."""
+        from . import odeint as _ode
+        if sampling_method not in _ode.METHODS:
+            raise NotImplementedError(f"ODE method '{sampling_method}' is not implemented (have: {', '.join(_ode.METHODS)})")
         if reverse:
             raise NotImplementedError("reverse-time sampling is not implemented")
         tr = self.transport
@@ -265,13 +273,30 @@ class Sampler:
         @torch.no_grad()
         def _sample(init: Tensor, model: Callable, **model_kwargs) -> Tensor:
             bb = _find_backbone(model)
-            if bb is not None:
+            if bb is not None and sampling_method == "euler":
                 return bb.ode_sample(init, model_kwargs["x_cond"], model_kwargs["x_cond_mask"], model_kwargs.get("y"),
                                      path_type=path, prediction=pred, num_steps=num_steps)
-            # generic callable: Python loop, one fused drift+Euler launch per step
             _lib.require_cuda(init)
             lib = _lib.load()
             grid = torch.linspace(t0, t1, num_steps)  # fp32 on the host, as integrators.py:98
+            if sampling_method != "euler":
+                B = init.shape[0]
+
+                def drift(t: float, x: Tensor) -> Tensor:
+                    """Transport.get_drift (transport.py:158-202) around one network evaluation: v = cm(t) m + cx(t) x."""
+                    tv = torch.full((B,), t, device=x.device, dtype=torch.float32)
+                    m = model(x, tv, **model_kwargs).to(torch.float32).contiguous()
+                    assert m.shape == x.shape, "Output shape from ODE solver must match input shape"  # transport.py:197-199
+                    cm, cx = drift_coeffs(path, pred, t)
+                    if cx == 0.0 and cm == 1.0:
+                        return m
+                    return _lincomb(torch.empty_like(x), x, m, None, cx, cm, 0.0)
+
+                stats: Dict[str, Any] = {}
+                out = _ode.odeint(drift, init, grid, method=sampling_method, rtol=rtol, atol=atol, stats=stats)
+                _sample.stats = stats
+                return out
+            # fixed-grid Euler around a generic callable: Python loop, one fused drift + update launch per step
             x = init.to(torch.float32).contiguous().clone()
             states = [x.clone()]
             for i in range(num_steps - 1):
@@ -285,4 +310,5 @@ class Sampler:
                 states.append(x.clone())
             return torch.stack(states)
 
+        _sample.stats = {}
         return _sample

@@ -38,33 +38,35 @@ def attn():
 
 
 def attn_tc_probe():
-    """numerics of the tcgen05 attention kernel for the four descriptor variants (prints, does not assert) + timing"""
+    """numerics of the tcgen05 attention kernel on a few shapes (prints, does not assert) + timing of the exponential-mix variants
+    (mode 3 + 4 v: v = 0 shipped mix, 1 all MUFU, 2 / 3: 2 / 4 of 8 pairs on the FMA-pipe polynomial) against the mma.sync kernel"""
     from tests.test_gpu_kernels import _attention_reference
     lib = L.load()
     st = torch.cuda.current_stream().cuda_stream
-    for (B, T, Lx, H, heads) in [(1, 300, 2, 384, 16), (1, 512, 1, 256, 16), (2, 130, 3, 128, 4)]:
+    for (B, T, Lx, H, heads) in [(1, 300, 2, 384, 16), (1, 512, 1, 256, 16), (2, 130, 3, 128, 4), (1, 64, 1, 256, 16), (2, 1000, 2, 384, 16)]:
         n = B * T * Lx
         g = torch.Generator().manual_seed(n)
         qkv = torch.randn(n, 3 * H, generator=g).to(torch.bfloat16).cuda()
         ref = _attention_reference(qkv, B, T, Lx, H, heads, True)
-        for variant in range(4):
-            out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
-            rc = lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, 3 + 4 * variant, st)
-            try:
-                torch.cuda.synchronize()
-                err = float((out.float() - ref).abs().max() / ref.abs().max())
-                mean = float((out.float() - ref).abs().mean() / ref.abs().mean())
-                print(f"attn_tc B={B} T={T} L={Lx} H={H} heads={heads} variant={variant}: rc={rc} max_rel={err:.3e} mean_rel={mean:.3e}", flush=True)
-            except Exception as e:  # a trapped launch poisons the context: stop
-                print(f"attn_tc variant={variant}: CUDA error {e}", flush=True)
-                return
+        out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
+        rc = lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, 3, st)
+        try:
+            torch.cuda.synchronize()
+            err = float((out.float() - ref).abs().max() / ref.abs().max())
+            mean = float((out.float() - ref).abs().mean() / ref.abs().mean())
+            print(f"attn_tc B={B} T={T} L={Lx} H={H} heads={heads}: rc={rc} max_rel={err:.3e} mean_rel={mean:.3e}", flush=True)
+        except Exception as e:  # a trapped launch poisons the context: stop
+            print(f"attn_tc: CUDA error {e}", flush=True)
+            return
     B, T, Lx, H, heads = 64, 1000, 2, 384, 16
     n = B * T * Lx
     qkv = (torch.randn(n, 3 * H, device="cuda") * 0.6).to(torch.bfloat16)
     out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
-    for mode, name in [(3, "tcgen05"), (2, "mma.sync whole-sequence")]:
+    for mode, name in [(3, "tcgen05 shipped mix (3/8 poly)"), (7, "tcgen05 all MUFU"), (11, "tcgen05 2/8 poly"), (15, "tcgen05 4/8 poly"),
+                       (19, "tcgen05 pipeline only (no exponentials)"),
+                       (2, "mma.sync whole-sequence")]:
         us = time_fn(lambda: L.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, mode, st)), iters=10)
-        print(f"attention 4AA temporal [{name}] poly={os.environ.get('LAMSLIDE_ATTN_TC_POLY', '0')}: {us:8.1f} us  {4.0 * 24 * T * T * heads * B * Lx / us * 1e-6:7.1f} TFLOP/s", flush=True)
+        print(f"attention 4AA temporal [{name}]: {us:8.1f} us  {4.0 * 24 * T * T * heads * B * Lx / us * 1e-6:7.1f} TFLOP/s", flush=True)
 
 
 def linear1():
@@ -111,7 +113,49 @@ def fused():
         print(f"fused mlp rows={rows} debug={dbg} max_stages={stages}: {us:8.1f} us  {flops / us * 1e-6:7.1f} TFLOP/s", flush=True)
 
 
+def attn_tc_once():
+    """one warm launch pair of the shipped tcgen05 attention kernel at the 4AA shape (target of an ncu capture)"""
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    B, T, Lx, H, heads = 64, 1000, 2, 384, 16
+    n = B * T * Lx
+    qkv = (torch.randn(n, 3 * H, device="cuda") * 0.6).to(torch.bfloat16)
+    out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
+    for _ in range(3):
+        L.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, 3, st))
+    torch.cuda.synchronize()
+
+
+def attn_tc_trace():
+    """where the MMA warp and a softmax warp of the tcgen05 attention kernel spend their cycles (trace variants 5 / 6)"""
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    B, T, Lx, H, heads = 64, 1000, 2, 384, 16
+    n = B * T * Lx
+    qkv = (torch.randn(n, 3 * H, device="cuda") * 0.6).to(torch.bfloat16)
+    out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
+    buf = torch.zeros(148, 32, dtype=torch.int64, device="cuda")
+    lib.lamslide_debug_attention_trace(buf.data_ptr())
+    mma = ["wait s_free", "wait p_full", "issue QK (+q/kv waits)", "issue PV + commits", "-", "-", "-", "-"]
+    smx = ["wait S + first ld", "-", "exponent phase", "-", "hand-off P", "epilogue", "-", "-"]
+    for variant, name in [(5, "shipped mix"), (6, "no exponentials")]:
+        buf.zero_()
+        for _ in range(2):  # the kernel overwrites the buffer: the numbers are those of the second (warm) launch
+            L.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, 3 + 4 * variant, st))
+        torch.cuda.synchronize()
+        t = buf.double().mean(0).cpu()
+        steps = 13.84 * 32
+        print(f"--- trace [{name}] cycles per 128-key chunk step (average over CTAs; {steps:.0f} steps per group and CTA)")
+        print("  MMA warp 0   : " + ", ".join(f"{mma[i]} {t[i] / steps:.0f}" for i in range(0, 4)) + f"  | total {t[0:4].sum() / steps:.0f}")
+        print("  softmax warp4: " + ", ".join(f"{smx[i]} {t[8 + i] / steps:.0f}" for i in range(6)) + f"  | total {t[8:16].sum() / steps:.0f}")
+    lib.lamslide_debug_attention_trace(0)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "attn_tc_trace":
+        return attn_tc_trace()
+    if len(sys.argv) > 1 and sys.argv[1] == "attn_tc_once":
+        return attn_tc_once()
     if len(sys.argv) > 1 and sys.argv[1] == "fused":
         return fused()
     if len(sys.argv) > 1 and sys.argv[1] == "attn":

@@ -76,7 +76,9 @@ def test_transport_interval_and_api():
     assert callable(P.Sampler(tr).get_sample_fn("SDE", {}))  # Euler-Maruyama with the reference's defaults (transport.py:480-487)
     with pytest.raises(NotImplementedError):
         P.Sampler(tr).get_sample_fn("SDE", {"sampling_method": "Milstein"})
+    assert callable(P.Sampler(tr).get_sample_fn("ODE", {}))  # the reference's default: dopri5, num_steps 50, atol 1e-6, rtol 1e-3 (transport.py:365-372)
+    assert callable(P.Sampler(tr).get_sample_fn("ODE", {"sampling_method": "dopri5"}))  # configs/eval_peptide.yaml:21-23
     with pytest.raises(NotImplementedError):
-        P.Sampler(tr).get_sample_fn("ODE", {})  # reference default dopri5 is not implemented
+        P.Sampler(tr).get_sample_fn("ODE", {"sampling_method": "dopri8"})
     fn = P.Sampler(tr).get_sample_fn("ODE", {"sampling_method": "euler", "num_steps": 10})
     assert callable(fn)

@@ -181,12 +181,16 @@ def test_linear2_gated_residual(rows, H, M, rps, legacy):
     assert max_rel(h, ref) < 2e-5
 
 
-@pytest.mark.parametrize("B,T,L,H,heads,temporal", [
-    (2, 1000, 2, 384, 16, 1), (1, 300, 2, 384, 16, 1), (1, 129, 2, 384, 16, 1), (1, 1040, 1, 384, 16, 1), (2, 130, 3, 128, 4, 1),
-    (1, 512, 1, 256, 16, 1), (2, 7, 192, 256, 16, 0), (1, 64, 1, 256, 16, 1),
+@pytest.mark.parametrize("B,T,L,H,heads,temporal,variant", [
+    (2, 1000, 2, 384, 16, 1, 0), (1, 300, 2, 384, 16, 1, 0), (1, 129, 2, 384, 16, 1, 0), (1, 1024, 1, 384, 16, 1, 0), (2, 130, 3, 128, 4, 1, 0),
+    (1, 512, 1, 256, 16, 1, 0), (2, 7, 192, 256, 16, 0, 0), (1, 64, 1, 256, 16, 1, 0), (6, 640, 2, 384, 16, 1, 0), (3, 1000, 2, 384, 16, 1, 0),
+    (10, 100, 1, 384, 16, 1, 0), (2, 1000, 2, 384, 16, 1, 1), (2, 1000, 2, 384, 16, 1, 2), (2, 1000, 2, 384, 16, 1, 3), (5, 700, 2, 128, 4, 1, 0),
 ])
-def test_tcgen05_attention_matches_softmax_reference(B, T, L, H, heads, temporal):
-    """mode 3: S = Q K^T and O = P V on tcgen05 (accumulators and P in TMEM), K / V images in the no-swizzle UMMA layout."""
+def test_tcgen05_attention_matches_softmax_reference(B, T, L, H, heads, temporal, variant):
+    """mode 3 (+ 4 * variant: share of the exponentials on the FMA-pipe polynomial): the persistent tcgen05 kernel — S = Q K^T and
+    O = P V on the 5th-gen tensor cores, accumulators and P in TMEM, K / V images in the no-swizzle UMMA layout, double buffered over
+    (sequence, head) items.  Shapes: 1 .. 8 query tiles per item (odd and even counts: the two softmax groups interleave over the
+    CTA's tile stream), fewer and more items than SMs, sequences that end inside a tile and inside a 32-key group, hd 16 / 24 / 32."""
     L_ = _lib()
     lib = L_.load()
     n = B * T * L
@@ -194,7 +198,7 @@ def test_tcgen05_attention_matches_softmax_reference(B, T, L, H, heads, temporal
     qkv = (torch.randn(n, 3 * H, generator=g)).to(torch.bfloat16).cuda()
     ldo = H + 64
     out = torch.zeros(n, ldo, dtype=torch.bfloat16, device="cuda")
-    L_.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, L, H, heads, ldo, temporal, 3,
+    L_.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, L, H, heads, ldo, temporal, 3 + 4 * variant,
                                           torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = _attention_reference(qkv, B, T, L, H, heads, bool(temporal))
@@ -203,6 +207,12 @@ def test_tcgen05_attention_matches_softmax_reference(B, T, L, H, heads, temporal
     assert float(out[:, H:].float().abs().max()) == 0.0
     assert max_rel(got, ref) < 2e-2
     assert float((got - ref).abs().mean() / ref.abs().mean()) < 5e-3
+    # deterministic: same bits on a second launch (catches races between the softmax groups, the loaders and the MMA warp)
+    out2 = torch.zeros_like(out)
+    L_.check(lib.lamslide_debug_attention(qkv.data_ptr(), out2.data_ptr(), B, T, L, H, heads, ldo, temporal, 3 + 4 * variant,
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
 
 
 @pytest.mark.parametrize("rows,H,M,rps", [

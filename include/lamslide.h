@@ -201,7 +201,9 @@ int lamslide_debug_attention(const void* qkv_bf16, void* out_bf16, int32_t B, in
  * erf-GELU) in isolation: u [rows,H] bf16, w1 [3H+M,H] bf16 -> qkv [rows,3H] bf16, act[:, H:] of [rows,H+M] bf16.
  * The rope position of a row is (row / pos_div) % pos_mod.  legacy: 0 persistent kernel, 1 one-tile-per-CTA kernel,
  * 2 / 3 profiling aids of the persistent kernel (2: epilogue math without the global stores, 3: stores without the math);
- * + 16: run the persistent kernel as single CTAs instead of 2-CTA clusters that multicast the weight tiles. */
+ * + 16: run the persistent kernel as single CTAs instead of 2-CTA clusters that multicast the weight tiles;
+ * + 64: the spatial attention fused into the epilogue (sequences of pos_mod consecutive rows, pos_div = 1): only the q | k | v columns
+ *       are computed, qkv is not written, act[:, :H] receives softmax(q k^T / sqrt(hd)) v (mmdit.py:42-55, 240-249). */
 int lamslide_debug_linear1(const void* u_bf16, const void* w1_bf16, const float* bias, const float* q_scale, const float* k_scale,
                            void* qkv_bf16, void* act_bf16, int32_t rows, int32_t H, int32_t M, int32_t heads, int32_t pos_div,
                            int32_t pos_mod, float theta, int32_t legacy, void* stream);

@@ -285,20 +285,23 @@ layernorm_f32_kernel(const float* __restrict__ x, int ldx, int x_bcast_period, f
 
 // ---- dst[r, col0 + j] = table[idx[r], j]   (embedding gather into a column block of a wider row-major matrix)
 __global__ void gather_cols_kernel(float* __restrict__ dst, int ldd, int col0, const float* __restrict__ table, int width,
-                                   const long long* __restrict__ idx, long long rows) {
+                                   const long long* __restrict__ idx, long long rows, int pad = 0) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * width) return;
-  long long r = i / width;
-  int j = (int)(i % width);
-  dst[(size_t)r * ldd + col0 + j] = table[(size_t)idx[r] * width + j];
+  const int wp = width + pad;  // `pad` zero columns behind the gathered ones (see copy_cols_kernel)
+  if (i >= rows * wp) return;
+  long long r = i / wp;
+  int j = (int)(i % wp);
+  dst[(size_t)r * ldd + col0 + j] = j < width ? table[(size_t)idx[r] * width + j] : 0.f;
 }
-// ---- dst[r, col0 + j] = src[r, j]
-__global__ void copy_cols_kernel(float* __restrict__ dst, int ldd, int col0, const float* __restrict__ src, int width, long long rows) {
+// ---- dst[r, col0 + j] = src[r, j] for j < width, 0 for width <= j < width + pad (zero columns that round a feature row up to a
+// multiple of 4 floats, so the following linear layer can take the vectorised / tensor-core kernels)
+__global__ void copy_cols_kernel(float* __restrict__ dst, int ldd, int col0, const float* __restrict__ src, int width, int pad, long long rows) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * width) return;
-  long long r = i / width;
-  int j = (int)(i % width);
-  dst[(size_t)r * ldd + col0 + j] = src[(size_t)r * width + j];
+  const int wp = width + pad;
+  if (i >= rows * wp) return;
+  long long r = i / wp;
+  int j = (int)(i % wp);
+  dst[(size_t)r * ldd + col0 + j] = j < width ? src[(size_t)r * width + j] : 0.f;
 }
 // ---- dst[r, :] = src[r % period, :]   (broadcast of the learned latents over frames)
 __global__ void bcast_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, int width, int period, long long rows) {

@@ -50,7 +50,12 @@ __device__ __forceinline__ uint32_t stage_off64(int r, int c) { return r * 64 + 
 //   mlp : + bias -> erf-GELU (mmdit.py:11-18; ptx.cuh gelu_fast) -> bf16 -> act[:, H + j]   (A operand of linear2)
 // A chunk is one head (HD columns).  Output: thread-per-row packs the chunk into a padded shared-memory box (pitch = odd
 // number of 16-byte units), then the warp stores the box with row-contiguous 16-byte st.global (HD * 2 bytes per row).
-template <int HD>
+// AL > 0 (spatial blocks, sequences of AL CONSECUTIVE rows, AL a power of two <= 8, M = 0): the attention itself runs in this epilogue
+// (latent_si_v31.py:51-54, mmdit.py:42-55 for S = L).  The n-tiles are walked as (q, k, v) triples over the same heads; thread = row
+// keeps its normalised / rotated q (bf16) in the warp's shared-memory scratch, gets the k and v rows of its sequence from the
+// neighbouring lanes with shuffles, and writes softmax(q k^T) v straight into act[:, :H] — q, k and v of a spatial block never go to
+// HBM and the separate attention launch disappears (4AA: 87 us and ~670 MB per block).
+template <int HD, int AL = 0>
 struct EpiLinear1Ws {
   struct Params {
     const float* bias;      // [3H + M]
@@ -62,14 +67,20 @@ struct EpiLinear1Ws {
     int H, M, rows;
     int pos_div, pos_mod;   // rope position of a row = (row / pos_div) % pos_mod
     int debug;              // profiling aid (lamslide_debug_linear1): bit 0 = skip the global stores, bit 1 = skip the epilogue math
+    int act_ld;             // row pitch of act in elements (H + mlp hidden; M above is 0 when the MLP half runs in the fused kernel)
   };
   static constexpr int CW = HD;                                  // chunk width (columns)
-  static constexpr int kStageBytes = kWsStageBytesPerWarp;
   static constexpr int CH = HD / 8;                              // 16-byte units per chunk row
   // Global stores must cover whole 32-byte sectors (partial-sector writes ran at ~1.8 TB/s into L2 on B200 and bounded the
   // kernel): when a chunk row (HD * 2 bytes) is not a multiple of 32 bytes, two consecutive chunks are staged side by side
   // and written out together.
   static constexpr bool kPair = (HD * 2) % 32 != 0;
+  // AL mode scratch: 32 rows x (heads of a warp's column quarter) x HD bf16 — q, later the probabilities.  Paired boxes (hd = 24)
+  // have exactly that shape and are reused; the other layouts get 32 x 64 bytes behind the staging box.
+  static constexpr int kScratchOff = (AL > 0 && !kPair) ? kWsStageBytesPerWarp : 0;
+  static constexpr int kStageBytes = kWsStageBytesPerWarp + ((AL > 0 && !kPair) ? 2048 : 0);
+  static_assert(AL == 0 || (AL & (AL - 1)) == 0, "sequence length must be a power of two");
+  static_assert(AL * 4 <= HD * 2, "the probabilities of a head reuse its q slot");
   static constexpr int UNITS = kPair ? 2 * CH : CH;             // 16-byte units per staged row
   static constexpr int PITCH = (kPair ? UNITS : (UNITS % 2 == 0 ? UNITS + 1 : UNITS)) * 16;  // bytes (pairs: dense, 2-way conflicts on the writes only)
   static_assert(32 * PITCH <= kWsStageBytesPerWarp, "staging box too large");
@@ -80,6 +91,7 @@ struct EpiLinear1Ws {
   struct Tile {
     int kind;  // 0 q, 1 k, 2 v, 3 mlp
     const float4 *cs, *sn;  // this row's RoPE table entries (L1-resident: re-read per head rather than held in 24 registers)
+    int qrow_bytes;         // AL mode: bytes per scratch row = heads per column quarter * HD * 2
   };
   static __host__ __device__ int smem_floats(const Params& p) { return 3 * p.H + p.M; }
   static __device__ void load_consts(const Params& p, float* smf, int tid, int nthreads) {
@@ -89,13 +101,15 @@ struct EpiLinear1Ws {
   // n-tile order: MLP (MUFU-heavy epilogue) and q/k/v tiles alternate so the epilogue load is even over time
   template <int BN>
   static __device__ __forceinline__ int tile_n0(const Params& p, int nt) {
+    if constexpr (AL > 0) return (nt % 3) * p.H + (nt / 3) * BN;  // (q, k, v) triples over the same BN / HD heads
     const int nq = 3 * p.H / BN, nm = p.M / BN;
     const int pairs = nq < nm ? nq : nm;
     if (nt < 2 * pairs) return (nt & 1) ? (nt >> 1) * BN : 3 * p.H + (nt >> 1) * BN;
     const int r = nt - 2 * pairs + pairs;
     return nq > nm ? r * BN : 3 * p.H + r * BN;
   }
-  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx&, Tile& t, int row, int n0w) {
+  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx&, Tile& t, int row, int n0w, int qw) {
+    t.qrow_bytes = qw * 2;
     t.kind = n0w >= 3 * p.H ? 3 : n0w / p.H;  // BN divides H, so a tile — and a slice of it — is one kind
     const int pos = row < p.rows ? (row / p.pos_div) % p.pos_mod : 0;
     t.cs = reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * (HD / 2));
@@ -167,6 +181,37 @@ struct EpiLinear1Ws {
         w[2 * j] = pack_bf16x2(__uint_as_float(v[4 * j + 0]) + bv.x, __uint_as_float(v[4 * j + 1]) + bv.y);
         w[2 * j + 1] = pack_bf16x2(__uint_as_float(v[4 * j + 2]) + bv.z, __uint_as_float(v[4 * j + 3]) + bv.w);
       }
+      if constexpr (AL > 0) {
+        // ---- out = sum_j p_j v_j over the AL rows of this row's sequence (v_j from the neighbouring lanes), written as the
+        // attention half of act (mmdit.py:248: cat(attn, gelu(mlp)))
+        const uint32_t slot = c.stage_s + kScratchOff + c.lane * t.qrow_bytes + ck * (HD * 2);
+        float pr[AL];
+#pragma unroll
+        for (int j = 0; j < AL; j += 4) {
+          const float4 pv = ld_shared_f4(slot + j * 4);
+          pr[j] = pv.x;
+          if (j + 1 < AL) pr[j + 1] = pv.y;
+          if (j + 2 < AL) pr[j + 2] = pv.z;
+          if (j + 3 < AL) pr[j + 3] = pv.w;
+        }
+        float acc[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+        const int seq0 = c.lane & ~(AL - 1);
+#pragma unroll
+        for (int j = 0; j < AL; ++j) {
+#pragma unroll
+          for (int i = 0; i < HD / 2; ++i) {
+            const uint32_t vw = __shfl_sync(0xffffffffu, w[i], seq0 + j);
+            acc[2 * i] = fmaf(pr[j], __uint_as_float(vw << 16), acc[2 * i]);
+            acc[2 * i + 1] = fmaf(pr[j], __uint_as_float(vw & 0xffff0000u), acc[2 * i + 1]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < HD / 2; ++i) w[i] = pack_bf16x2(acc[2 * i], acc[2 * i + 1]);
+        emit(p, c, w, p.act, p.act_ld, col - 2 * p.H, ck);
+        return;
+      }
       emit(p, c, w, p.qkv, H3, col, ck);
       return;
     }
@@ -174,6 +219,58 @@ struct EpiLinear1Ws {
     // operands of the FMULs (a run-time q / k select made them 24 indexed LDC per chunk: 18 % of the kernel's stall samples).
     if (t.kind == 0) rms_rope<0>(p, t, v, bias_s, w);
     else rms_rope<1>(p, t, v, bias_s, w);
+    if constexpr (AL > 0) {
+      const uint32_t slot = c.stage_s + kScratchOff + c.lane * t.qrow_bytes + ck * (HD * 2);
+      if (t.kind == 0) {  // ---- q (already * hd^-0.5 * log2 e): park it until the k tile of the same heads arrives
+        if (ck == 0) {
+          if (kTmaStore && c.lane == 0) bulk_wait_read<0>();  // the previous triple's output box has been read by the TMA unit
+          __syncwarp();
+        }
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) st_shared_v4(slot + ch * 16, w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+        return;
+      }
+      // ---- k: logits of this row against the AL keys of its sequence, softmax in the exp2 domain, probabilities over the q slot
+      float q[HD];
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const uint4 qv = ld_shared_v4(slot + ch * 16);
+        const uint32_t qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          q[ch * 8 + 2 * i] = __uint_as_float(qq[i] << 16);
+          q[ch * 8 + 2 * i + 1] = __uint_as_float(qq[i] & 0xffff0000u);
+        }
+      }
+      float sc[AL];
+      const int seq0 = c.lane & ~(AL - 1);
+#pragma unroll
+      for (int j = 0; j < AL; ++j) {
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < HD / 2; ++i) {
+          const uint32_t kw = __shfl_sync(0xffffffffu, w[i], seq0 + j);
+          dot = fmaf(q[2 * i], __uint_as_float(kw << 16), dot);
+          dot = fmaf(q[2 * i + 1], __uint_as_float(kw & 0xffff0000u), dot);
+        }
+        sc[j] = dot;
+      }
+      float mx = sc[0];
+#pragma unroll
+      for (int j = 1; j < AL; ++j) mx = fmaxf(mx, sc[j]);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < AL; ++j) {
+        sc[j] = fast_exp2(sc[j] - mx);
+        sum += sc[j];
+      }
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < AL; j += 4)
+        st_shared_v4(slot + j * 4, __float_as_uint(sc[j] * inv), __float_as_uint(j + 1 < AL ? sc[j + 1] * inv : 0.f),
+                     __float_as_uint(j + 2 < AL ? sc[j + 2] * inv : 0.f), __float_as_uint(j + 3 < AL ? sc[j + 3] * inv : 0.f));
+      return;
+    }
     emit(p, c, w, p.qkv, H3, col, ck);
   }
   template <int IS_K>
@@ -236,7 +333,7 @@ struct EpiLinear2Ws {
   }
   template <int BN>
   static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
-  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx&, Tile& t, int row, int) {
+  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx&, Tile& t, int row, int, int) {
     const int b = (row < p.rows ? row : p.rows - 1) / p.rows_per_sample;
     t.gate = p.gate + (size_t)b * p.gate_stride;
   }
@@ -294,7 +391,7 @@ struct EpiEmbedWs {
   }
   template <int BN>
   static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
-  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx& c, Tile& t, int row, int) {
+  static __device__ __forceinline__ void tile_begin(const Params& p, const WsCtx& c, Tile& t, int row, int, int) {
     const int m = row < p.rows ? (p.mask[row] != 0 ? 1 : 0) : 0;
     t.em_s = c.smf_s + (p.H + m * p.H) * 4;
   }
@@ -331,7 +428,7 @@ struct EpiNullWs {
   static __device__ void load_consts(const Params&, float*, int, int) {}
   template <int BN>
   static __device__ __forceinline__ int tile_n0(const Params&, int nt) { return nt * BN; }
-  static __device__ __forceinline__ void tile_begin(const Params&, const WsCtx&, Tile&, int, int) {}
+  static __device__ __forceinline__ void tile_begin(const Params&, const WsCtx&, Tile&, int, int, int) {}
   static __device__ __forceinline__ void chunk(const Params&, const WsCtx&, const Tile&, const uint32_t*, int, int) {}
   static __device__ __forceinline__ void finish(const WsCtx&) {}
 };
@@ -549,7 +646,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t acc = tile & 1, use = tile >> 1;
         const int n0w = Epi::template tile_n0<BN>(ep, nt) + cq * QW;
         typename Epi::Tile ts;
-        Epi::tile_begin(ep, c, ts, row, n0w);
+        Epi::tile_begin(ep, c, ts, row, n0w, QW);
         mbar_wait(&tmem_full[acc], use & 1);
         tcgen05_fence_after();
 #pragma unroll 1

@@ -587,6 +587,21 @@ static int launch_linear2(const lamslide_backbone* bb, const CUtensorMap& ta, co
   }
 }
 
+// linear1 (q | k | v columns only) with the spatial attention fused into its epilogue (gemm_ws.cuh: EpiLinear1Ws<HD, AL>): sequences of
+// AL consecutive rows.  Returns 1 when the shape is not covered (caller: plain linear1 + attention kernel).
+template <int HD, int AL>
+static int launch_linear1_attn(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, const CUtensorMap& qkv_st,
+                               const CUtensorMap& act_st, int rows, const typename EpiLinear1Ws<HD, AL>::Params& ep, cudaStream_t st) {
+  const int N = 3 * bb->H, K = bb->H;
+  if (ep.M != 0 || bb->H % bb->bn1 != 0 || rows % AL != 0) return 1;
+  if constexpr (HD == 24) {
+    if (bb->bn1 == 192) return launch_gemm_ws<192, EpiLinear1Ws<24, AL>>(ta, bw.tm_w1, &bw.tm_w1_h, qkv_st, act_st, rows, N, K, ep, st);
+  } else {
+    if (bb->bn1 == 128) return launch_gemm_ws<128, EpiLinear1Ws<HD, AL>>(ta, bw.tm_w1, &bw.tm_w1_h, qkv_st, act_st, rows, N, K, ep, st);
+  }
+  return 1;
+}
+
 // warp-specialised variants; return 1 when the tiling is not covered (caller falls back to the kernels above)
 template <int HD>
 static int launch_linear1_ws(const lamslide_backbone* bb, const CUtensorMap& ta, const BlockWeights& bw, const CUtensorMap& qkv_st,
@@ -869,6 +884,9 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   const bool fused = !legacy_gemm && !no_fused && fused_mlp_ok(H, M) && (3 * H) % bb->bn1 == 0 &&
                      (bb->bn1 == 192 || bb->bn1 == 128 || (bb->bn1 == 64 && hd == 16));
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)hd));
+  // spatial attention over L <= 8 latents inside the linear1 epilogue (needs the fused-MLP path: linear1 computes q | k | v only)
+  static const bool no_fuse_spatial = env_flag("LAMSLIDE_NO_FUSED_SPATIAL_ATTN");
+  const bool fuse_spatial = fused && !no_fuse_spatial;
   for (int i = 0; i < bb->depth; ++i) {
     for (int s = 0; s < 2; ++s) {
       const BlockWeights& bw = bb->blocks[2 * i + s];
@@ -890,11 +908,22 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
         n_seq = B * L;
         cs = w.cos_t, sn = w.sin_t, pos_div = L, pos_mod = T;
       }
+#define L1_ATTN(HD_, AL_)                                                                                              \
+  {                                                                                                                      \
+    typename EpiLinear1Ws<HD_, AL_>::Params epa{bw.b1, {}, cs, sn, w.qkv, w.act, H, 0, n, pos_div, pos_mod, 0, H + M};  \
+    for (int j = 0; j < HD_; ++j) epa.gam[0][j] = bw.gq_h[j] * q_premul, epa.gam[1][j] = bw.gk_h[j];                     \
+    r1 = launch_linear1_attn<HD_, AL_>(bb, fc.tm_u, bw, fc.tm_qkv_st, fc.tm_act_st, n, epa, st);                         \
+    if (r1 < 0) return r1;                                                                                               \
+    attn_done = r1 == 0;                                                                                                 \
+  }
 #define L1_PARAMS(HD_)                                                                                                 \
   ProfScope ps(PC_LINEAR1, st);                                                                                          \
   int r1 = 1;                                                                                                            \
-  if (!legacy_gemm) {                                                                                                    \
-    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, {}, cs, sn, w.qkv, w.act, H, fused ? 0 : M, n, pos_div, pos_mod, 0};                    \
+  if (fuse_spatial && s == 0 && L == 2) L1_ATTN(HD_, 2)                                                                  \
+  else if (fuse_spatial && s == 0 && L == 4) L1_ATTN(HD_, 4)                                                             \
+  else if (fuse_spatial && s == 0 && L == 8 && HD_ >= 16) L1_ATTN(HD_, 8)                                                \
+  if (r1 == 1 && !legacy_gemm) {                                                                                         \
+    typename EpiLinear1Ws<HD_>::Params epw{bw.b1, {}, cs, sn, w.qkv, w.act, H, fused ? 0 : M, n, pos_div, pos_mod, 0, H + M};             \
     for (int j = 0; j < HD_; ++j) epw.gam[0][j] = bw.gq_h[j] * q_premul, epw.gam[1][j] = bw.gk_h[j];                                         \
     r1 = launch_linear1_ws<HD_>(bb, fc.tm_u, bw, fc.tm_qkv_st, fc.tm_act_st, n, epw, st);                                \
     if (r1 < 0) return r1;                                                                                               \
@@ -903,6 +932,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
     typename EpiLinear1<HD_>::Params ep{bw.b1, bw.gq, bw.gk, cs, sn, w.qkv, w.act, H, M, n, pos_div, pos_mod, q_premul}; \
     TRY(launch_linear1<HD_>(bb, fc.tm_u, bw, n, ep, st));                                                                \
   }
+      bool attn_done = false;  // the spatial attention ran inside the linear1 epilogue
       if (hd == 16) {
         L1_PARAMS(16)
       } else if (hd == 24) {
@@ -911,7 +941,8 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
         L1_PARAMS(32)
       }
 #undef L1_PARAMS
-      {
+#undef L1_ATTN
+      if (!attn_done) {
         ProfScope ps(s == 0 ? PC_ATTN_SPATIAL : PC_ATTN_TEMPORAL, st);
         TRY(attention_dispatch(w.qkv, w.act, H, H + M, heads, hd, sm, n_seq, 0, bw.logit_bound, st));
       }
@@ -1158,7 +1189,8 @@ struct lamslide_first_stage {
   std::vector<std::string> out_names;
   int device = 0;
   Arena arena;
-  int feat_dim = 0;
+  int feat_dim = 0;   // columns of the feature matrix = K of net_merge.0 as packed (rounded up to a multiple of 4, zero padded)
+  int feat_used = 0;  // columns that carry features
   float* ent_table = nullptr;                           // [num_entities, entity_dim], max_norm pre-applied
   float *tab0 = nullptr, *tab1 = nullptr;               // embedding_res / embed_atom / embed_team ; embed_group
   int tab0_dim = 0, tab1_dim = 0;
@@ -1264,7 +1296,7 @@ extern "C" int lamslide_first_stage_create(const lamslide_first_stage_config* cf
     case LAMSLIDE_FS_PEPTIDE: {
       TRY(ld.table("embedding_res.weight", 20, 64, true, &fs->tab0));
       fs->tab0_dim = 64;
-      fs->feat_dim = 64 + 42;
+      fs->feat_used = 64 + 42;
       const lamslide_tensor* sc = ld.sd.get("embed_res_pos.embeddings", {cfg->max_res, Din});
       if (!sc) return LAMSLIDE_ERR_MISSING;
       TRY(fs->arena.upload_f32(sc->data, (size_t)cfg->max_res * Din, &fs->sincos));
@@ -1278,19 +1310,32 @@ extern "C" int lamslide_first_stage_create(const lamslide_first_stage_config* cf
       if (!pb) return LAMSLIDE_ERR_MISSING;
       TRY(fs->arena.upload_f32(pb->data, 3 * 63, &fs->point_basis));
       TRY(ld.lin("embed_pos.mlp", 128, 129, true, &fs->point_mlp));
-      fs->feat_dim = 64 + 128;
+      fs->feat_used = 64 + 128;
       break;
     }
     case LAMSLIDE_FS_NBA:
       TRY(ld.table("embed_team.weight", 3, 32, false, &fs->tab0));
       TRY(ld.table("embed_group.weight", 2, 32, false, &fs->tab1));
       fs->tab0_dim = fs->tab1_dim = 32;
-      fs->feat_dim = 2 + 32 + 32;
+      fs->feat_used = 2 + 32 + 32;
       break;
-    case LAMSLIDE_FS_PEDESTRIAN: fs->feat_dim = 2; break;
+    case LAMSLIDE_FS_PEDESTRIAN: fs->feat_used = 2; break;
     default: return fail(LAMSLIDE_ERR_INVALID, "unknown first-stage kind %d", cfg->kind);
   }
-  TRY(ld.lin("net_merge.0", Din, fs->feat_dim, true, &fs->merge0));
+  // feature widths that are not a multiple of 4 (peptide 106, nba 66) are zero padded — in the feature matrix and in net_merge.0's K —
+  // so that layer takes the vectorised / 3xTF32 kernels (the scalar fallback cost 552 us per 4AA encode); the 2-wide pedestrian
+  // input is used in place
+  fs->feat_dim = fs->feat_used >= 4 ? (fs->feat_used + 3) / 4 * 4 : fs->feat_used;
+  {
+    const lamslide_tensor* w = ld.sd.get("net_merge.0.weight", {Din, fs->feat_used});
+    const lamslide_tensor* b = ld.sd.get("net_merge.0.bias", {Din});
+    if (!w || !b) return LAMSLIDE_ERR_MISSING;
+    std::vector<float> wp((size_t)Din * fs->feat_dim, 0.f);
+    for (int r = 0; r < Din; ++r) memcpy(&wp[(size_t)r * fs->feat_dim], &w->data[(size_t)r * fs->feat_used], (size_t)fs->feat_used * 4);
+    TRY(fs->arena.upload_f32(wp.data(), wp.size(), &fs->merge0.w));
+    TRY(fs->arena.upload_f32(b->data, Din, &fs->merge0.b));
+    fs->merge0.out = Din, fs->merge0.in = fs->feat_dim;
+  }
   TRY(ld.lin("net_merge.2", Din, Din, true, &fs->merge2));
   TRY(ld.lin("encoder.mlp.0", D, C, true, &fs->enc_mlp0));
   TRY(ld.lin("encoder.mlp.2", C, D, true, &fs->enc_mlp2));
@@ -1476,7 +1521,7 @@ static int encode_impl(lamslide_first_stage* fs, const lamslide_frame_inputs* in
       if (N > c.max_res) return fail(LAMSLIDE_ERR_INVALID, "N = %d exceeds max_res = %d", N, c.max_res);
       gather_cols_kernel<<<cdiv(R * 64, TB), TB, 0, st>>>(feat, fs->feat_dim, 0, fs->tab0, 64, (const long long*)in->index0, R);
       LAUNCH_CHECK();
-      copy_cols_kernel<<<cdiv(R * 42, TB), TB, 0, st>>>(feat, fs->feat_dim, 64, in->pos, 42, R);
+      copy_cols_kernel<<<cdiv(R * (fs->feat_dim - 64), TB), TB, 0, st>>>(feat, fs->feat_dim, 64, in->pos, 42, fs->feat_dim - fs->feat_used, R);
       LAUNCH_CHECK();
       break;
     case LAMSLIDE_FS_MD17:
@@ -1489,11 +1534,12 @@ static int encode_impl(lamslide_first_stage* fs, const lamslide_frame_inputs* in
       break;
     case LAMSLIDE_FS_NBA:
       if (!in->index0 || !in->index1) return fail(LAMSLIDE_ERR_INVALID, "nba encode needs team (index0) and group (index1)");
-      copy_cols_kernel<<<cdiv(R * 2, TB), TB, 0, st>>>(feat, fs->feat_dim, 0, in->pos, 2, R);
+      copy_cols_kernel<<<cdiv(R * 2, TB), TB, 0, st>>>(feat, fs->feat_dim, 0, in->pos, 2, 0, R);
       LAUNCH_CHECK();
       gather_cols_kernel<<<cdiv(R * 32, TB), TB, 0, st>>>(feat, fs->feat_dim, 2, fs->tab0, 32, (const long long*)in->index0, R);
       LAUNCH_CHECK();
-      gather_cols_kernel<<<cdiv(R * 32, TB), TB, 0, st>>>(feat, fs->feat_dim, 34, fs->tab1, 32, (const long long*)in->index1, R);
+      gather_cols_kernel<<<cdiv(R * (fs->feat_dim - 34), TB), TB, 0, st>>>(feat, fs->feat_dim, 34, fs->tab1, 32, (const long long*)in->index1, R,
+                                                                           fs->feat_dim - fs->feat_used);
       LAUNCH_CHECK();
       break;
     default: feat_in = in->pos; break;
@@ -1700,12 +1746,36 @@ static int debug_linear1_impl(const void* u, const void* w1, const float* bias, 
   TRY(make_tmap_ex(&tact, act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, H + M, 2 * HD, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
   const CUtensorMap* tbh = (legacy & 16) ? nullptr : &tbh_map;  // +16: force the one-CTA (no multicast) variant
   const bool flags32 = (legacy & 32) != 0;
+  const bool fused_attn = (legacy & 64) != 0;  // +64: spatial attention in the epilogue, sequences of pos_mod consecutive rows
   legacy &= 15;
   const float q_premul = (float)(1.4426950408889634 / std::sqrt((double)HD));
   int rc;
+  if (fused_attn) {
+    if (pos_div != 1) return fail(LAMSLIDE_ERR_INVALID, "fused spatial attention needs pos_div = 1");
+    float hq[32], hk[32];
+    CUDA_TRY(cudaMemcpy(hq, gq, HD * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hk, gk, HD * 4, cudaMemcpyDeviceToHost));
+    lamslide_backbone fake;  // only H and bn1 are read by launch_linear1_attn
+    fake.H = H, fake.bn1 = bn;
+    BlockWeights bw;
+    bw.tm_w1 = tb, bw.tm_w1_h = tbh_map;
+#define DBG_ATTN(AL_)                                                                                                              \
+  {                                                                                                                                \
+    typename EpiLinear1Ws<HD, AL_>::Params ep{bias, {}, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, 0, rows, 1, pos_mod, 0, H + M}; \
+    for (int j = 0; j < HD; ++j) ep.gam[0][j] = hq[j] * q_premul, ep.gam[1][j] = hk[j];                                            \
+    rc = launch_linear1_attn<HD, AL_>(&fake, ta, bw, tq, tact, rows, ep, st);                                                      \
+  }
+    if (pos_mod == 2) DBG_ATTN(2)
+    else if (pos_mod == 4) DBG_ATTN(4)
+    else if (pos_mod == 8) DBG_ATTN(8)
+    else rc = 1;
+#undef DBG_ATTN
+    if (rc == 1) rc = fail(LAMSLIDE_ERR_INVALID, "fused spatial attention does not cover H %d hd %d L %d rows %d", H, HD, pos_mod, rows);
+    return rc;
+  }
   if (legacy != 1) {
     typename EpiLinear1Ws<HD>::Params ep{bias, {}, cs, sn, (__nv_bfloat16*)qkv, (__nv_bfloat16*)act, H, M, rows, pos_div, pos_mod,
-                                         legacy == 2 ? 1 : legacy == 3 ? 2 : legacy == 4 ? 3 : legacy == 5 ? 4 : 0};
+                                         legacy == 2 ? 1 : legacy == 3 ? 2 : legacy == 4 ? 3 : legacy == 5 ? 4 : 0, H + M};
     {  // debug hook: the scales arrive as device pointers; fetch them once per distinct pointer pair (not thread-safe)
       static const float *last_q = nullptr, *last_k = nullptr;
       static float hq[32], hk[32];

@@ -155,6 +155,41 @@ def test_linear1_fused_epilogue(rows, H, M, heads, pos_div, pos_mod, legacy):
         assert float(err.mean() / ref.abs().mean()) < 3e-3, name
 
 
+@pytest.mark.parametrize("rows,H,M,heads,L", [
+    (2000, 384, 1536, 16, 2), (20000 + 38, 384, 1536, 16, 2), (128 * 150, 384, 1536, 16, 2), (128 * 151 + 64, 384, 1536, 16, 2), (2, 384, 1536, 16, 2),
+    (1600, 256, 1024, 16, 8), (8 * 2501, 256, 1024, 16, 8), (40 * 33, 128, 256, 4, 2), (4096 + 4, 384, 1536, 16, 4), (8 * 300, 384, 1536, 16, 8),
+])
+def test_linear1_with_fused_spatial_attention(rows, H, M, heads, L):
+    """linear1 (q | k | v columns) + QK-RMSNorm + RoPE + the attention over sequences of L consecutive rows, all inside the GEMM epilogue
+    (latent_si_v31.py:51-54; mmdit.py:42-55, 240-249), against an fp64 restatement: act[:, :H] = softmax(q k^T / sqrt(hd)) v."""
+    L_ = _lib()
+    lib = L_.load()
+    hd = H // heads
+    g = torch.Generator(device="cpu").manual_seed(rows + H + L)
+    u = torch.randn(rows, H, generator=g).to(torch.bfloat16).cuda()
+    w1 = (torch.randn(3 * H + M, H, generator=g) / math.sqrt(H)).to(torch.bfloat16).cuda()
+    bias = (0.1 * torch.randn(3 * H + M, generator=g)).cuda()
+    gq = (1.0 + 0.1 * torch.randn(hd, generator=g)).cuda()
+    gk = (1.0 + 0.1 * torch.randn(hd, generator=g)).cuda()
+    qkv = torch.zeros(rows, 3 * H, dtype=torch.bfloat16, device="cuda")
+    act = torch.zeros(rows, H + M, dtype=torch.bfloat16, device="cuda")
+    L_.check(lib.lamslide_debug_linear1(u.data_ptr(), w1.data_ptr(), bias.data_ptr(), gq.data_ptr(), gk.data_ptr(), qkv.data_ptr(),
+                                        act.data_ptr(), rows, H, M, heads, 1, L, 10000.0, 64, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    qkv_ref, _ = _linear1_reference(u, w1, bias, gq, gk, H, M, heads, 1, L)
+    q, k, v = (qkv_ref[:, i * H:(i + 1) * H].reshape(rows // L, L, heads, hd).permute(0, 2, 1, 3) for i in range(3))
+    p = torch.softmax((q @ k.transpose(-1, -2)) * math.log(2.0), dim=-1)  # q carries hd^-0.5 * log2(e)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(rows, H)
+    got = act[:, :H].double()
+    assert torch.isfinite(got).all()
+    assert float(act[:, H:].float().abs().max()) == 0.0 and float(qkv.float().abs().max()) == 0.0  # nothing else is written
+    err = (got - ref).abs()
+    # q and k are rounded to bf16 before the logits (as in the unfused path, where they travel through HBM): ~2^-8 of a logit of
+    # size ~5 moves a probability by up to ~1e-2
+    assert bool((err <= 2.0 ** -6 * ref.abs() + 3e-2).all()), f"max err {float(err.max()):.3e} at {int(err.argmax())}"
+    assert float(err.mean() / ref.abs().mean()) < 6e-3, f"mean rel err {float(err.mean() / ref.abs().mean()):.3e}"
+
+
 @pytest.mark.parametrize("rows,H,M,rps,legacy", [
     (1000, 384, 1536, 250, 0), (1000, 384, 1536, 250, 1), (20000 + 37, 384, 1536, 2000, 0), (333, 256, 1024, 160, 0),
     (777, 128, 256, 40, 0), (128 * 150, 384, 1536, 2000, 0), (20000 + 37, 384, 1536, 2000, 16), (128 * 151, 384, 1536, 2000, 0),

@@ -7,6 +7,8 @@ Public surface (mirrors the reference's interfaces for this path; see DESIGN.md 
     SecondStageSampler    encode -> conditioning -> Euler ODE -> decode  (SecondStageCondLightningBase.sample)
     SIAtom14SamplingWrapper  autoregressive roll-out driver, batched on device  (src/modules/sampling.py)
     KSampleEvaluator      K-sample min/mean ADE-FDE evaluation, one batched solve  (second_stage/{nba,pedestrian,md17}.py test_step)
+    odeint                dopri5 / bosh3 / adaptive_heun / midpoint / rk4 / heun behind Sampler.sample_ode  (torchdiffeq call of integrators.py)
+    formats               atom14 -> atom37 -> heavy-atom topology -> PDB / DCD  (sampling.py:64-142, geometry.py:14-33)
 """
 from .backbone import LatentSIV3  # noqa: F401
 from .configs import CONFIGS, get_config  # noqa: F401
@@ -16,3 +18,4 @@ from .rollout import SIAtom14SamplingWrapper  # noqa: F401
 from .evaluation import KSampleEvaluator, ksample_errors  # noqa: F401
 from .checkpoint import load_checkpoint, select_state_dict  # noqa: F401
 from .transport import CreateTransport, Sampler, Transport  # noqa: F401
+from . import formats, odeint  # noqa: F401

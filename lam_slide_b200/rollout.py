@@ -9,7 +9,9 @@ device between steps, and the conditioning frame is encoded ONCE per chain and s
 independently, so broadcasting its latents over T is identical to encoding T copies (tests/test_gpu_parity.py checks
 that bit for bit against ``model.sample(create_batch(...))``; at sizes where the first stage switches its GEMM kernel by row
 count — FMA below 4096 rows, 3xTF32 above — the two agree to fp32 rounding instead).
-Trajectory-file I/O (``sample_traj``, mdtraj / PDB writers; sampling.py:65-142) is out of scope.
+``sample_traj_files`` is the file-producing half of ``sample_traj`` + ``eval_peptide.sample_trajectory`` (sampling.py:65-142,
+eval_peptide.py:329-349) without mdtraj: conditioning frame and residue types in, ``<prefix>.dcd`` / ``<prefix>.pdb`` out
+(``lam_slide_b200/formats.py``; XTC's compression codec is not implemented).
 """
 from __future__ import annotations
 
@@ -18,6 +20,7 @@ from typing import Dict, Optional
 import torch
 from torch import Tensor
 
+from . import formats
 from .model import SecondStageSampler
 
 
@@ -74,3 +77,16 @@ class SIAtom14SamplingWrapper:
         positions = torch.cat(blocks, dim=1)
         positions[:, 0] = cond
         return positions * self.scale + self.shift
+
+    # sampling.py:65-100 + eval_peptide.py:340-349, from tensors instead of an mdtraj trajectory
+    @torch.no_grad()
+    def sample_traj_files(self, cond_pos: Tensor, res: Tensor, prefix: str, num_rollouts: int = 1, noise: Optional[Tensor] = None):
+        """``cond_pos [R, 14, 3]`` (nm, heavy atoms in atom14 slots, centred as ``sample_traj`` does), ``res [R]`` residue types ->
+        roll-out -> padding atom14 slots zeroed (sampling.py:96) -> atom37 heavy-atom trajectory -> ``<prefix>.dcd`` (all frames) and
+        ``<prefix>.pdb`` (first frame).  Returns ``(positions [frames, R, 14, 3] on the host, dcd path, pdb path)``."""
+        res = torch.as_tensor(res, dtype=torch.long)
+        res_mask = torch.as_tensor(formats.RESTYPE_ATOM14_MASK)[res].to(torch.bool)
+        pos = self.sample_rollout(cond_pos.to(torch.float32), res, res_mask, num_rollouts, noise=noise).detach().cpu()
+        pos = pos * res_mask[None, ..., None]
+        dcd, pdb = formats.save_trajectory(prefix, pos, res.tolist())
+        return pos, dcd, pdb

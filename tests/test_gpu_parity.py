@@ -3,6 +3,7 @@ generated from the real reference modules.  Tolerances are the ones BASELINE.jso
     per-step velocity max relative error  <= 1e-2   (bf16 tensor-core operands, fp32 state)
     final-frame coordinate RMSD           <= 1e-3 of the data scale (synthetic data scale = 1)
 The first stage runs in fp32 and is held to 1e-4."""
+import numpy as np
 import pytest
 import torch
 
@@ -220,6 +221,30 @@ def test_rollout_batched_equals_chain_by_chain():
         want[0] = ((cond[b] - c["shift"]) / c["scale"]).cuda()
         want = (want * c["scale"] + c["shift"]).cpu()
         assert torch.equal(got[b], want), f"chain {b}: max diff {float((got[b] - want).abs().max()):.3e}"
+
+
+def test_rollout_to_trajectory_files():
+    """sample_traj_files: roll-out -> atom37 heavy atoms -> DCD + PDB (sampling.py:65-142, eval_peptide.py:340-349 without mdtraj)."""
+    import os
+    import tempfile
+    import lam_slide_b200 as P
+    from lam_slide_b200 import formats as F
+    from oracle.make_golden import ROLLOUT_CASE, rollout_case_inputs
+    c = ROLLOUT_CASE
+    cfg, fs_sd, bb_sd, cond_pos, res, res_mask, noises = rollout_case_inputs(c)
+    m = _build(cfg, fs_sd, bb_sd)
+    m.hparams.sampling_kwargs["num_steps"] = c["num_steps"]
+    w = P.SIAtom14SamplingWrapper(m, shift=c["shift"], scale=c["scale"])
+    with tempfile.TemporaryDirectory() as d:
+        pos, dcd, pdb = w.sample_traj_files(cond_pos, res, os.path.join(d, "pep"), num_rollouts=2, noise=torch.stack(noises[:2]))
+        n_atoms = int(F.RESTYPE_ATOM14_MASK[res].sum())
+        xyz = F.read_dcd(dcd)
+        assert xyz.shape == (2 * c["T"], n_atoms, 3) and np.isfinite(xyz).all()
+        want = F.atom14_to_heavy_atoms(pos, res) * 10.0
+        assert np.array_equal(xyz, want.numpy().astype(np.float32))
+        px, atoms = F.read_pdb(pdb)
+        assert px.shape == (1, n_atoms, 3) and len(atoms) == n_atoms
+        assert np.abs(px[0] - want[0].numpy()).max() <= 5.01e-4
 
 
 def test_ksample_errors_kernel_vs_reference_golden():

@@ -11,33 +11,34 @@
 //     a tcgen05.ld -> exp2 -> row sum -> bf16 -> tcgen05.st loop (17.6 / 19.9 with ONE warp per scheduler); more loses again.
 // So the kernel is a "softmax engine" that keeps MUFU and the FMA pipe busy side by side, with everything else off its critical path:
 //
-// Persistent kernel, ONE CTA per SM, 12 warps.  A CTA walks (sequence, head) items  blockIdx.x, + gridDim.x, ...  K and V of the item
+// Persistent kernel, ONE CTA per SM, 20 warps.  A CTA walks (sequence, head) items  blockIdx.x, + gridDim.x, ...  K and V of the item
 // live in shared memory for the whole item in the canonical NO-SWIZZLE UMMA layout (8 x 16-byte core matrices): element (key, d) at
 //     (key / 8) * (hd / 8) * 128 + (d / 8) * 128 + (key % 8) * 16 + (d % 8) * 2          bytes,
 // which serves BOTH MMAs from one image each (K as the K-major B operand of S = Q K^T, V as the MN-major B operand of O = P V), and are
 // DOUBLE BUFFERED across items: the loader warp fills the next item's images while this one is being computed.
 // Two 128-row query tiles are in flight (groups A and B: alternate tiles of the CTA's tile stream).  TMEM columns of a group: S (128
 // keys = 128 fp32 columns), P (bf16 pairs: keys 0 .. 63 double buffered, keys 64 .. 127 single, 96 columns), O (32 columns).
-//   warps 0, 1  : MMA issuer of group A / B:   logits of S_g(n) in registers -> S_g(n + 1) = Q_g K_c'^T (KSTEPS x M128 N128 K16);
-//                                              P_g(n) complete -> O_g += P_g(n) V_c (8 x M128 N32 K16, A from TMEM) -> commits
-//   warp 2      : K / V loader (cp.async into the core-matrix layout)     warp 3 : Q-tile loader
-//   warps 4..7  : softmax of group A, thread = query row; warps 8..11 : group B.  Per 128-key chunk: 4 x (tcgen05.ld 32 columns,
-//                 software pipelined) -> exp2 (MUFU / polynomial mix) -> packed row sum -> bf16x2 -> tcgen05.st 16 columns of P.
-// Every hand-shake through an mbarrier, tcgen05.wait or fence costs the issuing warp 50 - 100 cycles in series with its exponentials,
-// and a round trip through the MMA warp ~700 (a small-N tcgen05.mma costs its issuer ~48 cycles whatever the tensor pipe needs: 350 -
-// 400 cycles to issue a chunk's Q K^T or P V with the commits), so the protocol is built to keep both OFF the softmax warps' path:
-//   * the S buffer is released when its last logits are in registers, three quarters into the exponent phase, and Q K^T of the next
-//     chunk executes under the rest of it;
-//   * P has its own columns, the lower half double buffered: a chunk starts writing P at once, and only the store of its upper half
-//     (half way through) needs P V of the previous chunk to be complete;
-//   * one MMA warp per group (one for both: +30 %).
-// What is left per chunk step and group (cycle trace, scripts/gpu_time_kernels.py attn_tc_trace): 1650 cycles of exponentials with both
-// groups sharing the pipes at the engine's 20 exp/clk/SM, ~280 waiting for S + the first tcgen05.ld, ~50 for the P hand-off, ~240
-// (amortised) for the O epilogue.  The two groups run IN PHASE (each scheduler holds one warp of A and one of B; when one stalls
-// the other speeds up, so any offset decays), so those ~570 cycles are idle pipes: 565 us per 4AA launch against 661 us for the
-// mma.sync kernel and 0.39 ms for the exponent engine alone.  Tried and measured on the way (B200, same launch): P over S with one
-// buffer per group and one MMA warp 567 us; three-slot rings of 64-key chunks 584 - 762 us (twice the hand-shakes per exponential);
-// a named-barrier baton that lets only one group compute at a time 650 - 690 us (one warp per scheduler reaches 3.7 exp/clk, two 5).
+//   warps 0, 1   : MMA issuer of group A / B:   logits of S_g(n) in registers -> S_g(n + 1) = Q_g K_c'^T (KSTEPS x M128 N128 K16);
+//                                               P_g(n) complete -> O_g += P_g(n) V_c (8 x M128 N32 K16, A from TMEM) -> commits
+//   warp 2       : K / V loader (cp.async into the core-matrix layout)     warp 3 : Q-tile loader
+//   warps 4..11  : softmax of group A, thread = (query row, half of the chunk's keys); warps 12..19 : group B.  Per 128-key chunk a
+//                  thread takes 64 logits: 4 x (tcgen05.ld 16 columns, double buffered) -> exp2 (MUFU / polynomial mix) -> packed
+//                  row sum -> bf16x2 -> tcgen05.st 8 columns of P; the two halves of a row add their sums through shared memory.
+// Every hand-shake through an mbarrier, tcgen05.wait or fence costs the issuing warp 50 - 100 cycles in series with its exponentials
+// (~450 cycles per chunk step to see S and pull the first logits, ~100 to hand P over, ~300 amortised for the O epilogue), and a
+// round trip through the MMA warp ~700 (a small-N tcgen05.mma costs its issuer ~48 cycles whatever the tensor pipe needs: 350 - 450
+// cycles to issue a chunk's Q K^T or P V with the commits).  The protocol keeps the round trips off the softmax warps' path —
+//   * the S buffer is released when a warp's last logits are in registers, half way through its exponentials, and Q K^T of the next
+//     chunk executes under the rest;
+//   * P has its own columns, the lower half double buffered: only the warps of the upper key half wait for P V of the previous chunk,
+//     and only before their first store;
+//   * one MMA warp per group (one for both: +30 %) —
+// and FOUR softmax warps per scheduler hide each other's hand-shake latency.  With two (thread = whole row, one warp of each group
+// per scheduler) the groups lock IN PHASE — when one stalls the other speeds up, so any offset decays — and the hand-shake cycles are
+// idle pipes: 565 us per 4AA launch; half-step phase barriers between the groups: 578 us; a baton that lets one group compute at a
+// time: 650 - 690 us (one warp per scheduler reaches 3.7 exp/clk, two 5); three-slot rings of 64-key chunks: 584 - 762 us (twice the
+// hand-shakes per exponential); all 64 logits of a thread loaded at once to release S earlier: 563 us (register spills at the
+// 96-register limit of 20 warps).  This version: 524 us against 661 us for the mma.sync kernel; the exponent engine alone would need 390 us.
 // After the last chunk of a tile the group reads O (tcgen05.ld), scales by 1 / row sum and stores bf16; tensor pipe ~25 % busy.
 // The contraction of S runs over d padded to a multiple of 16: the Q image carries zero chunks there, so whatever (finite) bytes
 // the K image has at those offsets do not matter; O is computed with N = 32, the columns >= hd are ignored.
@@ -46,7 +47,7 @@
 
 namespace lam {
 
-constexpr int kAtcThreads = 384;
+constexpr int kAtcThreads = 640;   // 4 control warps + 2 groups x 8 softmax warps (<= 96 registers per thread)
 constexpr int kAtcChunk = 128;    // keys per S tile
 constexpr int kAtcQBytes = 8192;  // one 128-row query tile image: 16 row groups x 4 d-chunks x 128 B
 // TMEM columns of group g (256 g + ...): S 0 .. 127 (fp32 logits); P (bf16 pairs) in two halves — keys 0 .. 63 double buffered at
@@ -62,8 +63,8 @@ struct AtcCfg {
   // one item buffer: K image | V image | 128-byte zero tail (the N = 32 P V MMA and the padded Q K^T step read one d-chunk past the
   // last key group)
   static __host__ __device__ size_t item_bytes(int S) { return 2 * kv_bytes(S) + 128; }
-  // 2 item buffers | 4 Q tiles (2 groups x 2) | barriers
-  static __host__ __device__ size_t smem_bytes(int S) { return 2 * item_bytes(S) + 4 * kAtcQBytes + 256; }
+  // 2 item buffers | 4 Q tiles (2 groups x 2) | partial row sums [2 groups][2 key halves][128 rows] | barriers
+  static __host__ __device__ size_t smem_bytes(int S) { return 2 * item_bytes(S) + 4 * kAtcQBytes + 2048 + 256; }
 };
 
 // no-swizzle UMMA shared-memory descriptor: start address, leading-dimension byte offset, stride-dimension byte offset
@@ -89,6 +90,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
                "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -127,12 +133,12 @@ __device__ __forceinline__ void poly_exp2_x2(float x0, float x1, float& e0, floa
   e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-// 32 logits of one query row -> 16 packed bf16x2 probabilities + packed partial row sums.  POLY of every 8 pairs go through the
+// 16 logits of one query row -> 8 packed bf16x2 probabilities + packed partial row sums.  POLY of the 8 pairs go through the
 // FMA-pipe polynomial, the rest through MUFU.EX2.  MASKED: keys >= nvalid get probability 0 (last chunk of a sequence only).
 template <int POLY, bool MASKED>
-__device__ __forceinline__ void atc_exp32(const uint32_t* sv, uint32_t* pk, uint64_t& lsum, int nvalid) {
+__device__ __forceinline__ void atc_exp16(const uint32_t* sv, uint32_t* pk, uint64_t& lsum, int nvalid) {
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
+  for (int i = 0; i < 16; i += 2) {
     const float x0 = __uint_as_float(sv[i]), x1 = __uint_as_float(sv[i + 1]);
     float e0, e1;
     if (POLY < 0) {  // profiling aid: no exponentials at all (what the rest of the pipeline costs)
@@ -202,7 +208,7 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
   const int ntiles = (S + 127) / 128, nchunks = Spad / kAtcChunk;
   const uint32_t kvb = (uint32_t)Cfg::kv_bytes(S), itemb = (uint32_t)Cfg::item_bytes(S);
   uint8_t* q_img = atc_smem + 2 * itemb;  // [group][parity] tiles of kAtcQBytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(q_img + 4 * kAtcQBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(q_img + 4 * kAtcQBytes + 2048);  // (2 KB of partial row sums in between)
   uint64_t* kv_full = bars;        // [2] loader -> MMA
   uint64_t* kv_empty = bars + 2;   // [2] MMA (last P V of both groups) -> loader
   uint64_t* q_full = bars + 4;     // [2 groups][2] loader -> MMA
@@ -225,8 +231,8 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], groups_per_item);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_full[i], 8);
       mbar_init(&p_free[i], 1);
       mbar_init(&o_done[i], 1);
     }
@@ -381,97 +387,100 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
       }
     }
   } else {
-    // ===================================================== softmax group g: thread = query row =====================================================
-    const int g = (warp - 4) >> 2;
+    // ===================================================== softmax group g: thread = (query row, half of the chunk's keys) =====================================================
+    // 8 warps per group, 4 softmax warps per scheduler (two of each group): a warp spends ~500 cycles per chunk step in hand-shakes
+    // (mbarrier polls, tcgen05.wait, fences, arrivals — each 50 - 100 cycles, in series with its own exponentials); with only two
+    // warps per scheduler, one per group, the groups lock in phase and those cycles are idle pipes.  Four warps cover each other.
+    const int g = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;   // keys 64 half .. 64 half + 63 of every 128-key chunk
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const uint32_t s_col = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * kAtcGroupCols;
-    const uint32_t p_lo = s_col + kAtcPLoCol, p_hi = s_col + kAtcPHiCol, o_col = s_col + kAtcOCol;
+    const uint32_t lane_t = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * kAtcGroupCols;
+    const uint32_t s_col = lane_t + half * 64, o_col = lane_t + kAtcOCol + half * 16;
+    float* lsum_x = reinterpret_cast<float*>(q_img + 4 * kAtcQBytes) + (g * 2) * 128;  // [2 halves][128 rows] partial row sums of the group
     AtcCursor cu;
     cu.init(g, first, stride, n_items, ntiles);
     uint64_t lsum = f32x2_pack(0.f, 0.f);
-    auto s_release = [&]() {  // the S buffer can take the next Q K^T while the last quarter of the exponentials is computed
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[g]);
-    };
     while (cu.valid) {
-      uint32_t ra[32], rb[32], pk[16];
+      uint32_t ra[16], rb[16], pk[8];
       ATC_TIC();
       mbar_wait(&s_full[g], cu.n & 1);
       tcgen05_fence_after();
-      tmem_ld32(s_col, ra);
+      tmem_ld16(s_col, ra);
+      tmem_ld16(s_col + 16, rb);
+      // P: keys 0 .. 63 are double buffered, keys 64 .. 127 wait for P V of the previous step (polled now, consumed after the first block)
+      const uint32_t p_col = half == 0 ? lane_t + kAtcPLoCol + (cu.n & 1) * 32 : lane_t + kAtcPHiCol;
+      const bool ok_p = half == 0 ? true : mbar_try_wait(&p_free[g], (cu.n & 1) ^ 1);
+      const int nvalid = S - cu.c * kAtcChunk - half * 64;  // keys >= S (zero K rows -> exp2(0) = 1) must not count: last chunk only
       tmem_ld_wait();
       ATC_TOC(0);
-      {
-        // ---- exponent phase
-        const int nvalid = S - cu.c * kAtcChunk;  // keys >= S (zero K rows -> exp2(0) = 1) must not count: last chunk of a sequence only
-        const uint32_t p_col = p_lo + (cu.n & 1) * 32;
-        tmem_ld32(s_col + 32, rb);
-        const bool ok_p = mbar_try_wait(&p_free[g], (cu.n & 1) ^ 1);  // polled now, needed before the second half of P is written
-        if (nvalid >= kAtcChunk) {
-          atc_exp32<POLY, false>(ra, pk, lsum, 32);
-          tmem_st16(p_col, pk);
-          tmem_ld_wait();
-          tmem_ld32(s_col + 64, ra);
-          atc_exp32<POLY, false>(rb, pk, lsum, 32);
-          tmem_st16(p_col + 16, pk);
-          tmem_ld_wait();
-          tmem_ld32(s_col + 96, rb);
-          atc_exp32<POLY, false>(ra, pk, lsum, 32);
-          if (!ok_p) mbar_wait(&p_free[g], (cu.n & 1) ^ 1);  // P V(n - 1) has read the upper half of P
-          tcgen05_fence_after();
-          tmem_st16(p_hi, pk);
-          tmem_ld_wait();
-          s_release();
-          atc_exp32<POLY, false>(rb, pk, lsum, 32);
-          tmem_st16(p_hi + 16, pk);
-        } else {
-          atc_exp32<POLY, true>(ra, pk, lsum, nvalid);
-          tmem_st16(p_col, pk);
-          tmem_ld_wait();
-          tmem_ld32(s_col + 64, ra);
-          atc_exp32<POLY, true>(rb, pk, lsum, nvalid - 32);
-          tmem_st16(p_col + 16, pk);
-          tmem_ld_wait();
-          tmem_ld32(s_col + 96, rb);
-          atc_exp32<POLY, true>(ra, pk, lsum, nvalid - 64);
-          if (!ok_p) mbar_wait(&p_free[g], (cu.n & 1) ^ 1);
-          tcgen05_fence_after();
-          tmem_st16(p_hi, pk);
-          tmem_ld_wait();
-          s_release();
-          atc_exp32<POLY, true>(rb, pk, lsum, nvalid - 96);
-          tmem_st16(p_hi + 16, pk);
-        }
+      if (nvalid >= 64) {
+        atc_exp16<POLY, false>(ra, pk, lsum, 16);
+        if (!ok_p) mbar_wait(&p_free[g], (cu.n & 1) ^ 1);
+        tcgen05_fence_after();
+        tmem_st8(p_col, pk);
+        tmem_ld16(s_col + 32, ra);
+        atc_exp16<POLY, false>(rb, pk, lsum, 16);
+        tmem_st8(p_col + 8, pk);
+        tmem_ld16(s_col + 48, rb);
+        tmem_ld_wait();
+      } else {
+        atc_exp16<POLY, true>(ra, pk, lsum, nvalid);
+        if (!ok_p) mbar_wait(&p_free[g], (cu.n & 1) ^ 1);
+        tcgen05_fence_after();
+        tmem_st8(p_col, pk);
+        tmem_ld16(s_col + 32, ra);
+        atc_exp16<POLY, true>(rb, pk, lsum, nvalid - 16);
+        tmem_st8(p_col + 8, pk);
+        tmem_ld16(s_col + 48, rb);
+        tmem_ld_wait();
+      }
+      // every logit of this warp's half is in registers: the S buffer can take the next Q K^T while the second half is computed
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);
+      if (nvalid >= 64) {
+        atc_exp16<POLY, false>(ra, pk, lsum, 16);
+        tmem_st8(p_col + 16, pk);
+        atc_exp16<POLY, false>(rb, pk, lsum, 16);
+        tmem_st8(p_col + 24, pk);
+      } else {
+        atc_exp16<POLY, true>(ra, pk, lsum, nvalid - 32);
+        tmem_st8(p_col + 16, pk);
+        atc_exp16<POLY, true>(rb, pk, lsum, nvalid - 48);
+        tmem_st8(p_col + 24, pk);
       }
       ATC_TOC(2);
-      {
-        // ---- hand P to the MMA warp
-        tmem_st_wait();
+      // ---- hand P to the MMA warp
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      ATC_TOC(4);
+      if (cu.c == nchunks - 1) {
+        // ---- O of this tile: the two key halves of a row exchange their partial sums through shared memory, normalise, and each
+        // stores 16 of the 32 accumulator columns as bf16.  (The next tile's first P V — the only MMA that overwrites O — is issued
+        // after this group's next p_full arrival, i.e. after these loads have completed.)
+        const int z = cu.item / heads, hh = cu.item % heads;
+        const int qrow = cu.t * 128 + row;
+        float l0, l1;
+        f32x2_unpack(lsum, l0, l1);
+        lsum = f32x2_pack(0.f, 0.f);
+        lsum_x[half * 128 + row] = l0 + l1;
+        if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float inv = 1.f / ((l0 + l1) + lsum_x[(half ^ 1) * 128 + row]);
+        mbar_wait(&o_done[g], cu.job & 1);
+        tcgen05_fence_after();
+        uint32_t ov[16];
+        tmem_ld16(o_col, ov);
+        tmem_ld_wait();
         tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g]);
-        ATC_TOC(4);
-        if (cu.c == nchunks - 1) {
-          // ---- O of this tile: normalise, store bf16.  (The next tile's first P V — the only MMA that overwrites O — is issued
-          // after this group's next p_full arrival, i.e. after these loads have completed.)
-          const int z = cu.item / heads, hh = cu.item % heads;
-          const int qrow = cu.t * 128 + row;
-          float l0, l1;
-          f32x2_unpack(lsum, l0, l1);
-          const float inv = 1.f / (l0 + l1);
-          lsum = f32x2_pack(0.f, 0.f);
-          mbar_wait(&o_done[g], cu.job & 1);
-          tcgen05_fence_after();
-          uint32_t ov[32];
-          tmem_ld32(o_col, ov);
-          tmem_ld_wait();
-          tcgen05_fence_before();
-          if (qrow < S) {
-            __nv_bfloat16* op = out + (size_t)(sm.base(z) + (long long)qrow * sm.seq_stride) * ldo + hh * HD;
+        if (qrow < S) {
+          __nv_bfloat16* op = out + (size_t)(sm.base(z) + (long long)qrow * sm.seq_stride) * ldo + hh * HD + half * 16;
 #pragma unroll
-            for (int d = 0; d < HD; d += 8) {
+          for (int d = 0; d < 16; d += 8) {
+            if (half * 16 + d < HD) {
               uint4 o4;
               o4.x = pack_bf16x2(__uint_as_float(ov[d + 0]) * inv, __uint_as_float(ov[d + 1]) * inv);
               o4.y = pack_bf16x2(__uint_as_float(ov[d + 2]) * inv, __uint_as_float(ov[d + 3]) * inv);
@@ -480,12 +489,15 @@ attn_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict_
               *reinterpret_cast<uint4*>(op + d) = o4;
             }
           }
-          ATC_TOC(5);
         }
-        cu.advance(first, stride, n_items, ntiles, nchunks);
+        // both halves have read the exchanged sums before the next tile's sums are written
+        if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        ATC_TOC(5);
       }
+      cu.advance(first, stride, n_items, ntiles, nchunks);
     }
-    if (TRACE && warp == 4 && lane == 0 && trace)
+    if (TRACE && warp == 4 && lane == 0 && trace)  // (group A, first key half, lane quarter 0)
       for (int i = 0; i < 8; ++i) trace[blockIdx.x * 32 + 8 + i] = tr[i];
   }
 #undef ATC_TIC

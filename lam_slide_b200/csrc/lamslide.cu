@@ -1411,8 +1411,9 @@ static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, 
   static const bool legacy_fs = env_flag("LAMSLIDE_LEGACY_FS_LINEAR");
   const bool vec_ok = !legacy_fs && L.in % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)L.w & 15) == 0;
   static const bool no_tc = env_flag("LAMSLIDE_FS_NO_TF32X3");
-  const bool tc_ok = vec_ok && !no_tc && L.out % 2 == 0 && ldy % 2 == 0 && ((uintptr_t)Y & 7) == 0 && (!res || (ldr % 2 == 0 && ((uintptr_t)res & 7) == 0)) &&
-                     rows >= 4096;  // tiny problems stay on the FMA kernel (launch-bound either way)
+  // the kernel is chosen by the layer's shape only, never by the row count: a trajectory must decode to the same bits whether it is
+  // sampled alone, in a batch of 64 or as a shard of a multi-GPU run
+  const bool tc_ok = vec_ok && !no_tc && L.out % 2 == 0 && ldy % 2 == 0 && ((uintptr_t)Y & 7) == 0 && (!res || (ldr % 2 == 0 && ((uintptr_t)res & 7) == 0));
   if (tc_ok) {
     dim3 grid(cdiv(L.out, 64), cdiv(rows, 128));
     linear_f32_tc_kernel<<<grid, 256, 0, st>>>(a);

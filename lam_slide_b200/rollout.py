@@ -6,9 +6,8 @@ The reference rolls ONE peptide at a time: every roll-out step builds a B = 1 ba
 frame, calls ``sample()`` (which encodes all T identical frames), moves the block to the host side of the loop and continues
 from its last frame.  Here many chains advance together (``[B, R, 14, 3]`` conditioning frames), everything stays on the
 device between steps, and the conditioning frame is encoded ONCE per chain and step — the first stage treats frames
-independently, so broadcasting its latents over T is identical to encoding T copies (tests/test_gpu_parity.py checks
-that bit for bit against ``model.sample(create_batch(...))``; at sizes where the first stage switches its GEMM kernel by row
-count — FMA below 4096 rows, 3xTF32 above — the two agree to fp32 rounding instead).
+independently and picks its kernels by layer shape only, so broadcasting its latents over T is identical to encoding T copies
+(tests/test_gpu_parity.py checks that bit for bit against ``model.sample(create_batch(...))``).
 ``sample_traj_files`` is the file-producing half of ``sample_traj`` + ``eval_peptide.sample_trajectory`` (sampling.py:65-142,
 eval_peptide.py:329-349) without mdtraj: conditioning frame and residue types in, ``<prefix>.dcd`` / ``<prefix>.pdb`` out
 (``lam_slide_b200/formats.py``; XTC's compression codec is not implemented).

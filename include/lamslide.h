@@ -75,6 +75,9 @@ int lamslide_backbone_forward(lamslide_backbone* h, const float* x, const float*
  * The time interval follows Transport.check_interval (transport.py:69-101): [0,1] for velocity models, [1e-3, 1-1e-3] otherwise.
  * x holds the initial noise on entry and the final state on exit.  states_out (nullable): [num_steps,B,T,L,D] like the
  * reference's return value; velocities_out (nullable): [num_steps-1,B,T,L,D] drift evaluations (parity tests). */
+/* workspace of lamslide_ode_sample for `num_steps` grid points (>= lamslide_backbone_workspace_bytes: the per-sample vector path of
+ * up to 16 evaluations is computed in one pass, since the time grid is known in advance). */
+size_t lamslide_ode_workspace_bytes(const lamslide_backbone* h, int32_t B, int32_t T, int32_t L, int32_t num_steps);
 int lamslide_ode_sample(lamslide_backbone* h, float* x, const float* x_cond, const int64_t* x_cond_mask, const float* y,
                         int32_t path_type, int32_t prediction, int32_t num_steps, float* states_out, float* velocities_out,
                         int32_t B, int32_t T, int32_t L, void* workspace, size_t workspace_bytes, void* stream);

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "liblamslide.so")
 SYMBOLS = [
     "lamslide_abi_version", "lamslide_last_error", "lamslide_launch_count",
     "lamslide_backbone_create", "lamslide_backbone_destroy", "lamslide_backbone_workspace_bytes",
-    "lamslide_backbone_forward", "lamslide_ode_sample", "lamslide_euler_step", "lamslide_setup_conditioning", "lamslide_ksample_errors", "lamslide_lincomb3",
+    "lamslide_backbone_forward", "lamslide_ode_sample", "lamslide_ode_workspace_bytes", "lamslide_euler_step", "lamslide_setup_conditioning", "lamslide_ksample_errors", "lamslide_lincomb3",
     "lamslide_lincomb_n", "lamslide_rk_error_sumsq",
     "lamslide_first_stage_create", "lamslide_first_stage_destroy", "lamslide_first_stage_workspace_bytes",
     "lamslide_encode", "lamslide_decode", "lamslide_debug_gemm", "lamslide_debug_attention",
@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     lib.lamslide_backbone_destroy.restype = None
     lib.lamslide_backbone_workspace_bytes.argtypes = [vp, i32, i32, i32]
     lib.lamslide_backbone_workspace_bytes.restype = sz
+    lib.lamslide_ode_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
+    lib.lamslide_ode_workspace_bytes.restype = sz
     lib.lamslide_backbone_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.lamslide_ode_sample.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, sz, vp]
     lib.lamslide_euler_step.argtypes = [vp, vp, i32, i32, C.c_float, C.c_float, vp, i64, vp]

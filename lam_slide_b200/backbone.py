@@ -170,8 +170,10 @@ class LatentSIV3(nn.Module):
         if self._handle is None or self._packed_versions != self._versions() or self._packed_device != device:
             self.pack(device)
 
-    def _workspace(self, B: int, T: int, L: int, device: torch.device):
-        need = _lib.load().lamslide_backbone_workspace_bytes(self._handle, B, T, L)
+    def _workspace(self, B: int, T: int, L: int, device: torch.device, num_steps: int = 0):
+        lib = _lib.load()
+        need = (lib.lamslide_ode_workspace_bytes(self._handle, B, T, L, num_steps) if num_steps else
+                lib.lamslide_backbone_workspace_bytes(self._handle, B, T, L))
         return self._ws.get(need, device)
 
     @staticmethod
@@ -213,7 +215,7 @@ class LatentSIV3(nn.Module):
         states = torch.empty((num_steps,) + tuple(x.shape), device=x.device, dtype=torch.float32) if return_states else None
         vel = torch.empty((num_steps - 1,) + tuple(x.shape), device=x.device, dtype=torch.float32) if return_velocities else None
         with torch.cuda.device(x.device):
-            ws, nbytes = self._workspace(B, T, L, x.device)
+            ws, nbytes = self._workspace(B, T, L, x.device, num_steps)
             _lib.check(_lib.load().lamslide_ode_sample(
                 self._handle, x.data_ptr(), x_cond.data_ptr(), m.data_ptr(), _lib.ptr(yy), PATH_TYPES[path_type],
                 PREDICTIONS[prediction], num_steps, _lib.ptr(states), _lib.ptr(vel), B, T, L, ws, nbytes,

@@ -35,43 +35,6 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, float* __rest
   e[b * 256 + 128 + i] = sinf(arg);
 }
 
-// ---- small dense layer on per-sample vectors: out[b, n] = post( sum_k pre(in[b, k]) * W[n, k] + bias[n] ) (+ add[b, n])
-// One warp per output column, 8 samples per block staged in shared memory.  pre/post: 0 = identity, 1 = SiLU.
-__global__ void __launch_bounds__(256)
-vec_linear_kernel(const float* __restrict__ in, int ldi, const float* __restrict__ W, const float* __restrict__ bias,
-                  const float* add, float* out, int ldo, int B, int N, int K, int pre, int post) {
-  extern __shared__ float xs[];  // [8][K]
-  const int b0 = blockIdx.y * 8;
-  for (int i = threadIdx.x; i < 8 * K; i += 256) {
-    int bb = i / K, k = i % K;
-    float v = (b0 + bb < B) ? in[(size_t)(b0 + bb) * ldi + k] : 0.f;
-    xs[i] = pre == 1 ? silu_f(v) : v;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 8 + warp;
-  if (n >= N) return;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    float w = __ldg(W + (size_t)n * K + k);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, xs[i * K + k], acc[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane < 8 && b0 + lane < B) {
-    float v = acc[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) v = (lane == i) ? acc[i] : v;
-    v += bias ? bias[n] : 0.f;
-    if (post == 1) v = silu_f(v);
-    if (add) v += add[(size_t)(b0 + lane) * ldo + n];
-    out[(size_t)(b0 + lane) * ldo + n] = v;
-  }
-}
-
 // ---- input embedding (latent_si_v31.py:172-174): h = x Wx^T + x_cond Wc^T + (bx + bc) + E_mask[m]
 // Wt is the pre-transposed, concatenated weight [2D, H] (k-major so a warp reads consecutive output columns).
 // 32 tokens per block; each thread owns output columns tid and tid + 256.

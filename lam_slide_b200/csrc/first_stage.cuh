@@ -10,7 +10,7 @@ namespace lam {
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // ---- Y[r, n] = epi( sum_k X[r, k] W[n, k] + bias[n] )   64x64 tile, 16-deep k slices, 4x4 outputs per thread.
-//   epi: optional GELU, optional + rowadd[(r % rowadd_period), n], optional + res[r, n]
+//   epi: optional GELU (gelu = 1), optional + rowadd[(r % rowadd_period), n], optional + res[r, n], optional SiLU of the sum (gelu = 2)
 struct LinearArgs {
   const float* X; int ldx;
   const float* W;      // [N, K] (nn.Linear layout)
@@ -65,9 +65,10 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs a) {
       int n = n0 + tx * 4 + j;
       if (n >= a.N) continue;
       float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
-      if (a.gelu) v = gelu_exact(v);
+      if (a.gelu == 1) v = gelu_exact(v);
       if (a.rowadd) v += a.rowadd[(size_t)(r % a.rowadd_period) * a.ldra + n];
       if (a.res) v += a.res[(size_t)r * a.ldr + n];
+      if (a.gelu == 2) v = v / (1.0f + expf(-v));
       a.Y[(size_t)r * a.ldy + n] = v;
     }
   }
@@ -137,9 +138,10 @@ __global__ void __launch_bounds__(256) linear_f32_v2_kernel(LinearArgs a) {
       const int n = n0 + tx * 4 + j;
       if (n >= a.N) continue;
       float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
-      if (a.gelu) v = gelu_exact(v);
+      if (a.gelu == 1) v = gelu_exact(v);
       if (a.rowadd) v += a.rowadd[(size_t)(r % a.rowadd_period) * a.ldra + n];
       if (a.res) v += a.res[(size_t)r * a.ldr + n];
+      if (a.gelu == 2) v = v / (1.0f + expf(-v));
       a.Y[(size_t)r * a.ldy + n] = v;
     }
   }
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(256, 2) linear_f32_tc_kernel(LinearArgs a) {
         if (n >= a.N) continue;  // N % 2 == 0: a column pair is all-in or all-out
         float v0 = acc[mt][nt][2 * hr] + (a.bias ? a.bias[n] : 0.f);
         float v1 = acc[mt][nt][2 * hr + 1] + (a.bias ? a.bias[n + 1] : 0.f);
-        if (a.gelu) v0 = gelu_erf(v0), v1 = gelu_erf(v1);  // erf to 3e-7 abs in ~14 instructions (libm erff: ~40, half of this kernel at K = 128)
+        if (a.gelu == 1) v0 = gelu_erf(v0), v1 = gelu_erf(v1);  // erf to 3e-7 abs in ~14 instructions (libm erff: ~40, half of this kernel at K = 128)
         if (a.rowadd) {
           const float* ra = a.rowadd + (size_t)(r % a.rowadd_period) * a.ldra + n;
           v0 += ra[0], v1 += ra[1];
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(256, 2) linear_f32_tc_kernel(LinearArgs a) {
           const float* rs = a.res + (size_t)r * a.ldr + n;
           v0 += rs[0], v1 += rs[1];
         }
+        if (a.gelu == 2) v0 = v0 / (1.0f + expf(-v0)), v1 = v1 / (1.0f + expf(-v1));
         *reinterpret_cast<float2*>(a.Y + (size_t)r * a.ldy + n) = make_float2(v0, v1);
       }
     }

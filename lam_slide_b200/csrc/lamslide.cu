@@ -343,12 +343,15 @@ struct BackboneWorkspace {
   __nv_bfloat16* qkv;
   __nv_bfloat16* act;
   float* m_out;
-  float *e, *hid, *vec, *hid2, *mod, *tvec;
+  float *e, *hid, *svec, *yhid, *yvec, *mod, *tvec;  // per-sample vector path, sized for n_vec network evaluations at once
+  int n_vec;
   float *cos_s, *sin_s, *cos_t, *sin_t;
   size_t bytes;
 };
 
-static BackboneWorkspace plan_workspace(const lamslide_backbone* bb, void* base, int B, int T, int L) {
+// n_vec: network evaluations whose per-sample vectors (timestep embedding -> time_in -> all modulations) are computed in one pass
+// (lamslide_ode_sample knows its whole time grid in advance)
+static BackboneWorkspace plan_workspace(const lamslide_backbone* bb, void* base, int B, int T, int L, int n_vec = 1) {
   BackboneWorkspace w;
   size_t off = 0;
   const size_t n = (size_t)B * T * L;
@@ -363,12 +366,15 @@ static BackboneWorkspace plan_workspace(const lamslide_backbone* bb, void* base,
   w.qkv = (__nv_bfloat16*)take(n * 3 * H * 2);
   w.act = (__nv_bfloat16*)take(n * (size_t)(H + M) * 2);
   w.m_out = (float*)take(n * D * 4);
-  w.e = (float*)take((size_t)B * 256 * 4);
-  w.hid = (float*)take((size_t)B * H * 4);
-  w.vec = (float*)take((size_t)B * H * 4);
-  w.hid2 = (float*)take((size_t)B * H * 4);
-  w.mod = (float*)take((size_t)B * bb->mod_width * 4);
-  w.tvec = (float*)take((size_t)B * 4);
+  const size_t R = (size_t)B * n_vec;
+  w.n_vec = n_vec;
+  w.e = (float*)take(R * 256 * 4);
+  w.hid = (float*)take(R * H * 4);
+  w.svec = (float*)take(R * H * 4);
+  w.yhid = (float*)take((size_t)B * H * 4);
+  w.yvec = (float*)take((size_t)B * H * 4);
+  w.mod = (float*)take(R * bb->mod_width * 4);
+  w.tvec = (float*)take(R * 4);
   w.cos_s = (float*)take((size_t)L * half * 4);
   w.sin_s = (float*)take((size_t)L * half * 4);
   w.cos_t = (float*)take((size_t)T * half * 4);
@@ -554,13 +560,17 @@ extern "C" size_t lamslide_backbone_workspace_bytes(const lamslide_backbone* h, 
   return plan_workspace(h, nullptr, B, T, L).bytes;
 }
 
-// ---- vector path helpers
-static int vec_linear(const float* in, int ldi, const float* W, const float* bias, const float* add, float* out, int ldo, int B,
-                      int N, int K, int pre, int post, cudaStream_t st) {
-  dim3 grid(cdiv(N, 8), cdiv(B, 8));
-  vec_linear_kernel<<<grid, 256, (size_t)8 * K * sizeof(float), st>>>(in, ldi, W, bias, add, out, ldo, B, N, K, pre, post);
-  LAUNCH_CHECK();
-  return 0;
+// evaluations per pass of the batched vector path of lamslide_ode_sample: all of them when that costs little memory (4AA, B = 64:
+// 4.3 MB per evaluation), at most 16, and no more than 256 MB of modulation vectors
+static int ode_vec_chunk(const lamslide_backbone* bb, int B, int n_evals) {
+  const size_t per_eval = (size_t)B * bb->mod_width * 4;
+  const int by_mem = (int)std::max<size_t>(1, ((size_t)256 << 20) / per_eval);
+  return std::max(1, std::min(std::min(n_evals, 16), by_mem));
+}
+
+extern "C" size_t lamslide_ode_workspace_bytes(const lamslide_backbone* h, int32_t B, int32_t T, int32_t L, int32_t num_steps) {
+  if (!h || B <= 0 || T <= 0 || L <= 0 || num_steps < 2) return 0;
+  return plan_workspace(h, nullptr, B, T, L, ode_vec_chunk(h, B, num_steps - 1)).bytes;
 }
 
 template <int HD>
@@ -792,6 +802,43 @@ static int ln_modulate(const lamslide_backbone* bb, const float* h, __nv_bfloat1
   return 0;
 }
 
+// ---- per-sample vector path (mmdit.py:93-124, 184-197; latent_si_v31.py:176-186) for n evaluations at once: rows r = (evaluation,
+// sample), t_all [n * B].  e = timestep_embedding(t);  hid = silu(time_in.in_layer(e));  svec = silu(time_in.out_layer(hid) [+ vec_in(y)
+// of the row's sample]);  mod = [every modulation.lin | adaLN_modulation.1](svec)  ->  ws.mod [n * B, depth * 6H + 2H].
+// fp32 through the first stage's linear kernels (3xTF32 tensor-core GEMM when the shapes allow: fp32-accurate).
+struct LinW;
+static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, long long rows, int act, const float* res, int ldr,
+                     const float* rowadd, int period, int ldra, cudaStream_t st);
+struct LinW {
+  float *w = nullptr, *b = nullptr;
+  int out = 0, in = 0;
+};
+static int vector_path(const lamslide_backbone* bb, const BackboneWorkspace& w, const float* t_all, const float* y, int B, int n,
+                       cudaStream_t st) {
+  ProfScope ps(PC_VEC, st);
+  const int H = bb->H, R = B * n;
+  if (n > w.n_vec) return fail(LAMSLIDE_ERR_WORKSPACE, "vector path: %d evaluations, workspace planned for %d", n, w.n_vec);
+  timestep_embed_kernel<<<cdiv(R * 128, 256), 256, 0, st>>>(t_all, w.e, R);
+  LAUNCH_CHECK();
+  LinW l;
+  const float* yv = nullptr;
+  if (y) {
+    const int V = bb->cfg.vec_in_dim;
+    l.w = bb->vec_w1, l.b = bb->vec_b1, l.out = H, l.in = V;
+    TRY(fs_linear(l, y, V, w.yhid, H, B, 2, nullptr, 0, nullptr, 0, 0, st));
+    l.w = bb->vec_w2, l.b = bb->vec_b2, l.out = H, l.in = H;
+    TRY(fs_linear(l, w.yhid, H, w.yvec, H, B, 0, nullptr, 0, nullptr, 0, 0, st));
+    yv = w.yvec;
+  }
+  l.w = bb->time_w1, l.b = bb->time_b1, l.out = H, l.in = 256;
+  TRY(fs_linear(l, w.e, 256, w.hid, H, R, 2, nullptr, 0, nullptr, 0, 0, st));
+  l.w = bb->time_w2, l.b = bb->time_b2, l.out = H, l.in = H;
+  TRY(fs_linear(l, w.hid, H, w.svec, H, R, 2, nullptr, 0, yv, B, H, st));
+  l.w = bb->mod_w, l.b = bb->mod_b, l.out = bb->mod_width, l.in = H;
+  TRY(fs_linear(l, w.svec, H, w.mod, bb->mod_width, R, 0, nullptr, 0, nullptr, 0, 0, st));
+  return 0;
+}
+
 struct ForwardCtx {
   BackboneWorkspace ws;
   CUtensorMap tm_u, tm_act, tm_u3;
@@ -801,9 +848,9 @@ struct ForwardCtx {
 };
 
 static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, int L, void* workspace, size_t workspace_bytes,
-                           cudaStream_t st) {
+                           cudaStream_t st, int n_vec = 1) {
   if (B <= 0 || T <= 0 || L <= 0) return fail(LAMSLIDE_ERR_INVALID, "B, T, L must be positive");
-  fc.ws = plan_workspace(bb, workspace, B, T, L);
+  fc.ws = plan_workspace(bb, workspace, B, T, L, n_vec);
   if (!workspace || workspace_bytes < fc.ws.bytes)
     return fail(LAMSLIDE_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, fc.ws.bytes);
   if (((uintptr_t)workspace & 1023) != 0) return fail(LAMSLIDE_ERR_INVALID, "workspace must be 1024-byte aligned");
@@ -827,7 +874,8 @@ static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, 
 
 // LatentSIV3.forward on prepared workspace; result (net output) in ws.m_out, or `out` when given.
 static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, const float* t, const float* x_cond,
-                       const int64_t* mask, const float* y, float* out, int B, int T, int L, cudaStream_t st) {
+                       const int64_t* mask, const float* y, float* out, int B, int T, int L, cudaStream_t st,
+                       const float* mod_ready = nullptr) {
   const int H = bb->H, M = bb->M, D = bb->D, hd = bb->hd, heads = bb->heads;
   const int n = B * T * L;
   BackboneWorkspace& w = fc.ws;
@@ -864,18 +912,11 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
       LAUNCH_CHECK();
     }
   }
-  // 2. vec = time_in(timestep_embedding(t)) [+ vec_in(y)];  all modulations of all layers in one matrix product
-  {
-    ProfScope ps(PC_VEC, st);
-    timestep_embed_kernel<<<cdiv(B * 128, 256), 256, 0, st>>>(t, w.e, B);
-    LAUNCH_CHECK();
-    TRY(vec_linear(w.e, 256, bb->time_w1, bb->time_b1, nullptr, w.hid, H, B, H, 256, 0, 1, st));
-    TRY(vec_linear(w.hid, H, bb->time_w2, bb->time_b2, nullptr, w.vec, H, B, H, H, 0, 0, st));
-    if (y) {
-      TRY(vec_linear(y, bb->cfg.vec_in_dim, bb->vec_w1, bb->vec_b1, nullptr, w.hid2, H, B, H, bb->cfg.vec_in_dim, 0, 1, st));
-      TRY(vec_linear(w.hid2, H, bb->vec_w2, bb->vec_b2, w.vec, w.vec, H, B, H, H, 0, 0, st));
-    }
-    TRY(vec_linear(w.vec, H, bb->mod_w, bb->mod_b, nullptr, w.mod, bb->mod_width, B, bb->mod_width, H, 1, 0, st));
+  // 2. per-sample vectors: all modulations of all layers (vector_path), unless the caller computed them for a whole time grid
+  const float* mod = mod_ready;
+  if (!mod) {
+    TRY(vector_path(bb, w, t, y, B, 1, st));
+    mod = w.mod;
   }
   // 3. layers
   static const bool legacy_gemm = env_flag("LAMSLIDE_LEGACY_GEMM");  // A/B switch: one-tile-per-CTA GEMM kernels
@@ -890,7 +931,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   for (int i = 0; i < bb->depth; ++i) {
     for (int s = 0; s < 2; ++s) {
       const BlockWeights& bw = bb->blocks[2 * i + s];
-      const float* modl = w.mod + (size_t)i * 6 * H + (size_t)s * 3 * H;  // shift | scale | gate
+      const float* modl = mod + (size_t)i * 6 * H + (size_t)s * 3 * H;  // shift | scale | gate
       {
         ProfScope ps(PC_LNMOD, st);
         TRY(ln_modulate(bb, w.h, w.u, modl, modl + H, n, T * L, st));
@@ -968,7 +1009,7 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   // 4. final adaLN + linear
   {
     ProfScope ps(PC_HEAD, st);
-    const float* ada = w.mod + (size_t)bb->depth * 6 * H;  // shift | scale
+    const float* ada = mod + (size_t)bb->depth * 6 * H;  // shift | scale
     TRY(ln_modulate_split3(bb, w.h, w.qkv, ada, ada + H, n, T * L, st));
     EpiPlain::Params ep{out ? out : w.m_out, bb->b_out, D, n};
     TRY(launch_plain(bb->bn_out, fc.tm_u3, bb->tm_wout, n, D, 3 * H, ep, st));
@@ -994,9 +1035,13 @@ extern "C" int lamslide_backbone_forward(lamslide_backbone* h, const float* x, c
   return forward_run(h, fc, x, t, x_cond, x_cond_mask, y, out, B, T, L, st);
 }
 
-__global__ void fill_kernel(float* p, float v, int n) {
+// t_all[s * B + b] = times.t[s]: the time vectors of up to 16 consecutive ODE steps (integrators.py:107-112: th.ones(B) * t)
+struct StepTimes {
+  float t[16];
+};
+__global__ void fill_steps_kernel(float* p, StepTimes times, int B, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  if (i < B * n) p[i] = times.t[i / B];
 }
 __global__ void copy_f4_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long n4) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1052,8 +1097,11 @@ extern "C" int lamslide_ode_sample(lamslide_backbone* h, float* x, const float* 
   if (num_steps < 2) return fail(LAMSLIDE_ERR_INVALID, "num_steps must be >= 2");
   TRY(check_device(h));
   cudaStream_t st = (cudaStream_t)stream;
+  // the per-sample vector path (timestep embedding -> time_in -> every layer's modulation) depends on the time grid only, which is
+  // known in advance: it runs once per chunk of up to 16 steps instead of once per step
+  const int chunk = ode_vec_chunk(h, B, num_steps - 1);
   ForwardCtx fc;
-  TRY(forward_prepare(h, fc, B, T, L, workspace, workspace_bytes, st));
+  TRY(forward_prepare(h, fc, B, T, L, workspace, workspace_bytes, st, chunk));
   // Transport.check_interval (transport.py:69-101) for the ODE sampler
   float t0 = 0.f, t1 = 1.f;
   if (prediction != 0) t0 = 1e-3f, t1 = 1.f - 1e-3f;
@@ -1063,19 +1111,26 @@ extern "C" int lamslide_ode_sample(lamslide_backbone* h, float* x, const float* 
     copy_f4_kernel<<<cdiv(n4, 256), 256, 0, st>>>((const float4*)x, (float4*)states_out, n4);
     LAUNCH_CHECK();
   }
-  for (int i = 0; i < num_steps - 1; ++i) {
-    const float ti = linspace_f32(t0, t1, num_steps, i);
-    const float tn = linspace_f32(t0, t1, num_steps, i + 1);
-    fill_kernel<<<cdiv(B, 256), 256, 0, st>>>(fc.ws.tvec, ti, B);
+  for (int i0 = 0; i0 < num_steps - 1; i0 += chunk) {
+    const int n = std::min(chunk, num_steps - 1 - i0);
+    StepTimes times;
+    for (int s = 0; s < n; ++s) times.t[s] = linspace_f32(t0, t1, num_steps, i0 + s);
+    fill_steps_kernel<<<cdiv(B * n, 256), 256, 0, st>>>(fc.ws.tvec, times, B, n);
     LAUNCH_CHECK();
-    TRY(forward_run(h, fc, x, fc.ws.tvec, x_cond, x_cond_mask, y, nullptr, B, T, L, st));
-    double cm, cx;
-    TRY(drift_coefficients(path_type, prediction, (double)ti, &cm, &cx));
-    ProfScope ps(PC_EULER, st);
-    drift_euler_kernel<<<cdiv(n4, 256), 256, 0, st>>>(
-        (const float4*)fc.ws.m_out, (float4*)x, velocities_out ? (float4*)(velocities_out + (size_t)i * nel) : nullptr,
-        states_out ? (float4*)(states_out + (size_t)(i + 1) * nel) : nullptr, (float)cm, (float)cx, tn - ti, n4);
-    LAUNCH_CHECK();
+    TRY(vector_path(h, fc.ws, fc.ws.tvec, y, B, n, st));
+    for (int s = 0; s < n; ++s) {
+      const int i = i0 + s;
+      const float ti = times.t[s];
+      const float tn = linspace_f32(t0, t1, num_steps, i + 1);
+      TRY(forward_run(h, fc, x, nullptr, x_cond, x_cond_mask, y, nullptr, B, T, L, st, fc.ws.mod + (size_t)s * B * h->mod_width));
+      double cm, cx;
+      TRY(drift_coefficients(path_type, prediction, (double)ti, &cm, &cx));
+      ProfScope ps(PC_EULER, st);
+      drift_euler_kernel<<<cdiv(n4, 256), 256, 0, st>>>(
+          (const float4*)fc.ws.m_out, (float4*)x, velocities_out ? (float4*)(velocities_out + (size_t)i * nel) : nullptr,
+          states_out ? (float4*)(states_out + (size_t)(i + 1) * nel) : nullptr, (float)cm, (float)cx, tn - ti, n4);
+      LAUNCH_CHECK();
+    }
   }
   return 0;
 }
@@ -1171,10 +1226,6 @@ extern "C" int lamslide_ksample_errors(const float* preds, const float* target, 
 // ================================================================================================ first stage
 struct LNW {
   float *w = nullptr, *b = nullptr;
-};
-struct LinW {
-  float *w = nullptr, *b = nullptr;
-  int out = 0, in = 0;
 };
 struct AttnBlockW {  // CrossAttentionBlock / SelfAttentionBlock (torch_modules.py:189-273)
   bool cross = false;
@@ -1402,12 +1453,13 @@ struct Bump {
   }
 };
 
-static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, long long rows, bool gelu, const float* res, int ldr,
+// act: 0 none, 1 erf-GELU (before the adds), 2 SiLU of the sum (after the adds)
+static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, long long rows, int act, const float* res, int ldr,
                      const float* rowadd, int period, int ldra, cudaStream_t st) {
   LinearArgs a;
   a.X = X, a.ldx = ldx, a.W = L.w, a.bias = L.b, a.Y = Y, a.ldy = ldy, a.res = res, a.ldr = ldr;
   a.rowadd = rowadd, a.rowadd_period = period > 0 ? period : 1, a.ldra = ldra;
-  a.rows = (int)rows, a.N = L.out, a.K = L.in, a.gelu = gelu ? 1 : 0;
+  a.rows = (int)rows, a.N = L.out, a.K = L.in, a.gelu = act;
   static const bool legacy_fs = env_flag("LAMSLIDE_LEGACY_FS_LINEAR");
   const bool vec_ok = !legacy_fs && L.in % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)L.w & 15) == 0;
   static const bool no_tc = env_flag("LAMSLIDE_FS_NO_TF32X3");

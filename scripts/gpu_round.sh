@@ -1,25 +1,25 @@
 #!/bin/bash
-# One scripted GPU session: parity tests -> bench -> ncu launch list -> ncu full capture of the top kernels.
+# One scripted GPU session that regenerates the evidence under profiles/ from the commit it runs on:
+#   parity tests -> bench line -> ncu launch list of one step -> ncu --set full of the top kernels -> traffic.json
+# Usage (dev container): gpurun --timeout 3000 -- 'TAG=r02 bash scripts/gpu_round.sh'   then   python scripts/collect_profiles.py r02
+TAG=${TAG:-r02}
 mkdir -p gpurun_out
 LOG=gpurun_out/round.log
 : > $LOG
-echo "######## diag sample" >> $LOG
-timeout 600 python scripts/gpu_diag.py sample >> $LOG 2>&1
 echo "######## pytest -m gpu" >> $LOG
-timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 >> $LOG
+timeout 2400 python -m pytest tests -q -m gpu --tb=short 2>&1 | grep -E "^E  |passed|failed|FAILED|Error|skipped" | cut -c1-260 | head -40 >> $LOG
 echo "######## bench" >> $LOG
-timeout 900 python bench.py $BENCH_ARGS > gpurun_out/bench.json 2> gpurun_out/bench.err
-cat gpurun_out/bench.json >> $LOG; tail -5 gpurun_out/bench.err >> $LOG
-if [ -z "$SKIP_NCU" ]; then
-echo "######## ncu launch list" >> $LOG
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/ncu_bench.log 2>&1
-tail -2 gpurun_out/ncu_bench.log >> $LOG
-wc -l gpurun_out/launches.csv >> $LOG
-echo "######## ncu full: linear1 / linear2 / attention" >> $LOG
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_ws_kernel|mlp_fused_kernel|attn_seq_kernel|attn_rows_kernel|ln_modulate_kernel|linear_f32_v2_kernel' -s 120 -c 14 -f -o gpurun_out/prof_top \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_full.log >> $LOG
-ls -la gpurun_out >> $LOG
-fi
-tail -60 $LOG
+timeout 1500 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+tail -3 gpurun_out/${TAG}_bench.err >> $LOG
+echo "######## ncu launch list (one step)" >> $LOG
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-secondary > gpurun_out/ncu_bench.log 2>&1
+tail -2 gpurun_out/ncu_bench.log | cut -c1-200 >> $LOG
+wc -l gpurun_out/${TAG}_launches.csv >> $LOG
+echo "######## ncu --set full: top kernels" >> $LOG
+timeout 1200 ncu --set full --clock-control none --import-source on \
+  -k regex:'attn_tc_kernel|mlp_fused_kernel|gemm_ws_kernel|ln_modulate_kernel|linear_f32_tc_kernel' -s 150 -c 16 -f -o gpurun_out/${TAG}_top \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-secondary > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log | cut -c1-200 >> $LOG
+ls -la gpurun_out | grep ${TAG} >> $LOG
+tail -40 $LOG

@@ -34,5 +34,11 @@ def max_rel(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
+def mean_rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    """mean |a-b| / mean |b| — bounds the error where the reference is small too (a localized error in a low-magnitude region does
+    not move max_rel, which is normalised by the largest reference value)."""
+    return float((a.double() - b.double()).abs().mean() / b.double().abs().mean().clamp_min(1e-30))
+
+
 def rmsd(a: torch.Tensor, b: torch.Tensor) -> float:
     return float(((a.double() - b.double()) ** 2).mean().sqrt())

@@ -8,11 +8,12 @@ import pytest
 import torch
 
 from oracle import lamslide_oracle as O
-from tests.helpers import CASE_BY_NAME, case_inputs, check_inputs_match_fixture, frame_slice, load_golden, max_rel, rmsd
+from tests.helpers import CASE_BY_NAME, case_inputs, check_inputs_match_fixture, frame_slice, load_golden, max_rel, mean_rel, rmsd
 
 pytestmark = pytest.mark.gpu
 
-VEL_TOL = 1e-2
+VEL_TOL = 1e-2        # max |err| / max |ref|  (north_star: "per-step velocity max relative error <= 1e-2 in bf16")
+VEL_MEAN_TOL = 5e-3   # mean |err| / mean |ref|: the same contract where the reference is small
 RMSD_TOL = 1e-3
 FS_TOL = 1e-4
 
@@ -110,12 +111,14 @@ def test_sample_vs_reference_golden(name):
     yy = None if y is None else y.cuda()
     out0 = m.backbone(noise.cuda(), torch.full((B,), t0).cuda(), x_cond, x_mask, yy)
     assert max_rel(out0.cpu()[:, sl], fx["net_out_t0"]) < VEL_TOL
+    assert mean_rel(out0.cpu()[:, sl], fx["net_out_t0"]) < VEL_MEAN_TOL
     # fused ODE with velocity recording
     states, vel = m.backbone.ode_sample(noise.cuda(), x_cond, x_mask, yy, path_type=cfg["path_type"], prediction=cfg["prediction"],
                                         num_steps=c["num_steps"], return_velocities=True)
     vel = vel.cpu()[fx["velocity_steps"]][:, :, sl]
     for i in range(vel.shape[0]):
         assert max_rel(vel[i], fx["velocities"][i]) < VEL_TOL, f"velocity step {fx['velocity_steps'][i]}"
+        assert mean_rel(vel[i], fx["velocities"][i]) < VEL_MEAN_TOL, f"velocity step {fx['velocity_steps'][i]} (mean)"
     assert max_rel(states[-1].cpu()[:, sl], fx["final_latents"]) < VEL_TOL
     out = m.first_stage_model.decode(states[-1].flatten(0, 1), cb["entities"].flatten(0, 1))
     main = cfg["main_output"]

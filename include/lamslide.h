@@ -228,6 +228,21 @@ int lamslide_debug_fused_mlp(const void* u_bf16, const void* act_bf16, const voi
                              const float* b2, const float* gate, float* h, int32_t rows, int32_t H, int32_t M,
                              int32_t rows_per_sample, void* stream);
 
+/* the same kernel with the drain that also applies the NEXT block's pre-norm + modulate (latent_si_v31.py:50,57) to the rows it has
+ * just updated: u_out [rows,H] bf16 = LayerNorm(h_new) * (1 + ln_scale[b]) + ln_shift[b]  (no affine, eps 1e-6; ln_shift / ln_scale
+ * [n_samples,H] device fp32; u_out may be the buffer u_bf16 points to). */
+int lamslide_debug_fused_mlp_ln(const void* u_bf16, const void* act_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1,
+                                const float* b2, const float* gate, float* h, int32_t rows, int32_t H, int32_t M,
+                                int32_t rows_per_sample, const float* ln_shift, const float* ln_scale, void* u_out, void* stream);
+
+/* one linear layer of the first stage in isolation: y [rows, N] (pitch ldy) = epi(x [rows, K] (pitch ldx) . w^T + bias), with the
+ * epilogue options of the first-stage layers (act: 0 none, 1 erf-GELU, 2 SiLU of the sum; + rowadd[row % period] ; + res).
+ * w [N, K] and bias [N] are HOST fp32 (packed as lamslide_first_stage_create packs them), the rest device fp32.
+ * path: 0 = the kernel the product picks for this shape (tcgen05 3xTF32 when K % 4 == 0), 1 = the mma.sync / FMA kernels. */
+int lamslide_debug_fs_linear(const float* x, const float* w_host, const float* bias_host, float* y, int32_t rows, int32_t N, int32_t K,
+                             int32_t ldx, int32_t ldy, int32_t act, const float* res, int32_t ldr, const float* rowadd, int32_t period,
+                             int32_t ldra, int32_t path, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@
 #include "attn_tc.cuh"
 #include "elementwise.cuh"
 #include "first_stage.cuh"
+#include "linear_tc5.cuh"
 
 using namespace lam;
 
@@ -186,6 +187,20 @@ static int make_tmap_ex(CUtensorMap* map, const void* ptr, CUtensorMapDataType d
   CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)r);
+  return 0;
+}
+// row-major fp32 [rows, cols] with a row pitch of `ld` floats, tile box_rows x 32 columns (128 bytes), 128-byte swizzle: the
+// kind::tf32 operands of linear_tc5.cuh.  Columns / rows past the tensor are zero-filled by the TMA.
+static int make_tmap_f32(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  auto enc = get_tmap_encoder();
+  if (!enc) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAMSLIDE_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 operand) failed with CUresult %d", (int)r);
   return 0;
 }
 // A/B switches and profiling aids read from the environment exist only in debug builds (-DLAMSLIDE_DEBUG_KNOBS, see
@@ -658,7 +673,7 @@ static bool fused_mlp_ok(int H, int M) {
   return fused_mlp_stages(H, M, &a, &b);
 }
 static int launch_fused_mlp(const CUtensorMap& tm_u, const CUtensorMap& tm_attn, const CUtensorMap& tm_w1u, const CUtensorMap& tm_w2u,
-                            const CUtensorMap& tm_h, int rows, const FusedMlpParams& p_in, cudaStream_t st) {
+                            const CUtensorMap& tm_h, const CUtensorMap& tm_u_st, int rows, const FusedMlpParams& p_in, cudaStream_t st) {
   int s1 = 0, s2 = 0;
   if (!fused_mlp_stages(p_in.H, p_in.M, &s1, &s2)) return 1;
   FusedMlpParams p = p_in;
@@ -681,7 +696,7 @@ static int launch_fused_mlp(const CUtensorMap& tm_u, const CUtensorMap& tm_attn,
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, mlp_fused_kernel, tm_u, tm_attn, tm_w1u, tm_w2u, tm_h, mblocks, s1, s2, p));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, mlp_fused_kernel, tm_u, tm_attn, tm_w1u, tm_w2u, tm_h, tm_u_st, mblocks, s1, s2, p));
   LAUNCH_CHECK();
   return 0;
 }
@@ -812,6 +827,10 @@ static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, 
 struct LinW {
   float *w = nullptr, *b = nullptr;
   int out = 0, in = 0;
+  // tcgen05 3xTF32 path (linear_tc5.cuh): TF32 head / remainder of the weight and their TMA descriptors; bn = 0: not prepared
+  float *w_hi = nullptr, *w_lo = nullptr;
+  CUtensorMap tm_hi, tm_lo;
+  int bn = 0;
 };
 static int vector_path(const lamslide_backbone* bb, const BackboneWorkspace& w, const float* t_all, const float* y, int B, int n,
                        cudaStream_t st) {
@@ -842,6 +861,7 @@ static int vector_path(const lamslide_backbone* bb, const BackboneWorkspace& w, 
 struct ForwardCtx {
   BackboneWorkspace ws;
   CUtensorMap tm_u, tm_act, tm_u3;
+  CUtensorMap tm_u_st;                          // bf16 store of the fused MLP drain's LN + modulate output (16-column x 32-row boxes)
   CUtensorMap tm_h_red;                         // f32 reduce-add of the linear2 epilogue (16-column x 32-row boxes)
   CUtensorMap tm_qkv_st, tm_act_st;             // linear1 epilogue: dense {2 hd, 32} bf16 boxes (hd = 24: paired heads, 96-byte rows)
   CUtensorMap tm_emb_a;                         // [n, 6D] split input-embedding operand (lives in the act buffer)
@@ -864,6 +884,7 @@ static int forward_prepare(lamslide_backbone* bb, ForwardCtx& fc, int B, int T, 
                    CU_TENSOR_MAP_SWIZZLE_NONE));
   if (bb->w_emb) TRY(make_tmap(&fc.tm_emb_a, fc.ws.act, (uint64_t)n, 6 * bb->D, kBlockM));
   TRY(make_tmap_ex(&fc.tm_h_red, fc.ws.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)n, bb->H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  TRY(make_tmap_ex(&fc.tm_u_st, fc.ws.u, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)n, bb->H, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
   const int half = bb->hd / 2;
   rope_table_kernel<<<cdiv(L * half, 256), 256, 0, st>>>(fc.ws.cos_s, fc.ws.sin_s, L, half, (double)bb->cfg.theta);
   LAUNCH_CHECK();
@@ -928,14 +949,18 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
   // spatial attention over L <= 8 latents inside the linear1 epilogue (needs the fused-MLP path: linear1 computes q | k | v only)
   static const bool no_fuse_spatial = env_flag("LAMSLIDE_NO_FUSED_SPATIAL_ATTN");
   const bool fuse_spatial = fused && !no_fuse_spatial;
+  static const bool no_fuse_ln = env_flag("LAMSLIDE_NO_FUSED_LN");
+  const bool fuse_ln = fused && !no_fuse_ln;
+  bool u_ready = false;  // w.u already holds LN + modulate of the current h for this block (written by the previous block's drain)
   for (int i = 0; i < bb->depth; ++i) {
     for (int s = 0; s < 2; ++s) {
       const BlockWeights& bw = bb->blocks[2 * i + s];
       const float* modl = mod + (size_t)i * 6 * H + (size_t)s * 3 * H;  // shift | scale | gate
-      {
+      if (!u_ready) {
         ProfScope ps(PC_LNMOD, st);
         TRY(ln_modulate(bb, w.h, w.u, modl, modl + H, n, T * L, st));
       }
+      u_ready = false;
       SeqMap sm;
       int n_seq;
       const float *cs, *sn;
@@ -991,9 +1016,15 @@ static int forward_run(lamslide_backbone* bb, ForwardCtx& fc, const float* x, co
         ProfScope ps(PC_LINEAR2, st);
         int r2 = 1;
         if (fused) {
-          FusedMlpParams fp{bw.b1 + 3 * H, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, M, n, nullptr, 0};
-          r2 = launch_fused_mlp(fc.tm_u, fc.tm_act, bw.tm_w1_u, bw.tm_w2_u, fc.tm_h_red, n, fp, st);
+          FusedMlpParams fp{bw.b1 + 3 * H, bw.b2, modl + 2 * H, bb->mod_width, T * L, H, M, n, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+          const bool last_block = i == bb->depth - 1 && s == 1;
+          if (fuse_ln && !last_block) {  // the drain also writes the next block's LN + modulate input
+            const float* modn = s == 0 ? modl + 3 * H : mod + (size_t)(i + 1) * 6 * H;
+            fp.h = w.h, fp.u_out = w.u, fp.ln_shift = modn, fp.ln_scale = modn + H;
+          }
+          r2 = launch_fused_mlp(fc.tm_u, fc.tm_act, bw.tm_w1_u, bw.tm_w2_u, fc.tm_h_red, fc.tm_u_st, n, fp, st);
           if (r2 < 0) return r2;
+          u_ready = r2 == 0 && fp.ln_scale != nullptr;
         } else if (!legacy_gemm) {
           EpiLinear2Ws::Params e2w{bw.b2, modl + 2 * H, bb->mod_width, T * L, H, n};
           r2 = launch_linear2_ws(bb, fc.tm_act, bw, fc.tm_h_red, n, e2w, st);
@@ -1255,6 +1286,32 @@ struct lamslide_first_stage {
   std::vector<LinW> head0, head2;
 };
 
+// tile width of the tcgen05 linear kernel for an N-wide layer (a function of the layer shape only)
+static int tc5_bn(int N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 96) return 96;
+  if (N <= 128) return 128;
+  if (N <= 192 || N % 192 == 0) return 192;
+  return 256;
+}
+// split a host weight [out, in] into its TF32 head and remainder, upload both and describe them to the TMA
+static int prepare_tc5(Arena& A, const float* host_w, LinW* L) {
+  if (L->in % 4 != 0 || L->in < 4) return 0;  // TMA row pitch must be a multiple of 16 bytes: such layers stay on the legacy kernels
+  const size_t n = (size_t)L->out * L->in;
+  std::vector<float> hi(n), lo(n);
+  for (size_t i = 0; i < n; ++i) {
+    hi[i] = tf32_head(host_w[i]);
+    lo[i] = host_w[i] - hi[i];
+  }
+  TRY(A.upload_f32(hi.data(), n, &L->w_hi));
+  TRY(A.upload_f32(lo.data(), n, &L->w_lo));
+  L->bn = tc5_bn(L->out);
+  TRY(make_tmap_f32(&L->tm_hi, L->w_hi, L->out, L->in, L->in, L->bn));
+  TRY(make_tmap_f32(&L->tm_lo, L->w_lo, L->out, L->in, L->in, L->bn));
+  return 0;
+}
+
 struct FsLoader {
   StateDict sd;
   Arena& A;
@@ -1269,7 +1326,7 @@ struct FsLoader {
       TRY(A.upload_f32(b->data, out, &L->b));
     }
     L->out = out, L->in = in;
-    return 0;
+    return prepare_tc5(A, w->data, L);
   }
   int ln(const std::string& p, int dim, LNW* n) {
     const lamslide_tensor* w = sd.get(p + ".weight", {dim});
@@ -1386,6 +1443,7 @@ extern "C" int lamslide_first_stage_create(const lamslide_first_stage_config* cf
     TRY(fs->arena.upload_f32(wp.data(), wp.size(), &fs->merge0.w));
     TRY(fs->arena.upload_f32(b->data, Din, &fs->merge0.b));
     fs->merge0.out = Din, fs->merge0.in = fs->feat_dim;
+    TRY(prepare_tc5(fs->arena, wp.data(), &fs->merge0));
   }
   TRY(ld.lin("net_merge.2", Din, Din, true, &fs->merge2));
   TRY(ld.lin("encoder.mlp.0", D, C, true, &fs->enc_mlp0));
@@ -1434,6 +1492,7 @@ extern "C" int lamslide_first_stage_create(const lamslide_first_stage_config* cf
     TRY(fs->arena.upload_f32(wp.data(), wp.size(), &fs->extender.w));
     TRY(fs->arena.upload_f32(bp.data(), bp.size(), &fs->extender.b));
     fs->extender.out = D * n, fs->extender.in = D;
+    TRY(prepare_tc5(fs->arena, wp.data(), &fs->extender));
   }
   *out = guard.release();
   return 0;
@@ -1453,6 +1512,7 @@ struct Bump {
   }
 };
 
+static int launch_linear_tc5(const LinW& L, const LinearArgs& a, cudaStream_t st);
 // act: 0 none, 1 erf-GELU (before the adds), 2 SiLU of the sum (after the adds)
 static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, long long rows, int act, const float* res, int ldr,
                      const float* rowadd, int period, int ldra, cudaStream_t st) {
@@ -1462,6 +1522,8 @@ static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, 
   a.rows = (int)rows, a.N = L.out, a.K = L.in, a.gelu = act;
   static const bool legacy_fs = env_flag("LAMSLIDE_LEGACY_FS_LINEAR");
   const bool vec_ok = !legacy_fs && L.in % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)L.w & 15) == 0;
+  static const bool no_tc5 = env_flag("LAMSLIDE_FS_NO_TCGEN05");
+  if (L.bn && !legacy_fs && !no_tc5 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0) return launch_linear_tc5(L, a, st);
   static const bool no_tc = env_flag("LAMSLIDE_FS_NO_TF32X3");
   // the kernel is chosen by the layer's shape only, never by the row count: a trajectory must decode to the same bits whether it is
   // sampled alone, in a batch of 64 or as a shard of a multi-GPU run
@@ -1478,6 +1540,31 @@ static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, 
   }
   LAUNCH_CHECK();
   return 0;
+}
+template <int BN>
+static int launch_linear_tc5_bn(const LinW& L, const LinearArgs& a, cudaStream_t st) {
+  using C = L5Cfg<BN>;
+  auto kern = linear_tc5_kernel<BN>;
+  TRY(ensure_dynamic_smem((const void*)kern, C::kSmem));
+  CUtensorMap ta;
+  TRY(make_tmap_f32(&ta, a.X, (uint64_t)a.rows, (uint64_t)a.K, (uint64_t)a.ldx, 128));
+  const int m_tiles = cdiv(a.rows, 128), n_tiles = cdiv(a.N, BN);
+  const int grid = std::min(m_tiles * n_tiles, num_sms());
+  kern<<<grid, kL5Threads, C::kSmem, st>>>(ta, L.tm_hi, L.tm_lo, a, m_tiles, n_tiles);
+  LAUNCH_CHECK();
+  COUNT_KERNEL("linear_tc5");
+  return 0;
+}
+static int launch_linear_tc5(const LinW& L, const LinearArgs& a, cudaStream_t st) {
+  switch (L.bn) {
+    case 32: return launch_linear_tc5_bn<32>(L, a, st);
+    case 64: return launch_linear_tc5_bn<64>(L, a, st);
+    case 96: return launch_linear_tc5_bn<96>(L, a, st);
+    case 128: return launch_linear_tc5_bn<128>(L, a, st);
+    case 192: return launch_linear_tc5_bn<192>(L, a, st);
+    case 256: return launch_linear_tc5_bn<256>(L, a, st);
+  }
+  return fail(LAMSLIDE_ERR_INVALID, "linear_tc5: no kernel for tile width %d", L.bn);
 }
 static int fs_layernorm(const float* x, int ldx, int period, float* y, int ldy, const LNW* n, long long rows, int dim, float eps,
                         cudaStream_t st) {
@@ -1693,6 +1780,21 @@ extern "C" int lamslide_decode(lamslide_first_stage* h, const float* latents, co
   TRY(fs_check(h, frames, N, workspace, workspace_bytes));
   ProfScope ps(PC_DECODE, (cudaStream_t)stream);
   return decode_impl(h, latents, entities, outs, frames, N, workspace, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int lamslide_debug_fs_linear(const float* x, const float* w_host, const float* bias_host, float* y, int32_t rows, int32_t N,
+                                        int32_t K, int32_t ldx, int32_t ldy, int32_t act, const float* res, int32_t ldr,
+                                        const float* rowadd, int32_t period, int32_t ldra, int32_t path, void* stream) {
+  if (!x || !w_host || !y || rows <= 0 || N <= 0 || K <= 0) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  Arena arena;
+  LinW L;
+  TRY(arena.upload_f32(w_host, (size_t)N * K, &L.w));
+  if (bias_host) TRY(arena.upload_f32(bias_host, N, &L.b));
+  L.out = N, L.in = K;
+  if (path == 0) TRY(prepare_tc5(arena, w_host, &L));
+  TRY(fs_linear(L, x, ldx, y, ldy, rows, act, res, ldr, rowadd, period, ldra, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));  // the weights die with `arena`
+  return 0;
 }
 
 // ================================================================================================ misc + test hooks
@@ -1933,18 +2035,34 @@ extern "C" int lamslide_debug_gemm_mainloop(const void* a_bf16, const void* b_bf
 
 // fused MLP half + linear2 + gated residual in isolation (tests/test_gpu_kernels.py):  h += gate[b] * ([attn | gelu(u W1m^T + b1m)] W2^T + b2)
 // u [rows,H] bf16, act [rows,H+M] bf16 (only the attention half [:, :H] is read), w1 [3H+M,H] bf16, w2 [H,H+M] bf16, b1 [3H+M], b2 [H].
-extern "C" int lamslide_debug_fused_mlp(const void* u_bf16, const void* act_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1,
-                                        const float* b2, const float* gate, float* h, int32_t rows, int32_t H, int32_t M,
-                                        int32_t rows_per_sample, void* stream) {
+static int debug_fused_mlp(const void* u_bf16, const void* act_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1,
+                           const float* b2, const float* gate, float* h, int32_t rows, int32_t H, int32_t M, int32_t rows_per_sample,
+                           const float* ln_shift, const float* ln_scale, void* u_out, void* stream) {
   if (!u_bf16 || !act_bf16 || !w1_bf16 || !w2_bf16 || !b1 || !b2 || !gate || !h) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
-  CUtensorMap tu, ta, tw1, tw2, th;
+  CUtensorMap tu, ta, tw1, tw2, th, tus;
+  TRY(make_tmap_ex(&tus, u_out ? u_out : u_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, H, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B));
   TRY(make_tmap(&tu, u_bf16, rows, H, kBlockM));
   TRY(make_tmap(&ta, act_bf16, rows, H + M, kBlockM));
   TRY(make_tmap(&tw1, w1_bf16, 3 * H + M, H, 64));
   TRY(make_tmap(&tw2, w2_bf16, H, H + M, fused_mlp_out_unit(H) / 2));
   TRY(make_tmap_ex(&th, h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, H, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-  FusedMlpParams fp{b1 + 3 * H, b2, gate, H, rows_per_sample, H, M, rows, nullptr, 0};
-  int rc = launch_fused_mlp(tu, ta, tw1, tw2, th, rows, fp, (cudaStream_t)stream);
+  FusedMlpParams fp{b1 + 3 * H, b2, gate, H, rows_per_sample, H, M, rows, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  if (ln_scale) fp.h = h, fp.u_out = (__nv_bfloat16*)u_out, fp.ln_shift = ln_shift, fp.ln_scale = ln_scale;
+  int rc = launch_fused_mlp(tu, ta, tw1, tw2, th, tus, rows, fp, (cudaStream_t)stream);
   if (rc == 1) return fail(LAMSLIDE_ERR_INVALID, "fused MLP kernel does not cover H %d M %d", H, M);
   return rc;
+}
+extern "C" int lamslide_debug_fused_mlp(const void* u_bf16, const void* act_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1,
+                                        const float* b2, const float* gate, float* h, int32_t rows, int32_t H, int32_t M,
+                                        int32_t rows_per_sample, void* stream) {
+  return debug_fused_mlp(u_bf16, act_bf16, w1_bf16, w2_bf16, b1, b2, gate, h, rows, H, M, rows_per_sample, nullptr, nullptr, nullptr, stream);
+}
+// same with the drain that also writes the next block's LN + modulate input: u_out [rows, H] bf16 = LN(h_new) * (1 + scale[b]) + shift[b]
+// (shift, scale: [n_samples, H] device fp32; u_out may alias u_bf16)
+extern "C" int lamslide_debug_fused_mlp_ln(const void* u_bf16, const void* act_bf16, const void* w1_bf16, const void* w2_bf16,
+                                           const float* b1, const float* b2, const float* gate, float* h, int32_t rows, int32_t H,
+                                           int32_t M, int32_t rows_per_sample, const float* ln_shift, const float* ln_scale, void* u_out,
+                                           void* stream) {
+  if (!ln_shift || !ln_scale || !u_out) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  return debug_fused_mlp(u_bf16, act_bf16, w1_bf16, w2_bf16, b1, b2, gate, h, rows, H, M, rows_per_sample, ln_shift, ln_scale, u_out, stream);
 }

@@ -49,6 +49,14 @@ struct FusedMlpParams {
   int gate_stride;
   int rows_per_sample;  // T * L
   int H, M, rows;
+  // LN mode (ln_scale != nullptr): the drain also applies the NEXT block's pre-norm + modulate (latent_si_v31.py:50,57:
+  // u = LayerNorm(h) * (1 + scale) + shift, no affine, eps 1e-6) to the rows it has just updated and writes them to u_out as bf16 —
+  // the rows' new residual values are in registers anyway, which deletes one ln_modulate launch (a 270 MB pass over h and u) per block.
+  // h is then updated with plain loads / stores of the rows (each thread owns its row x column quarter) instead of TMA reduce-adds.
+  float* h;                  // [rows, H] residual stream
+  __nv_bfloat16* u_out;      // [rows, H]; may be the buffer tmap_u reads (an m-block's u tile is in shared memory long before its drain)
+  const float* ln_shift;     // shift / scale of sample b at + b * gate_stride, [H] each
+  const float* ln_scale;
   long long* trace;  // profiling aid: when set, CTA 0 records (tag << 48 | clock) events, 4096 slots per role (see TRACE below)
   int debug;  // profiling aid: 1 skip the GELU math, 2 skip the output reduce-add, 4 skip the G tile writes, 8 skip the weight TMA loads
 };
@@ -57,7 +65,7 @@ struct FusedMlpParams {
 static inline __host__ __device__ int fused_mlp_out_unit(int H) { return H % 192 == 0 && H > 256 ? 192 : (H <= 256 ? H : 128); }
 
 struct FusedMlpSmem {
-  int u_bytes, g_bytes, ring1_bytes, ring2_bytes, const_bytes, bar_bytes, total;
+  int u_bytes, g_bytes, ring1_bytes, ring2_bytes, const_bytes, bar_bytes, stat_bytes, total;
 };
 static inline __host__ __device__ FusedMlpSmem fused_mlp_smem(int H, int M, int stages1, int stages2) {
   FusedMlpSmem s;
@@ -67,7 +75,8 @@ static inline __host__ __device__ FusedMlpSmem fused_mlp_smem(int H, int M, int 
   s.ring2_bytes = (stages2 * fused_mlp_out_unit(H) * 64 + 1023) / 1024 * 1024;
   s.const_bytes = ((M + 3 * H) * 4 + 15) / 16 * 16;  // b1m | b2 | gate rows of two samples
   s.bar_bytes = 512;
-  s.total = s.u_bytes + s.g_bytes + s.ring1_bytes + s.ring2_bytes + s.const_bytes + s.bar_bytes;
+  s.stat_bytes = 4096;  // LN mode: (mean, M2) of [4 column quarters][128 rows]
+  s.total = s.u_bytes + s.g_bytes + s.ring1_bytes + s.ring2_bytes + s.const_bytes + s.bar_bytes + s.stat_bytes;
   return s;
 }
 
@@ -77,7 +86,8 @@ __device__ __forceinline__ uint32_t stage_off32(int r, int c) { return r * 32 + 
 __global__ void __launch_bounds__(kFusedThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_attn,
                  const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
-                 const __grid_constant__ CUtensorMap tmap_h, int num_m_blocks, int stages1, int stages2, FusedMlpParams p) {
+                 const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_u_st, int num_m_blocks, int stages1,
+                 int stages2, FusedMlpParams p) {
   constexpr int kTile = 16384;   // one [128 x 64] bf16 tile (u k-block, G tile, attention tile) = one ring-1 stage
   constexpr int kUnit1 = 16384;  // this CTA's half of a W1m unit: [64 rows x 128 k] as two 128-byte-swizzled [64 x 64] boxes
   const int H = p.H, M = p.M;
@@ -373,7 +383,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
     const uint32_t gg_full_l = mapa_u32(smem_u32(&gg_full[kk]), 0);
     const int etid = threadIdx.x - 128;
     const int b_max = (p.rows - 1) / p.rows_per_sample;
-    uint32_t it = 0, n_chunk = 0;
+    uint32_t it = 0, n_chunk = 0, n_hload = 0;
     for (int mbase = m_first; mbase < num_m_blocks; mbase += m_step, ++it) {
       const int m0 = (mbase + cta_rank) * kBlockM;
       const int row0 = m0 + q * 32;
@@ -382,6 +392,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
       // barrier also orders the previous m-block's staging boxes (each warp has waited for its own TMA reads) before G is rewritten.
       const int b0 = (m0 < p.rows ? m0 : p.rows - 1) / p.rows_per_sample;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kWsEpiWarps) : "memory");
+      if (p.ln_scale && elect_one()) {  // LN mode: this warp's h boxes of the m-block -> L2, a whole m-block ahead of the drain that reads them
+        for (int bx = 0; bx < H / 64; ++bx) tma_prefetch_2d(&tmap_h, cq * (H / 4) + bx * 16, row0);
+      }
+      __syncwarp();
       for (int i = etid; i < 2 * H; i += 32 * kWsEpiWarps) {
         const int bb = b0 + (i >= H ? 1 : 0);
         smf[M + H + i] = p.gate[(size_t)(bb < b_max ? bb : b_max) * p.gate_stride + (i >= H ? i - H : i)];
@@ -429,57 +443,184 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(gg_full_l);
       }
-      // ---- OUT: h += gate * (acc + b2) as TMA f32 reduce-add boxes of 16 columns x 32 rows, one staging box per warp in G
-      // (free once out_full fired: every MMA that reads G has completed)
-      if (warp == 4) TRACE(0, 5);
-      mbar_wait(out_full, it & 1);
-      tcgen05_fence_after();
-      if (warp == 4) TRACE(0, 6);
-      const int b = (row < p.rows ? row : p.rows - 1) / p.rows_per_sample;
-      const bool gate_in_smem = b - b0 <= 1;
-      const uint32_t gate_s = smf_s + (M + H + (b - b0) * H) * 4;
-      const float* gate_g = p.gate + (size_t)b * p.gate_stride;
-      const int wcols = H / 4;  // this warp's output columns
-      const uint32_t stage_s = g_s + (warp - 4) * 2048;
-      const int col0 = cq * wcols;
-      const bool issuer = elect_one();  // TMA issue, commit and wait all by the same (elected) lane
-      uint32_t v[16];
-      tmem_ld16(lane_t + col0, v);
-      for (int bx = 0; bx < wcols / 16; ++bx) {
-        const int col = col0 + bx * 16;
-        tmem_ld_wait();
-        float4 o[4];
-#pragma unroll
-        for (int jx = 0; jx < 4; ++jx) {
-          const float4 gv = gate_in_smem ? ld_shared_f4(gate_s + col * 4 + jx * 16) : __ldg(reinterpret_cast<const float4*>(gate_g + col) + jx);
-          const float4 bv = ld_shared_f4(smf_s + (M + col) * 4 + jx * 16);
-          o[jx].x = gv.x * (__uint_as_float(v[4 * jx + 0]) + bv.x);
-          o[jx].y = gv.y * (__uint_as_float(v[4 * jx + 1]) + bv.y);
-          o[jx].z = gv.z * (__uint_as_float(v[4 * jx + 2]) + bv.z);
-          o[jx].w = gv.w * (__uint_as_float(v[4 * jx + 3]) + bv.w);
+      if (p.ln_scale) {
+        // ---- OUT, LN mode: thread = (row, column quarter).  Pass 1, per 16-column box: the h box (prefetched into L2 at the top of the
+        // m-block) arrives by TMA in the warp's staging box, new h = h + gate * (acc + b2) leaves through the same box as a plain TMA
+        // store and goes back into the OUT columns of TMEM; shifted one-pass statistics of the thread's columns.  The four quarters
+        // of a row merge their (mean, M2) through shared memory.  Pass 2: u = (h - mean) rstd (1 + scale) + shift -> bf16 -> 1 KB
+        // boxes -> TMA store.  Measured (4AA, B200): 348 us per launch against 280 us for the reduce-add drain + 67 us for the
+        // ln_modulate launch it replaces — time-neutral (the drain sits on the epilogue warps' critical path and only 32 KB of staging
+        // are left, i.e. 6 serial load -> add -> store rounds per warp), 270 MB less HBM traffic per block.  Variants: rows read and
+        // written with 64-byte-per-thread global accesses 435 us (LSU-bound); TMA load + coalesced st.global through the box 358 us;
+        // without the L2 prefetch and with per-thread u stores 361 us.
+        const int wcols = H / 4, nb = wcols / 16, col0 = cq * wcols;
+        const bool row_ok = row < p.rows;
+        const uint32_t stage_s = g_s + (warp - 4) * 2048;
+        const int e = warp - 4;  // this warp's TMA-load barrier: one of the never-used slots of the ring barrier arrays
+        uint64_t* hbar = e < 4 ? &full1[4 + e] : e < 8 ? &empty1[e] : e < 10 ? &full2[e - 2] : e < 12 ? &empty2[e - 4] : e < 14 ? &a_full[e - 6] : &a_empty[e - 8];
+        const bool issuer = elect_one();
+        if (warp == 4) TRACE(0, 5);
+        mbar_wait(out_full, it & 1);  // also: every MMA that reads G has completed, the staging boxes are free
+        tcgen05_fence_after();
+        if (warp == 4) TRACE(0, 6);
+        if (issuer) {
+          mbar_arrive_expect_tx(hbar, 2048);
+          tma_load_2d(&tmap_h, hbar, g_buf + (warp - 4) * 2048, col0, row0);
         }
-        if (bx + 1 < wcols / 16) {  // next 16 columns: TMEM load in flight while these are staged and stored
-          tmem_ld16(lane_t + col + 16, v);
-        } else {  // OUT is in registers: the next m-block's first MMAs may overwrite it
-          tcgen05_fence_before();
+        const int b = (row_ok ? row : p.rows - 1) / p.rows_per_sample;
+        const bool gate_in_smem = b - b0 <= 1;
+        const uint32_t gate_s = smf_s + (M + H + (b - b0) * H) * 4;
+        const float* gate_g = p.gate + (size_t)b * p.gate_stride;
+        uint32_t v[16];
+        tmem_ld16(lane_t + col0, v);
+        float kshift = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int bx = 0; bx < nb; ++bx, ++n_hload) {
+          const int col = col0 + bx * 16;
+          tmem_ld_wait();
+          mbar_wait(hbar, n_hload & 1);
+          uint32_t nv[16];
+#pragma unroll
+          for (int jx = 0; jx < 4; ++jx) {
+            const float4 gv = gate_in_smem ? ld_shared_f4(gate_s + col * 4 + jx * 16) : __ldg(reinterpret_cast<const float4*>(gate_g + col) + jx);
+            const float4 bv = ld_shared_f4(smf_s + (M + col) * 4 + jx * 16);
+            const float4 hv = ld_shared_f4(stage_s + stage_off64(lane, jx));
+            float4 o;
+            o.x = fmaf(gv.x, __uint_as_float(v[4 * jx + 0]) + bv.x, hv.x);
+            o.y = fmaf(gv.y, __uint_as_float(v[4 * jx + 1]) + bv.y, hv.y);
+            o.z = fmaf(gv.z, __uint_as_float(v[4 * jx + 2]) + bv.z, hv.z);
+            o.w = fmaf(gv.w, __uint_as_float(v[4 * jx + 3]) + bv.w, hv.w);
+            if (bx == 0 && jx == 0) kshift = o.x;
+            const float d0 = o.x - kshift, d1 = o.y - kshift, d2 = o.z - kshift, d3 = o.w - kshift;
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 = fmaf(d0, d0, s2), s2 = fmaf(d1, d1, s2), s2 = fmaf(d2, d2, s2), s2 = fmaf(d3, d3, s2);
+            st_shared_v4(stage_s + stage_off64(lane, jx), __float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w));
+            nv[4 * jx + 0] = __float_as_uint(o.x), nv[4 * jx + 1] = __float_as_uint(o.y);
+            nv[4 * jx + 2] = __float_as_uint(o.z), nv[4 * jx + 3] = __float_as_uint(o.w);
+          }
+          fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(out_free_l);
+          if (issuer && !(p.debug & 2)) {
+            tma_store_2d_s(&tmap_h, stage_s, col, row0);
+            bulk_commit();
+          }
+          tmem_st16(lane_t + col, nv);
+          if (bx + 1 < nb) tmem_ld16(lane_t + col + 16, v);
+          if (issuer) {
+            bulk_wait_read<0>();  // the store has read the box: the next load (or the u boxes of pass 2) may overwrite it
+            if (bx + 1 < nb) {
+              mbar_arrive_expect_tx(hbar, 2048);
+              tma_load_2d(&tmap_h, hbar, g_buf + (warp - 4) * 2048, col + 16, row0);
+            }
+          }
+          __syncwarp();
         }
-        if (issuer) bulk_wait_read<0>();  // the previous reduce-add has read the staging box
-        __syncwarp();
+        tmem_st_wait();
+        float2* stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + plan.bar_bytes);
+        {
+          const float inv_w = 1.0f / (float)wcols;
+          const float mean_i = kshift + s1 * inv_w;
+          const float m2_i = fmaxf(s2 - s1 * s1 * inv_w, 0.f);
+          stats[cq * 128 + r_in_tile] = make_float2(mean_i, m2_i);
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kWsEpiWarps) : "memory");
+        float mean, rstd;
+        {
+          const float2 a0 = stats[r_in_tile], a1 = stats[128 + r_in_tile], a2 = stats[256 + r_in_tile], a3 = stats[384 + r_in_tile];
+          mean = 0.25f * ((a0.x + a1.x) + (a2.x + a3.x));
+          const float e0 = a0.x - mean, e1 = a1.x - mean, e2 = a2.x - mean, e3 = a3.x - mean;
+          const float m2 = ((a0.y + a1.y) + (a2.y + a3.y)) + (float)wcols * ((e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3));
+          rstd = rsqrtf(m2 * (1.0f / (float)H) + 1e-6f);
+        }
+        const float4* sh_g = reinterpret_cast<const float4*>(p.ln_shift + (size_t)b * p.gate_stride + col0);
+        const float4* sc_g = reinterpret_cast<const float4*>(p.ln_scale + (size_t)b * p.gate_stride + col0);
+        // u boxes: [32 rows x 16 columns] bf16 = 1 KB, two of them in the warp's staging box (32-byte rows, SWIZZLE_32B)
+        tmem_ld16(lane_t + col0, v);
+        for (int bx = 0; bx < nb; ++bx) {
+          tmem_ld_wait();
+          uint32_t pk[8];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          st_shared_v4(stage_s + stage_off64(lane, ch), __float_as_uint(o[ch].x), __float_as_uint(o[ch].y), __float_as_uint(o[ch].z),
-                       __float_as_uint(o[ch].w));
-        fence_proxy_async();
-        __syncwarp();
-        if (issuer && !(p.debug & 2)) {
-          tma_reduce_add_2d_s(&tmap_h, stage_s, col, row0);
-          bulk_commit();
+          for (int jx = 0; jx < 4; ++jx) {
+            const float4 sc = __ldg(sc_g + bx * 4 + jx), sh = __ldg(sh_g + bx * 4 + jx);
+            const float y0 = fmaf((__uint_as_float(v[4 * jx + 0]) - mean) * rstd, 1.0f + sc.x, sh.x);
+            const float y1 = fmaf((__uint_as_float(v[4 * jx + 1]) - mean) * rstd, 1.0f + sc.y, sh.y);
+            const float y2 = fmaf((__uint_as_float(v[4 * jx + 2]) - mean) * rstd, 1.0f + sc.z, sh.z);
+            const float y3 = fmaf((__uint_as_float(v[4 * jx + 3]) - mean) * rstd, 1.0f + sc.w, sh.w);
+            pk[2 * jx] = pack_bf16x2(y0, y1), pk[2 * jx + 1] = pack_bf16x2(y2, y3);
+          }
+          if (bx + 1 < nb) {
+            tmem_ld16(lane_t + col0 + (bx + 1) * 16, v);
+          } else {  // OUT is no longer needed: the next m-block's first MMAs may overwrite it
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(out_free_l);
+          }
+          if (issuer) bulk_wait_read<1>();  // the store two boxes back has read this half of the staging box
+          __syncwarp();
+          const uint32_t ub = stage_s + (bx & 1) * 1024;
+          st_shared_v4(ub + stage_off32(lane, 0), pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(ub + stage_off32(lane, 1), pk[4], pk[5], pk[6], pk[7]);
+          fence_proxy_async();
+          __syncwarp();
+          if (issuer && !(p.debug & 2)) {
+            tma_store_2d_s(&tmap_u_st, ub, col0 + bx * 16, row0);
+            bulk_commit();
+          }
         }
+        if (issuer) bulk_wait_read<0>();  // before the named barrier at the top of the next m-block lets G be rewritten
+        __syncwarp();
+      } else {
+        // ---- OUT: h += gate * (acc + b2) as TMA f32 reduce-add boxes of 16 columns x 32 rows, one staging box per warp in G
+        // (free once out_full fired: every MMA that reads G has completed)
+        if (warp == 4) TRACE(0, 5);
+        mbar_wait(out_full, it & 1);
+        tcgen05_fence_after();
+        if (warp == 4) TRACE(0, 6);
+        const int b = (row < p.rows ? row : p.rows - 1) / p.rows_per_sample;
+        const bool gate_in_smem = b - b0 <= 1;
+        const uint32_t gate_s = smf_s + (M + H + (b - b0) * H) * 4;
+        const float* gate_g = p.gate + (size_t)b * p.gate_stride;
+        const int wcols = H / 4;  // this warp's output columns
+        const uint32_t stage_s = g_s + (warp - 4) * 2048;
+        const int col0 = cq * wcols;
+        const bool issuer = elect_one();  // TMA issue, commit and wait all by the same (elected) lane
+        uint32_t v[16];
+        tmem_ld16(lane_t + col0, v);
+        for (int bx = 0; bx < wcols / 16; ++bx) {
+          const int col = col0 + bx * 16;
+          tmem_ld_wait();
+          float4 o[4];
+#pragma unroll
+          for (int jx = 0; jx < 4; ++jx) {
+            const float4 gv = gate_in_smem ? ld_shared_f4(gate_s + col * 4 + jx * 16) : __ldg(reinterpret_cast<const float4*>(gate_g + col) + jx);
+            const float4 bv = ld_shared_f4(smf_s + (M + col) * 4 + jx * 16);
+            o[jx].x = gv.x * (__uint_as_float(v[4 * jx + 0]) + bv.x);
+            o[jx].y = gv.y * (__uint_as_float(v[4 * jx + 1]) + bv.y);
+            o[jx].z = gv.z * (__uint_as_float(v[4 * jx + 2]) + bv.z);
+            o[jx].w = gv.w * (__uint_as_float(v[4 * jx + 3]) + bv.w);
+          }
+          if (bx + 1 < wcols / 16) {  // next 16 columns: TMEM load in flight while these are staged and stored
+            tmem_ld16(lane_t + col + 16, v);
+          } else {  // OUT is in registers: the next m-block's first MMAs may overwrite it
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(out_free_l);
+          }
+          if (issuer) bulk_wait_read<0>();  // the previous reduce-add has read the staging box
+          __syncwarp();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            st_shared_v4(stage_s + stage_off64(lane, ch), __float_as_uint(o[ch].x), __float_as_uint(o[ch].y), __float_as_uint(o[ch].z),
+                         __float_as_uint(o[ch].w));
+          fence_proxy_async();
+          __syncwarp();
+          if (issuer && !(p.debug & 2)) {
+            tma_reduce_add_2d_s(&tmap_h, stage_s, col, row0);
+            bulk_commit();
+          }
+        }
+        if (issuer) bulk_wait_read<0>();  // before the named barrier at the top of the next m-block lets G be rewritten
+        __syncwarp();
       }
-      if (issuer) bulk_wait_read<0>();  // before the named barrier at the top of the next m-block lets G be rewritten
-      __syncwarp();
       if (warp == 4) TRACE(0, 7);
     }
   }

@@ -282,3 +282,98 @@ def test_fused_mlp_linear2(rows, H, M, rps):
     assert torch.isfinite(h).all()
     assert max_rel(h, ref) < 2e-3  # bf16 rounding flips of the hidden activation (GELU fit 2.6e-5) only
     assert float((h.double() - ref).abs().mean() / ref.abs().mean()) < 2e-4
+
+
+@pytest.mark.parametrize("rows,N,K,ldx,ldy,act,res,rowadd", [
+    (256000 // 8, 256, 108, 108, 256, 1, False, 0),   # net_merge.0 (peptide): K tail of 12 inside the last 32-wide k-block
+    (4000, 256, 256, 256, 384, 0, False, 4),          # net_merge.2 written into the [x | E_ent] context matrix + sin/cos row add
+    (5000, 96, 384, 384, 96, 1, False, 0),            # encoder.mlp.0
+    (5000, 384, 96, 96, 384, 0, False, 0),            # encoder.mlp.2: two 192-wide tiles
+    (3000, 64, 384, 384, 64, 0, False, 0),            # to_kv
+    (1234, 96, 32, 32, 96, 0, True, 0),               # to_out with the in-place residual
+    (777, 96, 96, 96, 288, 0, False, 0),              # to_qkv-like pitch
+    (2000, 768, 96, 96, 768, 0, False, 0),            # extender (4 x 192)
+    (130, 42, 128, 128, 42, 0, False, 0),             # atom14_pos head: N % 16 != 0, scalar stores (pitch 42)
+    (513, 20, 128, 128, 20, 0, False, 0),             # aatype head
+    (64, 2, 128, 128, 2, 0, False, 0),                # 2-wide position head
+    (1, 128, 128, 128, 128, 2, True, 0),              # a single row, SiLU of the sum
+    (19000, 128, 128, 128, 128, 1, False, 0),         # more tiles than SMs: both accumulators and every ring phase
+    (300, 256, 12, 12, 256, 0, False, 0),             # K smaller than one k-block
+    (640, 32, 32, 32, 32, 0, False, 0),
+])
+@pytest.mark.parametrize("path", [0, 1])
+def test_first_stage_linear_is_fp32_accurate(rows, N, K, ldx, ldy, act, res, rowadd, path):
+    """One first-stage layer (torch_modules.py / encoder.py / decoder.py nn.Linear + its fused epilogue) against fp64: the
+    tcgen05 3xTF32 kernel (path 0) and the mma.sync / FMA kernels (path 1) must both be as good as an fp32 FMA chain."""
+    L_ = _lib()
+    lib = L_.load()
+    g = torch.Generator(device="cpu").manual_seed(rows * 3 + N + K)
+    x = torch.randn(rows, ldx, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).contiguous()
+    b = (0.3 * torch.randn(N, generator=g)).contiguous()
+    y0 = torch.randn(rows, ldy, generator=g).cuda()
+    y = y0.clone()
+    ra = torch.randn(max(rowadd, 1), N, generator=g).cuda()
+    L_.check(lib.lamslide_debug_fs_linear(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, N, K, ldx, ldy, act,
+                                          y.data_ptr() if res else 0, ldy, ra.data_ptr() if rowadd else 0, max(rowadd, 1), N, path,
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = x[:, :K].double() @ w.double().cuda().t() + b.double().cuda()
+    if act == 1:
+        ref = 0.5 * ref * (1.0 + torch.erf(ref / math.sqrt(2.0)))
+    if rowadd:
+        ref = ref + ra.double()[torch.arange(rows, device="cuda") % rowadd]
+    if res:
+        ref = ref + y0[:, :N].double()
+    if act == 2:
+        ref = ref * torch.sigmoid(ref)
+    assert torch.isfinite(y).all()
+    assert max_rel(y[:, :N], ref) < 5e-6, f"linear {rows}x{N}x{K} path={path}"
+    if ldy > N:
+        assert torch.equal(y[:, N:], y0[:, N:]), "columns past N must not be touched"
+
+
+@pytest.mark.parametrize("rows,H,M,rps", [
+    (4096, 384, 1536, 2000), (128 * 149 * 2 + 5, 384, 1536, 2000), (100, 384, 1536, 50), (1, 384, 1536, 7), (4096, 256, 512, 5760),
+    (128 * 149 * 2 + 5, 256, 1024, 1000), (40000, 128, 128, 640), (256 * 75, 384, 128, 2000),
+])
+def test_fused_mlp_drain_writes_next_layernorm_modulate(rows, H, M, rps):
+    """The fused MLP kernel in LN mode: besides h += gate * (...), its drain writes u' = LayerNorm(h_new) * (1 + scale) + shift
+    (the next block's pre_norm + modulate, latent_si_v31.py:50,57) over the buffer its own A operand came from."""
+    L_ = _lib()
+    lib = L_.load()
+    g = torch.Generator(device="cpu").manual_seed(rows + M + 11)
+    nb = (rows + rps - 1) // rps
+    u0 = torch.randn(rows, H, generator=g).to(torch.bfloat16).cuda()
+    u = u0.clone()
+    act = torch.randn(rows, H + M, generator=g).to(torch.bfloat16).cuda()
+    w1 = (torch.randn(3 * H + M, H, generator=g) / math.sqrt(H)).to(torch.bfloat16).cuda()
+    w2 = (torch.randn(H, H + M, generator=g) / math.sqrt(H + M)).to(torch.bfloat16).cuda()
+    b1 = (0.1 * torch.randn(3 * H + M, generator=g)).cuda()
+    b2 = (0.1 * torch.randn(H, generator=g)).cuda()
+    gate = torch.randn(nb, H, generator=g).cuda()
+    shift = torch.randn(nb, H, generator=g).cuda()
+    scale = (0.5 * torch.randn(nb, H, generator=g)).cuda()
+    # a residual stream with a row mean far from zero and very different row scales: the one-pass statistics must cope
+    h0 = (torch.randn(rows, H, generator=g) * (0.1 + 10.0 * torch.rand(rows, 1, generator=g)) + 5.0 * torch.randn(rows, 1, generator=g)).cuda()
+    h = h0.clone()
+    st = torch.cuda.current_stream().cuda_stream
+    L_.check(lib.lamslide_debug_fused_mlp_ln(u.data_ptr(), act.data_ptr(), w1.data_ptr(), w2.data_ptr(), b1.data_ptr(), b2.data_ptr(),
+                                             gate.data_ptr(), h.data_ptr(), rows, H, M, rps, shift.data_ptr(), scale.data_ptr(),
+                                             u.data_ptr(), st))
+    torch.cuda.synchronize()
+    # the residual update must equal the plain kernel's (TMA reduce-add path) to fp32 rounding
+    h_plain = h0.clone()
+    L_.check(lib.lamslide_debug_fused_mlp(u0.data_ptr(), act.data_ptr(), w1.data_ptr(), w2.data_ptr(), b1.data_ptr(), b2.data_ptr(),
+                                          gate.data_ptr(), h_plain.data_ptr(), rows, H, M, rps, st))
+    torch.cuda.synchronize()
+    assert torch.isfinite(h).all() and torch.isfinite(u.float()).all()
+    assert max_rel(h, h_plain.double()) < 1e-6
+    # u' against fp64 LayerNorm + modulate of the h the kernel produced
+    b_of_row = torch.arange(rows, device="cuda") // rps
+    hd = h.double()
+    ln = (hd - hd.mean(1, keepdim=True)) / torch.sqrt(hd.var(1, unbiased=False, keepdim=True) + 1e-6)
+    ref = ln * (1.0 + scale.double()[b_of_row]) + shift.double()[b_of_row]
+    err = (u.double() - ref).abs()
+    assert float((err / (ref.abs() + 1.0)).max()) < 2 ** -8  # one bf16 rounding of the output
+    assert float(err.mean() / ref.abs().mean()) < 2e-3

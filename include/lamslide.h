@@ -243,6 +243,13 @@ int lamslide_debug_fs_linear(const float* x, const float* w_host, const float* b
                              int32_t ldx, int32_t ldy, int32_t act, const float* res, int32_t ldr, const float* rowadd, int32_t period,
                              int32_t ldra, int32_t path, void* stream);
 
+/* the same layer followed by the LayerNorm of its result (eps 1e-5; the successor's pre-norm, run in the layer's epilogue where a
+ * thread or thread pair holds a group): ln_out [rows,N] = LN over groups of `group` columns (0: the whole row) [* ln_w + ln_b];
+ * res [rows,N] optional residual; y_needed == 0: y need not be written. */
+int lamslide_debug_fs_linear_ln(const float* x, const float* w_host, const float* bias_host, float* y, float* ln_out, const float* ln_w,
+                                const float* ln_b, int32_t group, int32_t rows, int32_t N, int32_t K, const float* res,
+                                int32_t y_needed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ SYMBOLS = [
     "lamslide_first_stage_create", "lamslide_first_stage_destroy", "lamslide_first_stage_workspace_bytes",
     "lamslide_encode", "lamslide_decode", "lamslide_debug_gemm", "lamslide_debug_attention",
     "lamslide_debug_linear1", "lamslide_debug_linear2", "lamslide_debug_gemm_mainloop", "lamslide_debug_fused_mlp",
-    "lamslide_debug_fs_linear", "lamslide_debug_fused_mlp_ln",
+    "lamslide_debug_fs_linear", "lamslide_debug_fused_mlp_ln", "lamslide_debug_fs_linear_ln",
     "lamslide_profile_begin", "lamslide_profile_end", "lamslide_debug_kernel_count", "lamslide_debug_attention_trace",
 ]
 
@@ -111,6 +111,7 @@ def load() -> C.CDLL:
     lib.lamslide_debug_gemm_mainloop.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.lamslide_debug_fused_mlp.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.lamslide_debug_fused_mlp_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.lamslide_debug_fs_linear_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, i32, vp]
     lib.lamslide_debug_fs_linear.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, i32, i32, vp]
     lib.lamslide_profile_end.argtypes = [C.c_char_p, sz]
     lib.lamslide_debug_attention_trace.argtypes = [vp]

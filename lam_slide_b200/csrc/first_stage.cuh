@@ -17,9 +17,19 @@ struct LinearArgs {
   const float* bias;   // [N] or null
   float* Y; int ldy;
   const float* res; int ldr;        // residual or null
+  const long long* res_idx = nullptr;  // residual row of output row r = res_idx[r] (a per-entity table) instead of r
   const float* rowadd; int rowadd_period; int ldra;  // e.g. sin/cos residue-index embedding, or null
   int rows, N, K;
   int gelu;
+  // fused LayerNorm of the result (tcgen05 kernel only): ln_out[r, n] = LN_group(y[r, :])[n] * ln_w[n] + ln_b[n] over groups of
+  // ln_group consecutive columns (ln_group = 0: nn.LayerNorm of the row, one n-tile; ln_group = BN / 2: the tokens a row is reshaped into).
+  // Y may be null when only the normalised output is needed.  ln_w / ln_b null: no affine.
+  float* ln_out = nullptr; int ld_ln = 0;
+  const float* ln_w = nullptr; const float* ln_b = nullptr;
+  int ln_group = 0;
+  float ln_eps = 1e-5f;
+  int debug = 0;  // profiling aid (LAMSLIDE_L5_DEBUG in debug builds): 1 no global stores, 2 epilogue only releases the accumulator,
+                  // 4 splitters only arrive, 8 no weight-tile loads
 };
 
 __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs a) {
@@ -67,7 +77,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(LinearArgs a) {
       float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
       if (a.gelu == 1) v = gelu_exact(v);
       if (a.rowadd) v += a.rowadd[(size_t)(r % a.rowadd_period) * a.ldra + n];
-      if (a.res) v += a.res[(size_t)r * a.ldr + n];
+      if (a.res) v += a.res[(size_t)(a.res_idx ? a.res_idx[r] : r) * a.ldr + n];
       if (a.gelu == 2) v = v / (1.0f + expf(-v));
       a.Y[(size_t)r * a.ldy + n] = v;
     }
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(256) linear_f32_v2_kernel(LinearArgs a) {
       float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
       if (a.gelu == 1) v = gelu_exact(v);
       if (a.rowadd) v += a.rowadd[(size_t)(r % a.rowadd_period) * a.ldra + n];
-      if (a.res) v += a.res[(size_t)r * a.ldr + n];
+      if (a.res) v += a.res[(size_t)(a.res_idx ? a.res_idx[r] : r) * a.ldr + n];
       if (a.gelu == 2) v = v / (1.0f + expf(-v));
       a.Y[(size_t)r * a.ldy + n] = v;
     }
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) linear_f32_tc_kernel(LinearArgs a) {
           v0 += ra[0], v1 += ra[1];
         }
         if (a.res) {
-          const float* rs = a.res + (size_t)r * a.ldr + n;
+          const float* rs = a.res + (size_t)(a.res_idx ? a.res_idx[r] : r) * a.ldr + n;
           v0 += rs[0], v1 += rs[1];
         }
         if (a.gelu == 2) v0 = v0 / (1.0f + expf(-v0)), v1 = v1 / (1.0f + expf(-v1));
@@ -296,6 +306,16 @@ __global__ void gather_cols_kernel(float* __restrict__ dst, int ldd, int col0, c
   int j = (int)(i % wp);
   dst[(size_t)r * ldd + col0 + j] = j < width ? table[(size_t)idx[r] * width + j] : 0.f;
 }
+// same for width, col0, ldd multiples of 4 and 16-byte aligned pointers: one float4 per thread
+__global__ void gather_cols4_kernel(float* __restrict__ dst, int ldd, int col0, const float* __restrict__ table, int width,
+                                    const long long* __restrict__ idx, long long rows) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w4 = width >> 2;
+  if (i >= rows * w4) return;
+  long long r = i / w4;
+  int j = (int)(i % w4) * 4;
+  *reinterpret_cast<float4*>(dst + (size_t)r * ldd + col0 + j) = __ldg(reinterpret_cast<const float4*>(table + (size_t)idx[r] * width + j));
+}
 // ---- dst[r, col0 + j] = src[r, j] for j < width, 0 for width <= j < width + pad (zero columns that round a feature row up to a
 // multiple of 4 floats, so the following linear layer can take the vectorised / tensor-core kernels)
 __global__ void copy_cols_kernel(float* __restrict__ dst, int ldd, int col0, const float* __restrict__ src, int width, int pad, long long rows) {
@@ -339,6 +359,7 @@ __global__ void point_feats_kernel(const float* __restrict__ pos, const float* _
 // keys with mask == 0 are excluded (bool key mask, True = keep).  q_frame_stride may be 0 (queries shared by all frames).
 struct SmallAttnArgs {
   const float* q; long long q_frame_stride; int ldq;   // q[frame, sq, head*16 + d]
+  const long long* q_index = nullptr;                  // when set: the query row of (frame, sq) is q[q_index[frame * Sq + sq]] (a per-entity table)
   const float* k; const float* v; long long kv_frame_stride; int ldkv;  // k/v[frame, sk, head*16 + d] (pointers pre-offset)
   const float* gq; const float* gk;                    // RMSNorm scales [16] or null
   const unsigned char* mask;                           // [frames, Sk] or null
@@ -357,7 +378,8 @@ __global__ void __launch_bounds__(128) small_attn_f32_kernel(SmallAttnArgs a) {
   const long long f = idx / ((long long)a.Sq * a.heads);
   float q[DH], acc[DH];
   {
-    const float4* qp = reinterpret_cast<const float4*>(a.q + f * a.q_frame_stride + (size_t)sq * a.ldq + hh * DH);
+    const float4* qp = reinterpret_cast<const float4*>(
+        a.q_index ? a.q + (size_t)a.q_index[f * a.Sq + sq] * a.ldq + hh * DH : a.q + f * a.q_frame_stride + (size_t)sq * a.ldq + hh * DH);
     float ss = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {

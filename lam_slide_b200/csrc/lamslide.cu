@@ -822,8 +822,10 @@ static int ln_modulate(const lamslide_backbone* bb, const float* h, __nv_bfloat1
 // of the row's sample]);  mod = [every modulation.lin | adaLN_modulation.1](svec)  ->  ws.mod [n * B, depth * 6H + 2H].
 // fp32 through the first stage's linear kernels (3xTF32 tensor-core GEMM when the shapes allow: fp32-accurate).
 struct LinW;
+struct FsLN;
 static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, long long rows, int act, const float* res, int ldr,
-                     const float* rowadd, int period, int ldra, cudaStream_t st);
+                     const float* rowadd, int period, int ldra, cudaStream_t st, const FsLN* ln = nullptr,
+                     const long long* res_idx = nullptr);
 struct LinW {
   float *w = nullptr, *b = nullptr;
   int out = 0, in = 0;
@@ -1281,6 +1283,10 @@ struct lamslide_first_stage {
   int point_nb = 0;
   LinW point_mlp, merge0, merge2, enc_mlp0, enc_mlp2, quant, post_quant, query_mlp, extender;
   float* latents = nullptr;                             // [L, D]
+  // folded at create (host fp64): what depends only on the learned latents / on the entity id
+  float* enc_q0 = nullptr;      // [L, inner]            to_q(LN(latents)) of the first encoder cross block
+  float* dec_q_tab = nullptr;   // [num_entities, dq]    query_mlp(entity_embedding)
+  float* dec_qq_tab = nullptr;  // [num_entities, inner] to_q(LN(dec_q_tab)) of the decoder output block
   std::vector<AttnBlockW> enc_cross, enc_self, dec_self, dec_cross;
   AttnBlockW out_block;
   std::vector<LinW> head0, head2;
@@ -1494,6 +1500,66 @@ extern "C" int lamslide_first_stage_create(const lamslide_first_stage_config* cf
     fs->extender.out = D * n, fs->extender.in = D;
     TRY(prepare_tc5(fs->arena, wp.data(), &fs->extender));
   }
+  // ---- constant folding (host, fp64): queries that depend only on the learned latents (encoder.py:39: the latents are the same
+  // for every frame) or only on the entity id (decoder.py:83-86) become small tables, so that the per-frame work starts at the
+  // attention itself
+  static const bool no_fold = env_flag("LAMSLIDE_FS_NO_FOLD");
+  if (!no_fold) {
+    auto layer_norm = [](std::vector<double>& x, int rows, int dim, const float* w, const float* b) {
+      for (int r = 0; r < rows; ++r) {
+        double m = 0, v = 0;
+        for (int j = 0; j < dim; ++j) m += x[(size_t)r * dim + j];
+        m /= dim;
+        for (int j = 0; j < dim; ++j) v += (x[(size_t)r * dim + j] - m) * (x[(size_t)r * dim + j] - m);
+        const double rstd = 1.0 / std::sqrt(v / dim + 1e-5);
+        for (int j = 0; j < dim; ++j) x[(size_t)r * dim + j] = (x[(size_t)r * dim + j] - m) * rstd * w[j] + b[j];
+      }
+    };
+    auto linear = [](const std::vector<double>& x, int rows, int in, const float* w, const float* b, int out) {
+      std::vector<double> y((size_t)rows * out);
+      for (int r = 0; r < rows; ++r)
+        for (int o = 0; o < out; ++o) {
+          double acc = b ? b[o] : 0.0;
+          for (int k = 0; k < in; ++k) acc += x[(size_t)r * in + k] * w[(size_t)o * in + k];
+          y[(size_t)r * out + o] = acc;
+        }
+      return y;
+    };
+    auto upload = [&](const std::vector<double>& x, float** dst) {
+      std::vector<float> f(x.begin(), x.end());
+      return fs->arena.upload_f32(f.data(), f.size(), dst);
+    };
+    if (cfg->enc_blocks_cross > 0) {
+      const int Lq = cfg->enc_num_latents, inner = cfg->enc_heads_cross * 16;
+      const std::string p = "encoder.cross_attn_blocks.0.attn.";
+      const lamslide_tensor *lt = ld.sd.get("encoder.latents", {Lq, D}), *nw = ld.sd.get(p + "norm.weight", {D}),
+                            *nb = ld.sd.get(p + "norm.bias", {D}), *wq = ld.sd.get(p + "fn.to_q.weight", {inner, D});
+      if (!lt || !nw || !nb || !wq) return LAMSLIDE_ERR_MISSING;
+      std::vector<double> x(lt->data, lt->data + (size_t)Lq * D);
+      layer_norm(x, Lq, D, nw->data, nb->data);
+      TRY(upload(linear(x, Lq, D, wq->data, nullptr, inner), &fs->enc_q0));
+    }
+    {
+      const int ne = cfg->num_entities, inner = cfg->dec_heads_cross * 16;
+      const std::string p = "decoder.output_block.attn.";
+      const lamslide_tensor *et = ld.sd.get("encoder.entity_embedding.embedding.weight", {ne, E}),
+                            *qw = ld.sd.get("decoder.query_mlp.1.weight", {dq, E}), *qb = ld.sd.get("decoder.query_mlp.1.bias", {dq}),
+                            *nw = ld.sd.get(p + "norm.weight", {dq}), *nb = ld.sd.get(p + "norm.bias", {dq}),
+                            *wq = ld.sd.get(p + "fn.to_q.weight", {inner, dq});
+      if (!et || !qw || !qb || !nw || !nb || !wq) return LAMSLIDE_ERR_MISSING;
+      std::vector<double> e((size_t)ne * E);
+      for (int r = 0; r < ne; ++r) {  // nn.Embedding(max_norm=1), as FsLoader::table
+        float ss = 0.f;
+        for (int j = 0; j < E; ++j) ss += et->data[(size_t)r * E + j] * et->data[(size_t)r * E + j];
+        const float nrm = std::sqrt(ss), sc = nrm > 1.0f ? 1.0f / (nrm + 1e-7f) : 1.0f;
+        for (int j = 0; j < E; ++j) e[(size_t)r * E + j] = nrm > 1.0f ? et->data[(size_t)r * E + j] * sc : et->data[(size_t)r * E + j];
+      }
+      std::vector<double> q = linear(e, ne, E, qw->data, qb->data, dq);
+      TRY(upload(q, &fs->dec_q_tab));
+      layer_norm(q, ne, dq, nw->data, nb->data);
+      TRY(upload(linear(q, ne, dq, wq->data, nullptr, inner), &fs->dec_qq_tab));
+    }
+  }
   *out = guard.release();
   return 0;
 }
@@ -1513,17 +1579,50 @@ struct Bump {
 };
 
 static int launch_linear_tc5(const LinW& L, const LinearArgs& a, cudaStream_t st);
+static int fs_layernorm(const float* x, int ldx, int period, float* y, int ldy, const LNW* n, long long rows, int dim, float eps,
+                        cudaStream_t st);
+// LayerNorm to apply to the result of a linear layer (the next sub-layer's pre-norm): out = LN(y) [* n->w + n->b] over groups of
+// `group` columns (0: the whole row).  y_needed = false: the un-normalised result itself is not used by anybody.
+struct FsLN {
+  float* out = nullptr;
+  int ld = 0;
+  const LNW* n = nullptr;
+  int group = 0;
+  bool y_needed = true;
+};
+// the same LayerNorm as a separate launch (layers the tcgen05 kernel does not take, or a group it cannot hold)
+static int fs_ln_after(const FsLN& ln, const float* Y, int ldy, long long rows, int N, int group, cudaStream_t st) {
+  if (group == N) return fs_layernorm(Y, ldy, 0, ln.out, ln.ld, ln.n, rows, N, 1e-5f, st);
+  if (ldy != N || ln.ld != N || N % group != 0) return fail(LAMSLIDE_ERR_INVALID, "grouped LayerNorm needs dense rows");
+  return fs_layernorm(Y, group, 0, ln.out, group, ln.n, rows * (N / group), group, 1e-5f, st);
+}
 // act: 0 none, 1 erf-GELU (before the adds), 2 SiLU of the sum (after the adds)
 static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, long long rows, int act, const float* res, int ldr,
-                     const float* rowadd, int period, int ldra, cudaStream_t st) {
+                     const float* rowadd, int period, int ldra, cudaStream_t st, const FsLN* ln, const long long* res_idx) {
   LinearArgs a;
-  a.X = X, a.ldx = ldx, a.W = L.w, a.bias = L.b, a.Y = Y, a.ldy = ldy, a.res = res, a.ldr = ldr;
+  a.X = X, a.ldx = ldx, a.W = L.w, a.bias = L.b, a.Y = Y, a.ldy = ldy, a.res = res, a.ldr = ldr, a.res_idx = res_idx;
   a.rowadd = rowadd, a.rowadd_period = period > 0 ? period : 1, a.ldra = ldra;
   a.rows = (int)rows, a.N = L.out, a.K = L.in, a.gelu = act;
+  a.debug = env_int("LAMSLIDE_L5_DEBUG", 0);
   static const bool legacy_fs = env_flag("LAMSLIDE_LEGACY_FS_LINEAR");
   const bool vec_ok = !legacy_fs && L.in % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)L.w & 15) == 0;
   static const bool no_tc5 = env_flag("LAMSLIDE_FS_NO_TCGEN05");
-  if (L.bn && !legacy_fs && !no_tc5 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0) return launch_linear_tc5(L, a, st);
+  static const bool no_ln_epi = env_flag("LAMSLIDE_FS_NO_LN_EPILOGUE");
+  const int group = ln ? (ln->group > 0 ? ln->group : L.out) : 0;
+  if (L.bn && !legacy_fs && !no_tc5 && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0) {
+    // the LayerNorm runs in the epilogue when a thread pair (group = the row, one n-tile) or a thread (group = half a tile) holds a group
+    const bool row_ln = ln && group == L.out && L.out <= L.bn;
+    const bool half_ln = ln && !row_ln && group * 2 == L.bn && L.out % L.bn == 0 && ln->ld == L.out;
+    const bool fuse_ln = !no_ln_epi && (row_ln || half_ln);
+    if (fuse_ln) {
+      a.ln_out = ln->out, a.ld_ln = ln->ld, a.ln_group = row_ln ? 0 : group;
+      a.ln_w = ln->n ? ln->n->w : nullptr, a.ln_b = ln->n ? ln->n->b : nullptr;
+      if (!ln->y_needed) a.Y = nullptr;
+    }
+    TRY(launch_linear_tc5(L, a, st));
+    if (ln && !fuse_ln) TRY(fs_ln_after(*ln, Y, ldy, rows, L.out, group, st));
+    return 0;
+  }
   static const bool no_tc = env_flag("LAMSLIDE_FS_NO_TF32X3");
   // the kernel is chosen by the layer's shape only, never by the row count: a trajectory must decode to the same bits whether it is
   // sampled alone, in a batch of 64 or as a shard of a multi-GPU run
@@ -1539,6 +1638,7 @@ static int fs_linear(const LinW& L, const float* X, int ldx, float* Y, int ldy, 
     linear_f32_kernel<<<grid, 256, 0, st>>>(a);
   }
   LAUNCH_CHECK();
+  if (ln) TRY(fs_ln_after(*ln, Y, ldy, rows, L.out, group, st));
   return 0;
 }
 template <int BN>
@@ -1578,6 +1678,15 @@ static int fs_attn(const SmallAttnArgs& a, cudaStream_t st) {
   LAUNCH_CHECK();
   return 0;
 }
+// dst[r, col0 : col0 + width] = table[idx[r]]
+static int fs_gather(float* dst, int ldd, int col0, const float* table, int width, const long long* idx, long long rows, cudaStream_t st) {
+  if (width % 4 == 0 && col0 % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)table & 15) == 0)
+    gather_cols4_kernel<<<cdiv(rows * (width / 4), 256), 256, 0, st>>>(dst, ldd, col0, table, width, idx, rows);
+  else
+    gather_cols_kernel<<<cdiv(rows * width, 256), 256, 0, st>>>(dst, ldd, col0, table, width, idx, rows);
+  LAUNCH_CHECK();
+  return 0;
+}
 
 struct BlockScratch {
   float *xn, *cn, *q, *kv, *att, *f1;
@@ -1593,32 +1702,54 @@ static BlockScratch block_scratch(Bump& bp, long long rows_x, int dim, long long
   return s;
 }
 
-// x [F*Sx, dim] (updated in place)  <-  CrossAttentionBlock(x, context = ctx [F*Sc, ctx_dim], mask)
+// What a block may find already done by its predecessor, and what it should leave for its successor.  Every LayerNorm whose input is
+// the output of a linear layer runs in that layer's epilogue (FsLN); queries that depend only on the entity id or on the learned
+// latents come from tables folded at *_create (FsFolded).
+struct BlockIo {
+  bool xn_ready = false;            // s.xn already holds LN(x; b.norm)
+  bool cn_ready = false;            // s.cn already holds LN(ctx; b.norm_ctx)
+  const float* q_table = nullptr;   // to_q(LN(x; b.norm)) as a table: rows q_index[row] (or, q_index null, row % Sx: the same for all frames)
+  const long long* q_index = nullptr;
+  const float* x_table = nullptr;   // the block input x itself as a table (residual of to_out): rows x_index[row] or row % Sx
+  const long long* x_index = nullptr;
+  const FsLN* after = nullptr;      // LayerNorm of the block's output (the successor's pre-norm)
+};
+
+// x [F*Sx, dim] (updated in place; written, not read, when io.x_table is given)  <-  CrossAttentionBlock(x, context = ctx [F*Sc, ctx_dim], mask)
 static int run_cross_block(const AttnBlockW& b, float* x, int F, int Sx, const float* ctx, int Sc, const uint8_t* mask,
-                           const BlockScratch& s, cudaStream_t st) {
+                           const BlockScratch& s, cudaStream_t st, const BlockIo& io = BlockIo()) {
   const long long rx = (long long)F * Sx, rc = (long long)F * Sc;
   const int inner = b.heads * b.dh;
-  TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.norm, rx, b.dim, 1e-5f, st));
-  TRY(fs_layernorm(ctx, b.ctx_dim, 0, s.cn, b.ctx_dim, &b.norm_ctx, rc, b.ctx_dim, 1e-5f, st));
-  TRY(fs_linear(b.to_q, s.xn, b.dim, s.q, inner, rx, false, nullptr, 0, nullptr, 0, 0, st));
-  TRY(fs_linear(b.to_kv, s.cn, b.ctx_dim, s.kv, 2 * inner, rc, false, nullptr, 0, nullptr, 0, 0, st));
   SmallAttnArgs a;
-  a.q = s.q, a.q_frame_stride = (long long)Sx * inner, a.ldq = inner;
+  if (io.q_table) {
+    a.q = io.q_table, a.q_frame_stride = 0, a.ldq = inner, a.q_index = io.q_index;
+  } else {
+    if (!io.xn_ready) TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.norm, rx, b.dim, 1e-5f, st));
+    TRY(fs_linear(b.to_q, s.xn, b.dim, s.q, inner, rx, false, nullptr, 0, nullptr, 0, 0, st));
+    a.q = s.q, a.q_frame_stride = (long long)Sx * inner, a.ldq = inner;
+  }
+  if (!io.cn_ready) TRY(fs_layernorm(ctx, b.ctx_dim, 0, s.cn, b.ctx_dim, &b.norm_ctx, rc, b.ctx_dim, 1e-5f, st));
+  TRY(fs_linear(b.to_kv, s.cn, b.ctx_dim, s.kv, 2 * inner, rc, false, nullptr, 0, nullptr, 0, 0, st));
   a.k = s.kv, a.v = s.kv + inner, a.kv_frame_stride = (long long)Sc * 2 * inner, a.ldkv = 2 * inner;  // k first, then v
   a.gq = b.gq, a.gk = b.gk, a.mask = mask, a.out = s.att, a.ldo = inner;
   a.frames = F, a.Sq = Sx, a.Sk = Sc, a.heads = b.heads, a.scale = 1.0f / std::sqrt((float)b.dh);
   TRY(fs_attn(a, st));
-  TRY(fs_linear(b.to_out, s.att, inner, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st));
-  TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.ff_norm, rx, b.dim, 1e-5f, st));
+  const FsLN ff{s.xn, b.dim, &b.ff_norm, 0, true};
+  if (io.x_table && io.x_index)
+    TRY(fs_linear(b.to_out, s.att, inner, x, b.dim, rx, false, io.x_table, b.dim, nullptr, 0, 0, st, &ff, io.x_index));
+  else if (io.x_table)
+    TRY(fs_linear(b.to_out, s.att, inner, x, b.dim, rx, false, nullptr, 0, io.x_table, Sx, b.dim, st, &ff));
+  else
+    TRY(fs_linear(b.to_out, s.att, inner, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st, &ff));
   TRY(fs_linear(b.ff0, s.xn, b.dim, s.f1, b.dim, rx, true, nullptr, 0, nullptr, 0, 0, st));
-  TRY(fs_linear(b.ff1, s.f1, b.dim, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st));
+  TRY(fs_linear(b.ff1, s.f1, b.dim, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st, io.after));
   return 0;
 }
 
-static int run_self_block(const AttnBlockW& b, float* x, int F, int S, const BlockScratch& s, cudaStream_t st) {
+static int run_self_block(const AttnBlockW& b, float* x, int F, int S, const BlockScratch& s, cudaStream_t st, const BlockIo& io = BlockIo()) {
   const long long rx = (long long)F * S;
   const int inner = b.heads * b.dh;
-  TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.norm, rx, b.dim, 1e-5f, st));
+  if (!io.xn_ready) TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.norm, rx, b.dim, 1e-5f, st));
   TRY(fs_linear(b.to_qkv, s.xn, b.dim, s.kv, 3 * inner, rx, false, nullptr, 0, nullptr, 0, 0, st));
   SmallAttnArgs a;
   a.q = s.kv, a.q_frame_stride = (long long)S * 3 * inner, a.ldq = 3 * inner;
@@ -1626,10 +1757,10 @@ static int run_self_block(const AttnBlockW& b, float* x, int F, int S, const Blo
   a.gq = b.gq, a.gk = b.gk, a.mask = nullptr, a.out = s.att, a.ldo = inner;
   a.frames = F, a.Sq = S, a.Sk = S, a.heads = b.heads, a.scale = 1.0f / std::sqrt((float)b.dh);
   TRY(fs_attn(a, st));
-  TRY(fs_linear(b.to_out, s.att, inner, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st));
-  TRY(fs_layernorm(x, b.dim, 0, s.xn, b.dim, &b.ff_norm, rx, b.dim, 1e-5f, st));
+  const FsLN ff{s.xn, b.dim, &b.ff_norm, 0, true};
+  TRY(fs_linear(b.to_out, s.att, inner, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st, &ff));
   TRY(fs_linear(b.ff0, s.xn, b.dim, s.f1, b.dim, rx, true, nullptr, 0, nullptr, 0, 0, st));
-  TRY(fs_linear(b.ff1, s.f1, b.dim, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st));
+  TRY(fs_linear(b.ff1, s.f1, b.dim, x, b.dim, rx, false, x, b.dim, nullptr, 0, 0, st, io.after));
   return 0;
 }
 
@@ -1659,15 +1790,13 @@ static int encode_impl(lamslide_first_stage* fs, const lamslide_frame_inputs* in
     case LAMSLIDE_FS_PEPTIDE:
       if (!in->index0) return fail(LAMSLIDE_ERR_INVALID, "peptide encode needs aatype (index0)");
       if (N > c.max_res) return fail(LAMSLIDE_ERR_INVALID, "N = %d exceeds max_res = %d", N, c.max_res);
-      gather_cols_kernel<<<cdiv(R * 64, TB), TB, 0, st>>>(feat, fs->feat_dim, 0, fs->tab0, 64, (const long long*)in->index0, R);
-      LAUNCH_CHECK();
+      TRY(fs_gather(feat, fs->feat_dim, 0, fs->tab0, 64, (const long long*)in->index0, R, st));
       copy_cols_kernel<<<cdiv(R * (fs->feat_dim - 64), TB), TB, 0, st>>>(feat, fs->feat_dim, 64, in->pos, 42, fs->feat_dim - fs->feat_used, R);
       LAUNCH_CHECK();
       break;
     case LAMSLIDE_FS_MD17:
       if (!in->index0) return fail(LAMSLIDE_ERR_INVALID, "md17 encode needs atom (index0)");
-      gather_cols_kernel<<<cdiv(R * 64, TB), TB, 0, st>>>(feat, fs->feat_dim, 0, fs->tab0, 64, (const long long*)in->index0, R);
-      LAUNCH_CHECK();
+      TRY(fs_gather(feat, fs->feat_dim, 0, fs->tab0, 64, (const long long*)in->index0, R, st));
       point_feats_kernel<<<cdiv(R * 129, TB), TB, 0, st>>>(in->pos, fs->point_basis, pfeat, fs->point_nb, R);
       LAUNCH_CHECK();
       TRY(fs_linear(fs->point_mlp, pfeat, 129, feat + 64, fs->feat_dim, R, false, nullptr, 0, nullptr, 0, 0, st));
@@ -1687,18 +1816,37 @@ static int encode_impl(lamslide_first_stage* fs, const lamslide_frame_inputs* in
   // net_merge (+ residue-index sin/cos embedding for peptides) written straight into the context matrix [x | E_ent]
   TRY(fs_linear(fs->merge0, feat_in, fs->feat_dim, hid1, Din, R, true, nullptr, 0, nullptr, 0, 0, st));
   TRY(fs_linear(fs->merge2, hid1, Din, ctx_in, C, R, false, nullptr, 0, fs->sincos, N, Din, st));
-  gather_cols_kernel<<<cdiv(R * E, TB), TB, 0, st>>>(ctx_in, C, Din, fs->ent_table, E, (const long long*)in->entities, R);
-  LAUNCH_CHECK();
+  TRY(fs_gather(ctx_in, C, Din, fs->ent_table, E, (const long long*)in->entities, R, st));
   // EncoderBase.prepare_inputs MLP (encoder.py:35-41)
   TRY(fs_linear(fs->enc_mlp0, ctx_in, C, hid2, D, R, true, nullptr, 0, nullptr, 0, 0, st));
   TRY(fs_linear(fs->enc_mlp2, hid2, D, ctx, C, R, false, nullptr, 0, nullptr, 0, 0, st));
-  bcast_rows_kernel<<<cdiv(FL * D, TB), TB, 0, st>>>(z, fs->latents, D, L, FL);
-  LAUNCH_CHECK();
-  for (auto& b : fs->enc_cross) TRY(run_cross_block(b, z, F, L, ctx, N, in->mask, s, st));
-  for (auto& b : fs->enc_self) TRY(run_self_block(b, z, F, L, s, st));
+  // the blocks: each leaves LN(z) with its successor's pre-norm in s.xn (z itself only where a residual needs it)
+  const int ncross = (int)fs->enc_cross.size(), nself = (int)fs->enc_self.size();
+  const bool fold0 = fs->enc_q0 != nullptr && ncross > 0;  // first cross block: its queries come from the learned latents alone
+  if (!fold0) {
+    bcast_rows_kernel<<<cdiv(FL * D, TB), TB, 0, st>>>(z, fs->latents, D, L, FL);
+    LAUNCH_CHECK();
+  }
+  bool xn_ready = false;
+  for (int i = 0; i < ncross + nself; ++i) {
+    const bool cross = i < ncross;
+    const AttnBlockW& b = cross ? fs->enc_cross[i] : fs->enc_self[i - ncross];
+    const AttnBlockW* nb = i + 1 < ncross ? &fs->enc_cross[i + 1] : i + 1 < ncross + nself ? &fs->enc_self[i + 1 - ncross] : nullptr;
+    FsLN after{s.xn, D, nb ? &nb->norm : nullptr, 0, true};
+    BlockIo io;
+    io.xn_ready = xn_ready;
+    io.after = nb ? &after : nullptr;
+    if (cross) {
+      if (i == 0 && fold0) io.q_table = fs->enc_q0, io.x_table = fs->latents;
+      TRY(run_cross_block(b, z, F, L, ctx, N, in->mask, s, st, io));
+    } else {
+      TRY(run_self_block(b, z, F, L, s, st, io));
+    }
+    xn_ready = nb != nullptr;
+  }
   // quant: Linear -> LayerNorm(no affine) (lightning_base.py:24-27)
-  TRY(fs_linear(fs->quant, z, D, s.xn, D, FL, false, nullptr, 0, nullptr, 0, 0, st));
-  TRY(fs_layernorm(s.xn, D, 0, latents_out, D, nullptr, FL, D, 1e-5f, st));
+  const FsLN qln{latents_out, D, nullptr, 0, false};
+  TRY(fs_linear(fs->quant, z, D, s.xn, D, FL, false, nullptr, 0, nullptr, 0, 0, st, &qln));
   return 0;
 }
 
@@ -1722,22 +1870,50 @@ static int decode_impl(lamslide_first_stage* fs, const float* latents, const int
     *bytes = bp.off;
     return 0;
   }
-  const int TB = 256;
-  // post_quant: LayerNorm(no affine) -> Linear (lightning_base.py:28-31)
+  const int nself = (int)fs->dec_self.size(), ncross = (int)fs->dec_cross.size();
+  // queries = query_mlp(entity_embedding(entities)) (decoder.py:83-86; Dropout inactive in eval) depend on the entity id only: with
+  // the folded tables (q_tab, its LayerNorm and to_q of the output block) the per-row matrix is built only as the context of
+  // decoder cross blocks, which no shipped config has
+  const bool folded = fs->dec_q_tab != nullptr;
+  if (!folded || ncross > 0) {
+    if (folded) {
+      TRY(fs_gather(Q, dq, 0, fs->dec_q_tab, dq, (const long long*)entities, R, st));
+    } else {
+      TRY(fs_gather(ent, E, 0, fs->ent_table, E, (const long long*)entities, R, st));
+      TRY(fs_linear(fs->query_mlp, ent, E, Q, dq, R, false, nullptr, 0, nullptr, 0, 0, st));
+    }
+  }
+  // post_quant: LayerNorm(no affine) -> Linear (lightning_base.py:28-31), leaving the first block's pre-norm in its xn
   TRY(fs_layernorm(latents, D, 0, zl, D, nullptr, FL, D, 1e-5f, st));
-  TRY(fs_linear(fs->post_quant, zl, D, z, D, FL, false, nullptr, 0, nullptr, 0, 0, st));
-  // queries = query_mlp(entity_embedding(entities)) (decoder.py:83-86; Dropout inactive in eval)
-  gather_cols_kernel<<<cdiv(R * E, TB), TB, 0, st>>>(ent, E, 0, fs->ent_table, E, (const long long*)entities, R);
-  LAUNCH_CHECK();
-  TRY(fs_linear(fs->query_mlp, ent, E, Q, dq, R, false, nullptr, 0, nullptr, 0, 0, st));
-  for (auto& b : fs->dec_self) TRY(run_self_block(b, z, F, L, s_self, st));
-  for (auto& b : fs->dec_cross) TRY(run_cross_block(b, z, F, L, Q, N, nullptr, s_cross, st));
+  {
+    const AttnBlockW* nb = nself > 0 ? &fs->dec_self[0] : ncross > 0 ? &fs->dec_cross[0] : nullptr;
+    const FsLN after{nself > 0 ? s_self.xn : s_cross.xn, D, nb ? &nb->norm : nullptr, 0, true};
+    TRY(fs_linear(fs->post_quant, zl, D, z, D, FL, false, nullptr, 0, nullptr, 0, 0, st, nb ? &after : nullptr));
+  }
+  for (int i = 0; i < nself + ncross; ++i) {
+    const bool self = i < nself;
+    const AttnBlockW& b = self ? fs->dec_self[i] : fs->dec_cross[i - nself];
+    const AttnBlockW* nb = i + 1 < nself ? &fs->dec_self[i + 1] : i + 1 < nself + ncross ? &fs->dec_cross[i + 1 - nself] : nullptr;
+    const bool next_self = i + 1 < nself;
+    FsLN after{next_self ? s_self.xn : s_cross.xn, D, nb ? &nb->norm : nullptr, 0, true};
+    BlockIo io;
+    io.xn_ready = true;
+    io.after = nb ? &after : nullptr;
+    if (self) TRY(run_self_block(b, z, F, L, s_self, st, io));
+    else TRY(run_cross_block(b, z, F, L, Q, N, nullptr, s_cross, st, io));
+  }
+  // output block: queries attend to the (extended) latents.  The LayerNorm of its context runs in the epilogue of the layer that
+  // produces the context when that is the extender (per 'D'-wide token of the [F*L, n*D] row = the [F, L*n, D] token matrix).
+  BlockIo io;
   const float* kvsrc = z;
   if (c.dec_query_splitter) {
-    TRY(fs_linear(fs->extender, z, D, zk, D * c.dec_num_split, FL, false, nullptr, 0, nullptr, 0, 0, st));
+    const FsLN kln{s_out.cn, D * c.dec_num_split, &fs->out_block.norm_ctx, D, false};
+    TRY(fs_linear(fs->extender, z, D, zk, D * c.dec_num_split, FL, false, nullptr, 0, nullptr, 0, 0, st, &kln));
     kvsrc = zk;
+    io.cn_ready = true;
   }
-  TRY(run_cross_block(fs->out_block, Q, F, N, kvsrc, Lk, nullptr, s_out, st));
+  if (folded) io.q_table = fs->dec_qq_tab, io.q_index = (const long long*)entities, io.x_table = fs->dec_q_tab, io.x_index = (const long long*)entities;
+  TRY(run_cross_block(fs->out_block, Q, F, N, kvsrc, Lk, nullptr, s_out, st, io));
   for (int i = 0; i < c.n_outputs; ++i) {
     if (!outs[i]) continue;
     TRY(fs_linear(fs->head0[i], Q, dq, t1, dq, R, true, nullptr, 0, nullptr, 0, 0, st));
@@ -1794,6 +1970,26 @@ extern "C" int lamslide_debug_fs_linear(const float* x, const float* w_host, con
   if (path == 0) TRY(prepare_tc5(arena, w_host, &L));
   TRY(fs_linear(L, x, ldx, y, ldy, rows, act, res, ldr, rowadd, period, ldra, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));  // the weights die with `arena`
+  return 0;
+}
+
+// the same layer followed by the LayerNorm of its result (the successor's pre-norm; in the kernel's epilogue where it can hold a group):
+// ln_out [rows, N] = LN over groups of `group` columns (0: the row) [* ln_w + ln_b]; y is skipped when y_needed == 0 and the LN is fused
+extern "C" int lamslide_debug_fs_linear_ln(const float* x, const float* w_host, const float* bias_host, float* y, float* ln_out,
+                                           const float* ln_w, const float* ln_b, int32_t group, int32_t rows, int32_t N, int32_t K,
+                                           const float* res, int32_t y_needed, void* stream) {
+  if (!x || !w_host || !y || !ln_out || rows <= 0 || N <= 0 || K <= 0) return fail(LAMSLIDE_ERR_INVALID, "bad argument");
+  Arena arena;
+  LinW L;
+  TRY(arena.upload_f32(w_host, (size_t)N * K, &L.w));
+  if (bias_host) TRY(arena.upload_f32(bias_host, N, &L.b));
+  L.out = N, L.in = K;
+  TRY(prepare_tc5(arena, w_host, &L));
+  LNW n;
+  n.w = const_cast<float*>(ln_w), n.b = const_cast<float*>(ln_b);
+  const FsLN ln{ln_out, N, ln_w ? &n : nullptr, group, y_needed != 0};
+  TRY(fs_linear(L, x, K, y, N, rows, 0, res, N, nullptr, 0, 0, (cudaStream_t)stream, &ln));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
 

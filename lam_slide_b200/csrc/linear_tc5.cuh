@@ -14,13 +14,23 @@
 //   warps 6..13 epilogue, thread = (row, column half): tcgen05.ld -> bias / GELU / row-add / residual / SiLU -> global fp32
 //
 // Persistent (one CTA per SM, tiles n-fastest so the CTAs that share an A tile run together and HBM sees it once); the epilogue of
-// tile i overlaps the main loop of tile i + 1 through the second accumulator.  The mma.sync 3xTF32 kernel this replaces reached
-// ~100-120 TFLOP/s of tensor work (every fragment split in registers, 24 MMAs per k8 step per warp); the layers here are
-// 2.4 - 34 GFLOP x 3 over 0.1 - 0.5 GB, i.e. HBM-bound once the tensor work runs at tcgen05 rate.
+// tile i overlaps the main loop of tile i + 1 through the second accumulator.  An optional LayerNorm of the result (the next
+// sub-layer's pre-norm) runs in the epilogue: the finished values go back into the accumulator columns (tcgen05.st), a thread — or
+// the two threads that share a row, through shared memory — merges shifted one-pass statistics, and a second pass over TMEM writes
+// the normalised row.
+// Measured (B200, 4AA first stage, 256 k entity rows / 128 k latent rows; scripts/gpu_l5var.sh switches parts of the kernel off):
+//   the mma.sync 3xTF32 kernel this replaces reached ~100 - 120 TFLOP/s of tensor work (every fragment split in registers):
+//   net_merge.2 [256 -> 256] 682 us, encoder.mlp.0 [384 -> 96] 466 us, decoder layers [128 -> 128] 195 us;
+//   this kernel: 250 / 149 / 125 us in the step (194 / 142 / 93 us alone).  With the epilogue reduced to releasing the accumulator:
+//   142 / 126 / 47 us; additionally without the splitters and the weight tiles (A stream + MMAs only): 127 / 111 / 44 us — i.e. the
+//   A stream of 2 - 3 stages x 16 KB per SM sustains ~3 TB/s, and the epilogue costs as much again on the narrow layers.  Both are
+//   latency, not bandwidth: tensor pipe 22 % busy, DRAM 25 %, LSU 30 %.  Next: weights resident in shared memory for the narrow
+//   layers (frees the ring for 4 - 6 A stages), 16 epilogue warps.
 #pragma once
 #include <cuda.h>
 
 #include "first_stage.cuh"
+#include "gemm_ws.cuh"
 #include "ptx.cuh"
 
 namespace lam {
@@ -33,11 +43,12 @@ template <int BN>
 struct L5Cfg {
   static constexpr int kBBytes = BN * kL5BK * 4;
   static constexpr int kStageBytes = 2 * kL5ABytes + 2 * kBBytes;  // A (-> hi), A lo, W hi, W lo
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;
   static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr uint32_t kTmemCols = 2 * kAccStride;
-  static constexpr int kSmem = kStages * kStageBytes + 256 + 1024;
+  // stages | barriers | LN statistics [2 halves][128 rows] | staging boxes of the epilogue warps (8 x 4 KB)
+  static constexpr int kSmem = kStages * kStageBytes + 256 + 2048 + 8 * 4096;
 };
 
 // kind::tf32, TF32 x TF32 -> FP32, both operands K-major (cute::UMMA::InstrDescriptor: a_format = b_format = 2)
@@ -74,14 +85,17 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                   const __grid_constant__ CUtensorMap tm_wlo, LinearArgs a, int m_tiles, int n_tiles) {
   using C = L5Cfg<BN>;
   static_assert(BN % 32 == 0 && BN <= 256, "two column halves of 16-column chunks");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_l5[];
+  uint8_t* smem = smem_l5;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128-byte swizzle atoms need 1024-byte aligned tiles
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
   uint64_t* split_bar = full_bar + C::kStages;
   uint64_t* empty_bar = split_bar + C::kStages;
   uint64_t* acc_full = empty_bar + C::kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float2* ln_stats = reinterpret_cast<float2*>(smem + C::kStages * C::kStageBytes + 256);
+  uint8_t* stage_box = smem + C::kStages * C::kStageBytes + 256 + 2048;  // 8 epilogue warps x (output box | residual box) of 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (a.K + kL5BK - 1) / kL5BK;
@@ -118,10 +132,12 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
           uint8_t* st = smem + s * C::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], kL5ABytes + 2 * C::kBBytes);
+          mbar_arrive_expect_tx(&full_bar[s], (a.debug & 8) ? kL5ABytes : kL5ABytes + 2 * C::kBBytes);
           tma_load_2d(&tm_a, &full_bar[s], st, kb * kL5BK, m0);
-          tma_load_2d(&tm_whi, &full_bar[s], st + 2 * kL5ABytes, kb * kL5BK, n0);
-          tma_load_2d(&tm_wlo, &full_bar[s], st + 2 * kL5ABytes + C::kBBytes, kb * kL5BK, n0);
+          if (!(a.debug & 8)) {
+            tma_load_2d(&tm_whi, &full_bar[s], st + 2 * kL5ABytes, kb * kL5BK, n0);
+            tma_load_2d(&tm_wlo, &full_bar[s], st + 2 * kL5ABytes + C::kBBytes, kb * kL5BK, n0);
+          }
         }
         __syncwarp();
         if (++s == C::kStages) s = 0, ph ^= 1;
@@ -172,6 +188,7 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         float4* lo = reinterpret_cast<float4*>(smem + s * C::kStageBytes + kL5ABytes);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          if (a.debug & 4) break;
           const int i = t + 128 * j;
           const float4 v = hi[i];
           float4 h, l;
@@ -188,54 +205,122 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else {
     // ===== epilogue: thread = (row, column half) =====
+    // Global memory is touched in row-contiguous 64-byte segments only: a 32-row x 16-column box goes through the warp's staging
+    // box in shared memory, written by thread = row and read back by lane = (row % 8, 16-byte piece), 8 rows per instruction (and the
+    // other way round for the residual).  With thread = row accesses straight to global memory every instruction touched 32 rows
+    // (32 L1 wavefronts for 512 bytes) and the LSU, not HBM, bounded the narrow layers.
     const int quarter = warp & 3, half = (warp - 6) >> 2;
     constexpr int HW = BN / 2;
-    const bool vec = (a.N & 3) == 0 && (a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.Y) & 15) == 0 &&
+    const bool ln = a.ln_out != nullptr;
+    const bool vec = (a.N & 3) == 0 && (!a.Y || ((a.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(a.Y) & 15) == 0)) &&
                      (!a.res || ((a.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0)) &&
                      (!a.rowadd || ((a.ldra & 3) == 0 && (reinterpret_cast<uintptr_t>(a.rowadd) & 15) == 0)) &&
-                     (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+                     (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) &&
+                     (!ln || ((a.ld_ln & 3) == 0 && (reinterpret_cast<uintptr_t>(a.ln_out) & 15) == 0 &&
+                              (!a.ln_w || ((reinterpret_cast<uintptr_t>(a.ln_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ln_b) & 15) == 0 &&
+                                           (a.ln_group & 3) == 0))));
+    const uint32_t box_st = smem_u32(stage_box) + (warp - 6) * 4096, box_rs = box_st + 2048;
+    const int rr0 = lane >> 2, pc = lane & 3;  // coalesced mapping: rows rr0 + 8 i (i < 4), 16-byte piece pc of the 64-byte row segment
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN + half * HW;
-      const int row = m0 + quarter * 32 + lane;
+      const int row0w = m0 + quarter * 32;
+      const int row = row0w + lane;
+      const uint32_t taddr = tmem_base + acc * C::kAccStride + half * HW + (static_cast<uint32_t>(quarter * 32) << 16);
+      const float* res_row = a.res ? a.res + (size_t)(a.res_idx ? (row < a.rows ? a.res_idx[row] : 0) : row) * a.ldr : nullptr;
+      const float* add_row = a.rowadd ? a.rowadd + (size_t)(row % a.rowadd_period) * a.ldra : nullptr;
+      float* y_row = a.Y ? a.Y + (size_t)row * a.ldy : nullptr;
+      // rows of the coalesced mapping
+      bool rok[4];
+      const float* rsrc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rw = row0w + rr0 + 8 * i;
+        rok[i] = rw < a.rows;
+        rsrc[i] = (a.res && rok[i]) ? a.res + (size_t)(a.res_idx ? a.res_idx[rw] : rw) * a.ldr + pc * 4 : nullptr;
+      }
+      float4 rp[4];
+      auto res_fetch = [&](int n) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rp[i] = rsrc[i] ? *reinterpret_cast<const float4*>(rsrc[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      // bias of a chunk: fetched one chunk ahead (with ~220 KB of shared memory per CTA there is no L1 to speak of: every fetch is an
+      // L2 round trip that would otherwise sit between the accumulator load and the first add of every chunk)
+      float4 bp[4];
+      auto bias_fetch = [&](int n) {
+        const bool ok = a.bias && vec && n + 16 <= a.N;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bp[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.bias + n) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if (a.res && vec && n0 + 16 <= a.N) res_fetch(n0);  // in flight while the accumulator is being finished
+      bias_fetch(n0);
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + acc * C::kAccStride + half * HW + (static_cast<uint32_t>(quarter * 32) << 16);
-      const float* res_row = a.res ? a.res + (size_t)row * a.ldr : nullptr;
-      const float* add_row = a.rowadd ? a.rowadd + (size_t)(row % a.rowadd_period) * a.ldra : nullptr;
-      float* y_row = a.Y + (size_t)row * a.ldy;
+      float kshift = 0.f, s1 = 0.f, s2 = 0.f;  // shifted one-pass statistics of this thread's columns (LN mode)
+      int cnt = 0;
+      uint32_t rn[16];
+      tmem_ld16(taddr, rn);
 #pragma unroll 1
-      for (int c = 0; c < HW; c += 16) {
+      for (int c = 0; c < ((a.debug & 2) ? 0 : HW); c += 16) {
         uint32_t r[16];
-        tmem_ld16(taddr + c, r);
-        tmem_ld_wait();
         const int n = n0 + c;
-        if (row >= a.rows || n >= a.N) continue;
-        if (vec && n + 16 <= a.N) {
+        const bool full = vec && n + 16 <= a.N;  // warp-uniform
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = rn[j];
+        if (c + 16 < HW) tmem_ld16(taddr + c + 16, rn);  // next chunk's accumulator columns in flight under this chunk's work
+        if (full && a.res) {
+          __syncwarp();  // the previous chunk's reads of the residual box are done
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_shared_v4(box_rs + stage_off64(rr0 + 8 * i, pc), __float_as_uint(rp[i].x), __float_as_uint(rp[i].y), __float_as_uint(rp[i].z),
+                         __float_as_uint(rp[i].w));
+          __syncwarp();
+          if (c + 16 < HW && n + 32 <= a.N) res_fetch(n + 16);
+        }
+        if (full) {
+          if (a.Y) __syncwarp();  // the previous chunk's reads of the output box are done
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            if (a.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n + j));
+            {
+              const float4 b = bp[j >> 2];
               v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+              if (j == 12 && c + 16 < HW) bias_fetch(n + 16);  // the next chunk's bias: in flight under the rest of this chunk
             }
             if (a.gelu == 1) v.x = gelu_erf(v.x), v.y = gelu_erf(v.y), v.z = gelu_erf(v.z), v.w = gelu_erf(v.w);
             if (add_row) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(add_row + n + j));
               v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
             }
-            if (res_row) {
-              const float4 b = *reinterpret_cast<const float4*>(res_row + n + j);
+            if (a.res) {
+              const float4 b = ld_shared_f4(box_rs + stage_off64(lane, j >> 2));
               v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
             }
             if (a.gelu == 2) {
               v.x = v.x / (1.0f + expf(-v.x)), v.y = v.y / (1.0f + expf(-v.y));
               v.z = v.z / (1.0f + expf(-v.z)), v.w = v.w / (1.0f + expf(-v.w));
             }
-            *reinterpret_cast<float4*>(y_row + n + j) = v;
+            if (a.Y) st_shared_v4(box_st + stage_off64(lane, j >> 2), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+            if (ln) {
+              if (cnt == 0 && j == 0) kshift = v.x;
+              const float d0 = v.x - kshift, d1 = v.y - kshift, d2 = v.z - kshift, d3 = v.w - kshift;
+              s1 += (d0 + d1) + (d2 + d3);
+              s2 = fmaf(d0, d0, s2), s2 = fmaf(d1, d1, s2), s2 = fmaf(d2, d2, s2), s2 = fmaf(d3, d3, s2);
+              r[j] = __float_as_uint(v.x), r[j + 1] = __float_as_uint(v.y), r[j + 2] = __float_as_uint(v.z), r[j + 3] = __float_as_uint(v.w);
+            }
           }
-        } else {
+          if (ln) cnt += 16;
+          if (a.Y) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 w = ld_shared_f4(box_st + stage_off64(rr0 + 8 * i, pc));
+              if (rok[i] && !(a.debug & 1)) *reinterpret_cast<float4*>(a.Y + (size_t)(row0w + rr0 + 8 * i) * a.ldy + n + pc * 4) = w;
+            }
+          }
+        } else if (row < a.rows && n < a.N) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             if (n + j >= a.N) continue;
@@ -244,7 +329,83 @@ linear_tc5_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             if (add_row) v += __ldg(add_row + n + j);
             if (res_row) v += res_row[n + j];
             if (a.gelu == 2) v = v / (1.0f + expf(-v));
-            y_row[n + j] = v;
+            if (y_row) y_row[n + j] = v;
+            if (ln) {
+              if (cnt == 0) kshift = v;
+              const float d = v - kshift;
+              s1 += d, s2 = fmaf(d, d, s2), ++cnt;
+              r[j] = __float_as_uint(v);
+            }
+          }
+        }
+        if (ln) tmem_st16(taddr + c, r);  // the finished values go back into the accumulator columns for the second pass
+      }
+      if (a.debug & 2) tmem_ld_wait();
+      if (ln) {
+        // ---- LayerNorm of the values just produced.  Group = this thread's column half: local statistics.  Group = the row: the two
+        // halves merge (mean, M2, count) through shared memory (Chan et al.).
+        tmem_st_wait();
+        float mean = 0.f, m2 = 0.f;
+        if (cnt > 0) {
+          mean = kshift + s1 / (float)cnt;
+          m2 = fmaxf(s2 - s1 * s1 / (float)cnt, 0.f);
+        }
+        float tot = (float)cnt;
+        if (a.ln_group == 0) {
+          ln_stats[half * 128 + quarter * 32 + lane] = make_float2(mean, m2);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float2 o = ln_stats[(half ^ 1) * 128 + quarter * 32 + lane];
+          const int n_other = half == 0 ? min(max(a.N - HW, 0), HW) : min(a.N, HW);  // single n-tile: the other half's column count
+          const float ca = (float)cnt, cb = (float)n_other;
+          tot = ca + cb;
+          if (tot > 0.f) {
+            const float delta = o.x - mean;
+            const float new_mean = mean + delta * (cb / tot);
+            m2 = m2 + o.y + delta * delta * (ca * cb / tot);
+            mean = new_mean;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // both halves have read before the next tile's statistics are written
+        }
+        const float rstd = rsqrtf(m2 / fmaxf(tot, 1.f) + a.ln_eps);
+        float* o_row = a.ln_out + (size_t)row * a.ld_ln;
+        uint32_t r0buf[16];
+        tmem_ld16(taddr, r0buf);
+#pragma unroll 1
+        for (int c = 0; c < HW; c += 16) {
+          uint32_t r[16];
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = r0buf[j];
+          if (c + 16 < HW) tmem_ld16(taddr + c + 16, r0buf);
+          const int n = n0 + c;
+          const bool full = vec && n + 16 <= a.N;
+          const int wbase = a.ln_group ? n % a.ln_group : n;  // 16-column chunks never straddle a group (group % 16 == 0 or one chunk)
+          if (full) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 y;
+              y.x = (__uint_as_float(r[j]) - mean) * rstd, y.y = (__uint_as_float(r[j + 1]) - mean) * rstd;
+              y.z = (__uint_as_float(r[j + 2]) - mean) * rstd, y.w = (__uint_as_float(r[j + 3]) - mean) * rstd;
+              if (a.ln_w) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(a.ln_w + wbase + j)), b = __ldg(reinterpret_cast<const float4*>(a.ln_b + wbase + j));
+                y.x = fmaf(y.x, w.x, b.x), y.y = fmaf(y.y, w.y, b.y), y.z = fmaf(y.z, w.z, b.z), y.w = fmaf(y.w, w.w, b.w);
+              }
+              st_shared_v4(box_st + stage_off64(lane, j >> 2), __float_as_uint(y.x), __float_as_uint(y.y), __float_as_uint(y.z), __float_as_uint(y.w));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 w = ld_shared_f4(box_st + stage_off64(rr0 + 8 * i, pc));
+              if (rok[i]) *reinterpret_cast<float4*>(a.ln_out + (size_t)(row0w + rr0 + 8 * i) * a.ld_ln + n + pc * 4) = w;
+            }
+          } else if (row < a.rows && n < a.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n + j >= a.N) continue;
+              const float t = (__uint_as_float(r[j]) - mean) * rstd;
+              o_row[n + j] = a.ln_w ? fmaf(t, __ldg(a.ln_w + wbase + j), __ldg(a.ln_b + wbase + j)) : t;
+            }
           }
         }
       }

@@ -377,3 +377,46 @@ def test_fused_mlp_drain_writes_next_layernorm_modulate(rows, H, M, rps):
     err = (u.double() - ref).abs()
     assert float((err / (ref.abs() + 1.0)).max()) < 2 ** -8  # one bf16 rounding of the output
     assert float(err.mean() / ref.abs().mean()) < 2e-3
+
+
+@pytest.mark.parametrize("rows,N,K,group,affine,res,y_needed", [
+    (5000, 96, 96, 0, True, True, 1),      # to_out + residual -> ff.norm (row LayerNorm, the two column halves merge their statistics)
+    (3001, 128, 32, 0, True, True, 1),     # decoder output block
+    (700, 32, 32, 0, True, False, 1),      # D = 32 configs
+    (4000, 96, 96, 0, False, False, 0),    # quant: Linear -> LayerNorm without affine, only the normalised output is needed
+    (2000, 768, 96, 96, True, False, 0),   # extender: LayerNorm per 96-wide token of the row (norm_context of the output block)
+    (900, 384, 96, 0, True, False, 1),     # a row wider than one tile: the LayerNorm runs as its own launch
+    (1, 96, 96, 0, True, True, 1),
+    (19000, 128, 128, 0, True, True, 1),   # more tiles than SMs
+])
+def test_first_stage_linear_with_layernorm_epilogue(rows, N, K, group, affine, res, y_needed):
+    """A first-stage layer whose result feeds a LayerNorm (torch_modules.py PreNorm of the next sub-layer, lightning_base.py quant,
+    decoder.py extender -> norm_context): y and LN(y) against fp64."""
+    L_ = _lib()
+    lib = L_.load()
+    g = torch.Generator(device="cpu").manual_seed(rows + N + K + group)
+    x = torch.randn(rows, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).contiguous()
+    b = (0.3 * torch.randn(N, generator=g) + 0.5).contiguous()
+    gw = max(group, 1) if group else N
+    lw = (1.0 + 0.2 * torch.randn(gw, generator=g)).cuda()
+    lb = (0.2 * torch.randn(gw, generator=g)).cuda()
+    r0 = (3.0 * torch.randn(rows, N, generator=g) + 2.0).cuda()
+    y = r0.clone()
+    out = torch.full((rows, N), float("nan"), device="cuda")
+    L_.check(lib.lamslide_debug_fs_linear_ln(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), out.data_ptr(),
+                                             lw.data_ptr() if affine else 0, lb.data_ptr() if affine else 0, group, rows, N, K,
+                                             y.data_ptr() if res else 0, y_needed, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().cuda().t() + b.double().cuda()
+    if res:
+        ref = ref + r0.double()
+    if y_needed:
+        assert max_rel(y, ref) < 5e-6
+    t = ref.reshape(rows, N // gw, gw)
+    ln = (t - t.mean(-1, keepdim=True)) / torch.sqrt(t.var(-1, unbiased=False, keepdim=True) + 1e-5)
+    if affine:
+        ln = ln * lw.double() + lb.double()
+    ln = ln.reshape(rows, N)
+    assert torch.isfinite(out).all()
+    assert float((out.double() - ln).abs().max()) < 2e-5

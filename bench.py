@@ -181,7 +181,7 @@ def secondary_lines(P, _lib, args, dev):
         randomize_zero_init(m, seed=1)
         return cfg, m.to(dev)
 
-    def time_sample(m, cfg, B, steps, warm, graph):
+    def time_sample(m, cfg, B, steps, warm, graph, shares=False):
         batch = {k: v.to(dev) for k, v in synthetic_batch(cfg, B, seed=2000 + B).items()}
         L, D = cfg["first_stage"]["encoder"]["num_latents"], cfg["backbone"]["in_dim"]
         noise = torch.randn(B, cfg["T"], L, D, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
@@ -199,14 +199,21 @@ def secondary_lines(P, _lib, args, dev):
         ms = e0.elapsed_time(e1) / steps
         launches = _lib.launch_count() / steps
         m.use_cuda_graphs = False
-        return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
-                "launches_per_step": launches if not graph else "1 graph replay"}
+        out = {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+               "launches_per_step": launches if not graph else "1 graph replay"}
+        if shares and not graph:  # live CUDA-event time per kernel class over one more step
+            _lib.profile_begin()
+            m.sample(dict(batch), noise=noise)
+            prof = _lib.profile_end()
+            tot = sum(v["ms"] for v in prof.values())
+            out["kernel_time_shares"] = {k: round(v["ms"] / tot, 4) for k, v in prof.items() if v["ms"] > 0}
+        return out
 
     from lam_slide_b200.configs import flops_per_trajectory
     out = {}
     for name in ("nba", "pedestrian"):
         cfg, m = build(name, 10)
-        eager = time_sample(m, cfg, 1024, 10, 3, False)
+        eager = time_sample(m, cfg, 1024, 10, 3, False, shares=True)
         graphed = time_sample(m, cfg, 1024, 10, 3, True)
         eager["tflops"] = flops_per_trajectory(cfg, 10) * eager["value"] / 1e12
         graphed["tflops"] = flops_per_trajectory(cfg, 10) * graphed["value"] / 1e12

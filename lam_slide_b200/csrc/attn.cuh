@@ -535,4 +535,94 @@ attn_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   }
 }
 
+// Short sequences with ANY token stride (temporal attention of the small-T configurations: NBA / pedestrian T = 20, MD17 T = 30, whose
+// tokens of a sequence lie L rows apart): one warp per (sequence, group of HG heads).  The warp copies the q | k | v pieces of its heads
+// (HG * HD bf16 = 64 - 192 contiguous bytes per token and part) into shared memory, every lane then serves (query, head) items out of
+// shared memory exactly as attn_rows_kernel, and the output pieces go out with 16-byte stores.  attn_small_kernel (one thread per item
+// gathering 32-byte pieces of every key from global memory) moved 13 x the bytes: 380 us per NBA launch (B = 1024) for 336 MB.
+template <int HD, int HG>
+__global__ void __launch_bounds__(256)
+attn_short_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, int heads, SeqMap sm, long long n_work) {
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  constexpr int CH = HD / 8;       // 16-byte units per head
+  constexpr int PU = HG * CH;      // 16-byte units per token and part (q, k or v)
+  const int S = sm.S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 8 + warp;
+  if (w >= n_work) return;
+  const int groups = heads / HG;
+  const int z = (int)(w / groups), hg = (int)(w % groups);
+  const long long base = sm.base(z);
+  uint4* my = reinterpret_cast<uint4*>(attn_smem) + (size_t)warp * S * 3 * PU;
+  for (int i = lane; i < S * 3 * PU; i += 32) {
+    const int tok = i / (3 * PU), r = i % (3 * PU), part = r / PU, u = r % PU;
+    my[i] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(base + (long long)tok * sm.seq_stride) * 3 * H + part * H + hg * HG * HD) + u);
+  }
+  __syncwarp();
+  for (int item = lane; item < S * HG; item += 32) {
+    const int sq = item / HG, hh = item % HG;
+    float q[HD], acc[HD];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const uint4 v = my[sq * 3 * PU + hh * CH + c];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h2[i]);
+        q[c * 8 + 2 * i] = f.x, q[c * 8 + 2 * i + 1] = f.y;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int sk = 0; sk < S; ++sk) {
+      const uint4* kp = my + sk * 3 * PU + PU + hh * CH;
+      const uint4* vp = kp + PU;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const uint4 v = kp[c];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h2[i]);
+          dot = fmaf(q[c * 8 + 2 * i], f.x, dot);
+          dot = fmaf(q[c * 8 + 2 * i + 1], f.y, dot);
+        }
+      }
+      const float mn = fmaxf(m, dot);
+      const float corr = fast_exp2(m - mn);
+      const float pr = fast_exp2(dot - mn);
+      m = mn;
+      l = l * corr + pr;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const uint4 v = vp[c];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h2[i]);
+          acc[c * 8 + 2 * i] = fmaf(pr, f.x, acc[c * 8 + 2 * i] * corr);
+          acc[c * 8 + 2 * i + 1] = fmaf(pr, f.y, acc[c * 8 + 2 * i + 1] * corr);
+        }
+      }
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {  // over this item's own q slot (no other lane reads it)
+      uint4 v;
+      v.x = pack_bf16x2(acc[c * 8 + 0] * inv, acc[c * 8 + 1] * inv);
+      v.y = pack_bf16x2(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
+      v.z = pack_bf16x2(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
+      v.w = pack_bf16x2(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
+      my[sq * 3 * PU + hh * CH + c] = v;
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < S * PU; i += 32) {
+    const int tok = i / PU, u = i % PU;
+    *reinterpret_cast<uint4*>(out + (size_t)(base + (long long)tok * sm.seq_stride) * ldo + hg * HG * HD + u * 8) = my[tok * 3 * PU + u];
+  }
+}
+
 }  // namespace lam

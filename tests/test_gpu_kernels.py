@@ -420,3 +420,34 @@ def test_first_stage_linear_with_layernorm_epilogue(rows, N, K, group, affine, r
     ln = ln.reshape(rows, N)
     assert torch.isfinite(out).all()
     assert float((out.double() - ln).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,L,H,heads", [
+    (2, 20, 8, 256, 16),     # NBA temporal: hd 16, groups of 4 heads
+    (3, 20, 2, 128, 4),      # pedestrian temporal: hd 32
+    (2, 30, 192, 256, 16),   # MD17 temporal: token stride 192
+    (2, 20, 8, 384, 16),     # hd 24
+    (2, 25, 5, 96, 6),       # head count not a multiple of 4: groups of 2
+    (1, 32, 3, 256, 16), (5, 1, 4, 256, 16), (1, 2, 1, 128, 4),
+])
+def test_short_strided_attention(B, T, L, H, heads):
+    """Temporal attention of the small-T configurations (sequence over T, tokens L rows apart): the warp-per-(sequence, head group)
+    kernel against the softmax reference, and the launch must be that kernel."""
+    L_ = _lib()
+    lib = L_.load()
+    n = B * T * L
+    g = torch.Generator(device="cpu").manual_seed(n + H + 3)
+    qkv = (torch.randn(n, 3 * H, generator=g)).to(torch.bfloat16).cuda()
+    ldo = H + 64
+    out = torch.zeros(n, ldo, dtype=torch.bfloat16, device="cuda")
+    L_.kernel_count("attn_short", reset=True)
+    L_.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, L, H, heads, ldo, 1, 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    if L > 1 and heads >= 8:
+        assert L_.kernel_count("attn_short") == 1
+    ref = _attention_reference(qkv, B, T, L, H, heads, True)
+    got = out[:, :H].float()
+    assert torch.isfinite(got).all()
+    assert float(out[:, H:].float().abs().max()) == 0.0
+    assert max_rel(got, ref) < 2e-2
+    assert float((got - ref).abs().mean() / ref.abs().mean()) < 5e-3

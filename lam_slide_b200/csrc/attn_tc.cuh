@@ -38,7 +38,11 @@
 // idle pipes: 565 us per 4AA launch; half-step phase barriers between the groups: 578 us; a baton that lets one group compute at a
 // time: 650 - 690 us (one warp per scheduler reaches 3.7 exp/clk, two 5); three-slot rings of 64-key chunks: 584 - 762 us (twice the
 // hand-shakes per exponential); all 64 logits of a thread loaded at once to release S earlier: 563 us (register spills at the
-// 96-register limit of 20 warps).  This version: 524 us against 661 us for the mma.sync kernel; the exponent engine alone would need 390 us.
+// 96-register limit of 20 warps); Q K^T and P V issued by separate warps (Q K^T issuer also loading its group's query tiles, one P V
+// issuer for both groups): 539 us — the issue time of the MMA warp is not on the critical loop.  This version: 524 us against 661 us
+// for the mma.sync kernel; the exponent engine alone would need 390 us, and the pipeline WITHOUT any exponential (variant 4: logits
+// passed through) takes 360 us: per chunk step and group ~1500 cycles of tcgen05.ld / wait / st / mbarrier latency in series in every
+// softmax warp, of which the exponentials hide about half.
 // After the last chunk of a tile the group reads O (tcgen05.ld), scales by 1 / row sum and stores bf16; tensor pipe ~25 % busy.
 // The contraction of S runs over d padded to a multiple of 16: the Q image carries zero chunks there, so whatever (finite) bytes
 // the K image has at those offsets do not matter; O is computed with N = 32, the columns >= hd are ignored.

@@ -197,7 +197,8 @@ int lamslide_debug_gemm(const void* a_bf16, const void* b_bf16, const float* bia
 /* the attention kernels in isolation on a token-major qkv buffer [tokens, 3H] bf16 -> out [tokens, ldo] bf16.
  * temporal != 0: sequences over T (stride L); else over L.  mode: 0 = automatic choice, 1 = streaming flash kernel
  * (running maximum), 2 = whole-sequence kernel (K/V resident in shared memory, no running maximum), 3 = tcgen05 kernel
- * (S = Q K^T and O = P V on the 5th-gen tensor cores, accumulators in TMEM; 3 + 4 v probes descriptor variant v). */
+ * (S = Q K^T and O = P V on the 5th-gen tensor cores, accumulators in TMEM; 3 + 4 v selects variant v: 1 - 4 exponential mixes of
+ * attn_tc.cuh (all MUFU, 2 / 8, 4 / 8 polynomial, none), 5 / 6 its cycle trace, 7 - 10 the three-group kernel of attn_tc3.cuh). */
 int lamslide_debug_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t L, int32_t H, int32_t heads,
                              int32_t ldo, int32_t temporal, int32_t mode, void* stream);
 /* linear1 of one ParallelMLPAttentionV2 block with its fused epilogue (mmdit.py:241-247: bias, QK-RMSNorm, RoPE, q pre-scale,

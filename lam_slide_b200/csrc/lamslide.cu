@@ -25,6 +25,7 @@
 #include "mlp_fused.cuh"
 #include "attn.cuh"
 #include "attn_tc.cuh"
+#include "attn_tc3.cuh"
 #include "elementwise.cuh"
 #include "first_stage.cuh"
 #include "linear_tc5.cuh"
@@ -740,6 +741,16 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
   if (tc_forced && !tc_ok) return fail(LAMSLIDE_ERR_INVALID, "sequence length %d too long for the tcgen05 attention kernel", sm.S);
   if (tc_ok) {
     const int variant = tc_forced ? (mode >> 2) : env_int("LAMSLIDE_ATTN_TC_VARIANT", 0);
+    if (variant >= 7 && variant <= 10) {  // three tile groups, P in place (attn_tc3.cuh): 7 shipped mix, 8 no exponentials, 9 / 10: 4 / 2 of 8 pairs polynomial
+      void (*k3)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int, int) =
+          variant == 8 ? attn_tc3_kernel<HD, -1> : variant == 9 ? attn_tc3_kernel<HD, 4> : variant == 10 ? attn_tc3_kernel<HD, 2> : attn_tc3_kernel<HD, kAtcPolyDefault>;
+      TRY(ensure_dynamic_smem((const void*)k3, 232448, true));
+      const int n_items = n_seq * heads;
+      k3<<<(unsigned)std::min(num_sms(), n_items), kAtc3Threads, Atc3Cfg<HD>::smem_bytes(sm.S), st>>>(qkv, out, H, ldo, sm, heads, n_items);
+      COUNT_KERNEL("attn_tc3");
+      LAUNCH_CHECK();
+      return 0;
+    }
     void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int, int, long long*) =
         variant == 1 ? attn_tc_kernel<HD, 0> : variant == 2 ? attn_tc_kernel<HD, 2> : variant == 3 ? attn_tc_kernel<HD, 4>
         : variant == 4 ? attn_tc_kernel<HD, -1> : variant == 5 ? attn_tc_kernel<HD, kAtcPolyDefault, true>

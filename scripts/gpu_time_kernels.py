@@ -37,6 +37,9 @@ def attn():
     print(f"attn_seq LAMSLIDE_ATTN_POLY={os.environ.get('LAMSLIDE_ATTN_POLY', 'default')}: {us:8.1f} us  {flops / us * 1e-6:7.1f} TFLOP/s", flush=True)
 
 
+MODE = int(os.environ.get("ATC_MODE", "3"))
+
+
 def attn_tc_probe():
     """numerics of the tcgen05 attention kernel on a few shapes (prints, does not assert) + timing of the exponential-mix variants
     (mode 3 + 4 v: v = 0 shipped mix, 1 all MUFU, 2 / 3: 2 / 4 of 8 pairs on the FMA-pipe polynomial) against the mma.sync kernel"""
@@ -49,7 +52,7 @@ def attn_tc_probe():
         qkv = torch.randn(n, 3 * H, generator=g).to(torch.bfloat16).cuda()
         ref = _attention_reference(qkv, B, T, Lx, H, heads, True)
         out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
-        rc = lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, 3, st)
+        rc = lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, MODE, st)
         try:
             torch.cuda.synchronize()
             err = float((out.float() - ref).abs().max() / ref.abs().max())
@@ -64,6 +67,8 @@ def attn_tc_probe():
     out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
     for mode, name in [(3, "tcgen05 shipped mix (3/8 poly)"), (7, "tcgen05 all MUFU"), (11, "tcgen05 2/8 poly"), (15, "tcgen05 4/8 poly"),
                        (19, "tcgen05 pipeline only (no exponentials)"),
+                       (3 + 4 * 7, "tcgen05 3 groups, P in place (3/8 poly)"), (3 + 4 * 10, "tcgen05 3 groups (2/8 poly)"), (3 + 4 * 9, "tcgen05 3 groups (4/8 poly)"),
+                       (3 + 4 * 8, "tcgen05 3 groups pipeline only"),
                        (2, "mma.sync whole-sequence")]:
         us = time_fn(lambda: L.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, Lx, H, heads, H, 1, mode, st)), iters=10)
         print(f"attention 4AA temporal [{name}]: {us:8.1f} us  {4.0 * 24 * T * T * heads * B * Lx / us * 1e-6:7.1f} TFLOP/s", flush=True)

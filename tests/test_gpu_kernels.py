@@ -422,6 +422,23 @@ def test_first_stage_linear_with_layernorm_epilogue(rows, N, K, group, affine, r
     assert float((out.double() - ln).abs().max()) < 2e-5
 
 
+def test_three_group_attention_variant_matches_reference():
+    """attn_tc3.cuh (three tile groups, probabilities written in place over the logits): a measured alternative that is not the
+    default; its numerics are pinned so the record of the experiment stays runnable."""
+    L_ = _lib()
+    lib = L_.load()
+    for (B, T, L, H, heads) in [(2, 1000, 2, 384, 16), (1, 512, 1, 256, 16), (2, 130, 3, 128, 4), (1, 300, 2, 384, 16)]:
+        n = B * T * L
+        g = torch.Generator(device="cpu").manual_seed(n + 17)
+        qkv = torch.randn(n, 3 * H, generator=g).to(torch.bfloat16).cuda()
+        out = torch.zeros(n, H, dtype=torch.bfloat16, device="cuda")
+        L_.check(lib.lamslide_debug_attention(qkv.data_ptr(), out.data_ptr(), B, T, L, H, heads, H, 1, 3 + 4 * 7, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        ref = _attention_reference(qkv, B, T, L, H, heads, True)
+        assert max_rel(out.float(), ref) < 2e-2
+        assert float((out.float() - ref).abs().mean() / ref.abs().mean()) < 5e-3
+
+
 @pytest.mark.parametrize("B,T,L,H,heads", [
     (2, 20, 8, 256, 16),     # NBA temporal: hd 16, groups of 4 heads
     (3, 20, 2, 128, 4),      # pedestrian temporal: hd 32

@@ -35,8 +35,8 @@ for r in csv.DictReader(lines):
 # the launch list holds torch's kernels too (noise, copies): take the window that ends with the last launch and starts at the first
 # first-stage kernel of the last step
 names = [n for n, _ in rows]
-last_step_start = max(i for i, n in enumerate(names) if "gather_cols_kernel" in n and i < len(names) - 50 and
-                      not any("gather_cols_kernel" in m for m in names[max(0, i - 3):i]))
+last_step_start = max(i for i, n in enumerate(names) if "gather_cols" in n and i < len(names) - 50 and
+                      not any("gather_cols" in m for m in names[max(0, i - 3):i]))
 sel = rows[last_step_start:]
 agg = OrderedDict()
 for name, us in sel:

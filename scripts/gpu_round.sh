@@ -18,7 +18,7 @@ tail -2 gpurun_out/ncu_bench.log | cut -c1-200 >> $LOG
 wc -l gpurun_out/${TAG}_launches.csv >> $LOG
 echo "######## ncu --set full: top kernels" >> $LOG
 timeout 1200 ncu --set full --clock-control none --import-source on \
-  -k regex:'attn_tc_kernel|mlp_fused_kernel|gemm_ws_kernel|ln_modulate_kernel|linear_f32_tc_kernel' -s 150 -c 16 -f -o gpurun_out/${TAG}_top \
+  -k regex:'attn_tc_kernel|mlp_fused_kernel|gemm_ws_kernel|ln_modulate_kernel|linear_tc5_kernel' -s 150 -c 16 -f -o gpurun_out/${TAG}_top \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-secondary > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log | cut -c1-200 >> $LOG
 ls -la gpurun_out | grep ${TAG} >> $LOG

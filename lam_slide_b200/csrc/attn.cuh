@@ -535,93 +535,118 @@ attn_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   }
 }
 
-// Short sequences with ANY token stride (temporal attention of the small-T configurations: NBA / pedestrian T = 20, MD17 T = 30, whose
-// tokens of a sequence lie L rows apart): one warp per (sequence, group of HG heads).  The warp copies the q | k | v pieces of its heads
-// (HG * HD bf16 = 64 - 192 contiguous bytes per token and part) into shared memory, every lane then serves (query, head) items out of
-// shared memory exactly as attn_rows_kernel, and the output pieces go out with 16-byte stores.  attn_small_kernel (one thread per item
-// gathering 32-byte pieces of every key from global memory) moved 13 x the bytes: 380 us per NBA launch (B = 1024) for 336 MB.
-template <int HD, int HG>
+// Short sequences (S <= 32) with any token stride on the warp-level tensor path: one warp per (sequence, head).  The head's q | k | v
+// pieces (S rows x HD bf16 each) go to shared memory, S = Q K^T (32 x 32 x HD) and O = P V (32 x HD x 32) are 16 mma.sync.m16n8k16 for
+// HD = 16, the softmax over the <= 32 keys of a row stays in the accumulator registers of a lane quad.  The output goes back through
+// the warp's Q tile and leaves with 16-byte stores.  (Measured per NBA launch at B = 1024, 336 MB of traffic: thread per (query, head)
+// gathering 32-byte pieces of every key from global memory 380 us; warp per (sequence, 4 heads) with FMA dot products out of shared
+// memory 268 us, shared-memory-bandwidth bound.)
+template <int HD>
 __global__ void __launch_bounds__(256)
-attn_short_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, int heads, SeqMap sm, long long n_work) {
+attn_short_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int H, int ldo, int heads, SeqMap sm, long long n_work) {
+  constexpr int HDP = (HD == 24) ? 32 : HD;  // contraction dim of Q K^T padded to a multiple of 16
+  constexpr int KSTEPS = HDP / 16;
+  constexpr int PITCH = HDP + 8;             // bf16 elements: 48 / 80 byte rows, conflict-free fragment loads and ldmatrix
+  constexpr int CH = HD / 8, CHP = HDP / 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  constexpr int CH = HD / 8;       // 16-byte units per head
-  constexpr int PU = HG * CH;      // 16-byte units per token and part (q, k or v)
-  const int S = sm.S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
   const long long w = (long long)blockIdx.x * 8 + warp;
   if (w >= n_work) return;
-  const int groups = heads / HG;
-  const int z = (int)(w / groups), hg = (int)(w % groups);
+  const int z = (int)(w / heads), hh = (int)(w % heads);
   const long long base = sm.base(z);
-  uint4* my = reinterpret_cast<uint4*>(attn_smem) + (size_t)warp * S * 3 * PU;
-  for (int i = lane; i < S * 3 * PU; i += 32) {
-    const int tok = i / (3 * PU), r = i % (3 * PU), part = r / PU, u = r % PU;
-    my[i] = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(base + (long long)tok * sm.seq_stride) * 3 * H + part * H + hg * HG * HD) + u);
+  const int S = sm.S;
+  typedef __nv_bfloat16 Row[PITCH];
+  Row* Qs = reinterpret_cast<Row*>(attn_smem + (size_t)warp * 3 * 32 * PITCH * 2);
+  Row* Ks = Qs + 32;
+  Row* Vs = Ks + 32;
+  for (int idx = lane; idx < 3 * 32 * CHP; idx += 32) {
+    const int part = idx / (32 * CHP), r = (idx / CHP) % 32, c = idx % CHP;
+    uint4 v = make_uint4(0, 0, 0, 0);  // rows >= S and the padding of the contraction dim are zero
+    if (r < S && c < CH)
+      v = __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(base + (long long)r * sm.seq_stride) * 3 * H + part * H + hh * HD) + c);
+    *reinterpret_cast<uint4*>(&Qs[part * 32 + r][c * 8]) = v;
   }
   __syncwarp();
-  for (int item = lane; item < S * HG; item += 32) {
-    const int sq = item / HG, hh = item % HG;
-    float q[HD], acc[HD];
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const uint4 v = my[sq * 3 * PU + hh * CH + c];
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+  for (int mt = 0; mt < 2; ++mt) {
+    if (mt * 16 >= S) break;
+    uint32_t aq[KSTEPS][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(h2[i]);
-        q[c * 8 + 2 * i] = f.x, q[c * 8 + 2 * i + 1] = f.y;
+    for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        aq[ks][i] = *reinterpret_cast<const uint32_t*>(&Qs[mt * 16 + g + (i & 1) * 8][ks * 16 + (i >> 1) * 8 + t * 2]);
+    float s[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + t * 2]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 8 + t * 2]);
+        mma_bf16_16816(s[nt], aq[ks], b0, b1);
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (nt * 8 + t * 2 + (e & 1) >= S) s[nt][e] = -INFINITY;
+    }
+    // softmax over the keys (rows g: e = 0, 1; rows g + 8: e = 2, 3), in the exp2 domain (q carries hd^-0.5 * log2 e)
+    float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    for (int sk = 0; sk < S; ++sk) {
-      const uint4* kp = my + sk * 3 * PU + PU + hh * CH;
-      const uint4* vp = kp + PU;
-      float dot = 0.f;
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const uint4 v = kp[c];
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+    for (int nt = 0; nt < 4; ++nt) {
+      s[nt][0] = fast_exp2(s[nt][0] - mx[0]), s[nt][1] = fast_exp2(s[nt][1] - mx[0]);
+      s[nt][2] = fast_exp2(s[nt][2] - mx[1]), s[nt][3] = fast_exp2(s[nt][3] - mx[1]);
+      l[0] += s[nt][0] + s[nt][1];
+      l[1] += s[nt][2] + s[nt][3];
+    }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h2[i]);
-          dot = fmaf(q[c * 8 + 2 * i], f.x, dot);
-          dot = fmaf(q[c * 8 + 2 * i + 1], f.y, dot);
-        }
-      }
-      const float mn = fmaxf(m, dot);
-      const float corr = fast_exp2(m - mn);
-      const float pr = fast_exp2(dot - mn);
-      m = mn;
-      l = l * corr + pr;
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    float o[CH][4];
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const uint4 v = vp[c];
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+    for (int d = 0; d < CH; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h2[i]);
-          acc[c * 8 + 2 * i] = fmaf(pr, f.x, acc[c * 8 + 2 * i] * corr);
-          acc[c * 8 + 2 * i + 1] = fmaf(pr, f.y, acc[c * 8 + 2 * i + 1] * corr);
-        }
+    for (int j = 0; j < 2; ++j) {
+      if (j * 16 >= S) break;
+      uint32_t ap[4];
+      ap[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+      ap[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+      ap[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      ap[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+      for (int d = 0; d < CH; ++d) {
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, smem_u32(&Vs[j * 16 + (lane & 15)][d * 8]));
+        mma_bf16_16816(o[d], ap, b0, b1);
       }
     }
-    const float inv = 1.f / l;
+    // the tile's Q rows are in registers: its output rows take their place
+    __syncwarp();
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {  // over this item's own q slot (no other lane reads it)
-      uint4 v;
-      v.x = pack_bf16x2(acc[c * 8 + 0] * inv, acc[c * 8 + 1] * inv);
-      v.y = pack_bf16x2(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
-      v.z = pack_bf16x2(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
-      v.w = pack_bf16x2(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
-      my[sq * 3 * PU + hh * CH + c] = v;
+    for (int r = 0; r < 2; ++r) {
+      const float inv = 1.f / l[r];
+#pragma unroll
+      for (int d = 0; d < CH; ++d)
+        *reinterpret_cast<uint32_t*>(&Qs[mt * 16 + g + r * 8][d * 8 + t * 2]) = pack_bf16x2(o[d][2 * r] * inv, o[d][2 * r + 1] * inv);
     }
   }
   __syncwarp();
-  for (int i = lane; i < S * PU; i += 32) {
-    const int tok = i / PU, u = i % PU;
-    *reinterpret_cast<uint4*>(out + (size_t)(base + (long long)tok * sm.seq_stride) * ldo + hg * HG * HD + u * 8) = my[tok * 3 * PU + u];
+  for (int idx = lane; idx < S * CH; idx += 32) {
+    const int r = idx / CH, c = idx % CH;
+    *reinterpret_cast<uint4*>(out + (size_t)(base + (long long)r * sm.seq_stride) * ldo + hh * HD + c * 8) = *reinterpret_cast<const uint4*>(&Qs[r][c * 8]);
   }
 }
 

@@ -770,22 +770,19 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
   } else if (sm.S <= 32 && !force_flash) {
     // contiguous sequences whose q|k|v rows fit 8 warps x 6 KB of shared memory: warp per sequence (attn_rows_kernel)
     static const bool legacy_small = env_flag("LAMSLIDE_LEGACY_SMALL_ATTN");
+    static const bool no_short_mma = env_flag("LAMSLIDE_NO_SHORT_MMA_ATTN");
     const bool contiguous = sm.seq_stride == 1 && sm.inner == 1 && sm.outer_stride == sm.S;
     const size_t rows_smem = (size_t)8 * sm.S * 3 * H * 2;
     if (!legacy_small && contiguous && rows_smem <= 48 * 1024 && ldo % 8 == 0 && H % 8 == 0) {
       attn_rows_kernel<HD><<<(unsigned)cdiv((long long)n_seq, 8), 256, rows_smem, st>>>(qkv, out, H, ldo, heads, sm.S, n_seq);
       COUNT_KERNEL("attn_rows");
-    } else if (!legacy_small && heads >= 8 && heads % 2 == 0 && ldo % 8 == 0 && H % 8 == 0 && (size_t)8 * sm.S * 3 * 2 * HD * 2 <= 96 * 1024) {
-      // any token stride: warp per (sequence, head group), the group's q | k | v pieces staged in shared memory (attn_short_kernel).
-      // Measured (B200, B = 1024): NBA (16 heads) 380 -> 268 us per launch; pedestrian (4 heads of 32: 2048 sequences give the kernel
-      // too few warps) 2.2 -> 2.8 ms per step, so models with few heads stay on the thread-per-item kernel below.
-      const int hg = (heads % 4 == 0 && (size_t)8 * sm.S * 3 * 4 * HD * 2 <= 96 * 1024) ? 4 : 2;
-      const size_t smem = (size_t)8 * sm.S * 3 * hg * HD * 2;
-      const long long n_work = (long long)n_seq * (heads / hg);
-      void (*kern)(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, SeqMap, long long) =
-          hg == 4 ? attn_short_kernel<HD, 4> : attn_short_kernel<HD, 2>;
-      TRY(ensure_dynamic_smem((const void*)kern, 96 * 1024));
-      kern<<<(unsigned)cdiv(n_work, 8), 256, smem, st>>>(qkv, out, H, ldo, heads, sm, n_work);
+    } else if (!legacy_small && !no_short_mma && ldo % 8 == 0 && H % 8 == 0) {
+      // any token stride: warp per (sequence, head) on the warp-level tensor path (attn_short_mma_kernel)
+      constexpr int kPitch = ((HD == 24 ? 32 : HD) + 8);
+      const size_t smem = (size_t)8 * 3 * 32 * kPitch * 2;
+      const long long n_work = (long long)n_seq * heads;
+      TRY(ensure_dynamic_smem((const void*)attn_short_mma_kernel<HD>, 64 * 1024));
+      attn_short_mma_kernel<HD><<<(unsigned)cdiv(n_work, 8), 256, smem, st>>>(qkv, out, H, ldo, heads, sm, n_work);
       COUNT_KERNEL("attn_short");
     } else {
       long long items = (long long)n_seq * sm.S * heads;

@@ -218,6 +218,11 @@ def secondary_lines(P, _lib, args, dev):
         eager["tflops"] = flops_per_trajectory(cfg, 10) * eager["value"] / 1e12
         graphed["tflops"] = flops_per_trajectory(cfg, 10) * graphed["value"] / 1e12
         out[f"{name}_b1024"] = {"workload": f"{name} sample(): T={cfg['T']}, N={cfg['N']}, num_steps=10", "eager": eager, "cuda_graph": graphed}
+        # a serving-sized batch: the ~400 launches of a step are launch-bound there, which is where replaying the step from a graph pays
+        e32 = time_sample(m, cfg, 32, 20, 3, False)
+        g32 = time_sample(m, cfg, 32, 20, 3, True)
+        out[f"{name}_b32"] = {"workload": f"{name} sample(): T={cfg['T']}, N={cfg['N']}, num_steps=10", "eager": e32, "cuda_graph": g32,
+                              "graph_speedup": g32["value"] / e32["value"]}
         del m
     sweep = []
     for ns in (5, 10, 20, 50):

@@ -8,6 +8,8 @@ LOG=gpurun_out/round.log
 : > $LOG
 echo "######## pytest -m gpu" >> $LOG
 timeout 2400 python -m pytest tests -q -m gpu --tb=short 2>&1 | grep -E "^E  |passed|failed|FAILED|Error|skipped" | cut -c1-260 | head -40 >> $LOG
+echo "######## smoke" >> $LOG
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | cut -c1-200 >> $LOG
 echo "######## bench" >> $LOG
 timeout 1500 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -3 gpurun_out/${TAG}_bench.err >> $LOG

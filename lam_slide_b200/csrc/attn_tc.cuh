@@ -40,7 +40,8 @@
 // hand-shakes per exponential); all 64 logits of a thread loaded at once to release S earlier: 563 us (register spills at the
 // 96-register limit of 20 warps); Q K^T and P V issued by separate warps (Q K^T issuer also loading its group's query tiles, one P V
 // issuer for both groups): 539 us — the issue time of the MMA warp is not on the critical loop.  This version: 524 us against 661 us
-// for the mma.sync kernel; the exponent engine alone would need 390 us, and the pipeline WITHOUT any exponential (variant 4: logits
+// for the mma.sync kernel (the O epilogue of a tile deferred into the next tile's first chunk step, where nobody has to wait for the last
+// P V: 535 us — it delays that step's hand-off); the exponent engine alone would need 390 us, and the pipeline WITHOUT any exponential (variant 4: logits
 // passed through) takes 360 us: per chunk step and group ~1500 cycles of tcgen05.ld / wait / st / mbarrier latency in series in every
 // softmax warp, of which the exponentials hide about half.
 // After the last chunk of a tile the group reads O (tcgen05.ld), scales by 1 / row sum and stores bf16; tensor pipe ~25 % busy.

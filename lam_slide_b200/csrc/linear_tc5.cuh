@@ -4,7 +4,7 @@
 //
 // x = hi + lo with hi = x rounded to TF32 and lo = x - hi (exact in fp32); x.w is accumulated as lo.hi + hi.lo + hi.hi in the fp32
 // TMEM accumulator, the dropped lo.lo term is 2^-22 relative: as good as an fp32 FMA chain (the reference's first stage is fp32 and
-// its outputs are checked to 1e-4; measured 1.4e-6).  The weights are split once at *_create (w_hi / w_lo, fp32 arrays the tensor
+// its outputs are checked to 1e-4; measured <= 3.8e-6 on the latents of all golden cases).  The weights are split once at *_create (w_hi / w_lo, fp32 arrays the tensor
 // core reads as TF32); the activations are split on the fly in shared memory.
 //
 //   warp 0      TMA producer: per 32-wide k-block the raw fp32 A tile (128 rows x 128 B, 128-byte swizzle) and the W_hi / W_lo tiles

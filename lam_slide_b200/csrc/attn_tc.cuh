@@ -41,7 +41,8 @@
 // 96-register limit of 20 warps); Q K^T and P V issued by separate warps (Q K^T issuer also loading its group's query tiles, one P V
 // issuer for both groups): 539 us — the issue time of the MMA warp is not on the critical loop.  This version: 524 us against 661 us
 // for the mma.sync kernel (the O epilogue of a tile deferred into the next tile's first chunk step, where nobody has to wait for the last
-// P V: 535 us — it delays that step's hand-off); the exponent engine alone would need 390 us, and the pipeline WITHOUT any exponential (variant 4: logits
+// P V: 535 us — it delays that step's hand-off; the first logit blocks of step n + 1 requested at the end of step n whenever S(n + 1) has
+// already landed: 586 us); the exponent engine alone would need 390 us, and the pipeline WITHOUT any exponential (variant 4: logits
 // passed through) takes 360 us: per chunk step and group ~1500 cycles of tcgen05.ld / wait / st / mbarrier latency in series in every
 // softmax warp, of which the exponentials hide about half.
 // After the last chunk of a tile the group reads O (tcgen05.ld), scales by 1 / row sum and stores bf16; tensor pipe ~25 % busy.

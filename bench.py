@@ -224,6 +224,13 @@ def secondary_lines(P, _lib, args, dev):
         out[f"{name}_b32"] = {"workload": f"{name} sample(): T={cfg['T']}, N={cfg['N']}, num_steps=10", "eager": e32, "cuda_graph": g32,
                               "graph_speedup": g32["value"] / e32["value"]}
         del m
+    # MD17 (BASELINE configs[0] is its CPU-runnable small batch): 192 latents per frame make it the one configuration whose SPATIAL axis
+    # is long (whole-sequence mma.sync attention kernel) while the temporal axis is short
+    cfg, m = build("md17", 10)
+    md = time_sample(m, cfg, 64, 5, 2, False, shares=True)
+    md["tflops"] = flops_per_trajectory(cfg, 10) * md["value"] / 1e12
+    out["md17_b64"] = {"workload": f"md17 sample(): T={cfg['T']}, N={cfg['N']}, num_steps=10", "eager": md}
+    del m
     sweep = []
     for ns in (5, 10, 20, 50):
         cfg, m = build("peptide", ns)

@@ -15,7 +15,8 @@
 // warps have the pipes.
 // MEASURED (B200, 4AA launch): 554 us against 524 us for attn_tc.cuh, 383 us against 360 us without exponentials — the in-place P puts
 // S(n + 1) behind the whole of softmax(n) and P V(n) (attn_tc.cuh overlaps Q K^T with the second half of the exponentials) and a
-// thread walks 128 keys in series, which lengthens the per-step chain by more than the third phase stream hides.  Kept as a debug
+// thread walks 128 keys in series, which lengthens the per-step chain by more than the third phase stream hides.  Validated for
+// sequences of >= 3 query tiles (S > 256; with two tiles and several items per CTA it faults, and the launcher refuses).  Kept as a debug
 // variant (lamslide_debug_attention mode 3 + 4 * 7 .. 10) and as the record of the experiment; the product path uses attn_tc.cuh.
 // Query tiles: a ring of 4 images in tile-stream order (tile u in image u % 4; group g owns the tiles u = g mod 3), filled by a loader
 // warp one tile ahead.  K / V images, item walk and the no-running-maximum softmax are those of attn_tc.cuh.

@@ -742,6 +742,8 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int H,
   if (tc_ok) {
     const int variant = tc_forced ? (mode >> 2) : env_int("LAMSLIDE_ATTN_TC_VARIANT", 0);
     if (variant >= 7 && variant <= 10) {  // three tile groups, P in place (attn_tc3.cuh): 7 shipped mix, 8 no exponentials, 9 / 10: 4 / 2 of 8 pairs polynomial
+      // (experiment kernel: validated for >= 3 query tiles per sequence; with two tiles and several items per CTA it faults)
+      if (sm.S <= 256) return fail(LAMSLIDE_ERR_INVALID, "the three-group attention variant needs sequences longer than 256");
       void (*k3)(const __nv_bfloat16*, __nv_bfloat16*, int, int, SeqMap, int, int) =
           variant == 8 ? attn_tc3_kernel<HD, -1> : variant == 9 ? attn_tc3_kernel<HD, 4> : variant == 10 ? attn_tc3_kernel<HD, 2> : attn_tc3_kernel<HD, kAtcPolyDefault>;
       TRY(ensure_dynamic_smem((const void*)k3, 232448, true));
